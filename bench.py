@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Benchmark of the scan hot path: nt·models scanned per second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mb M]
+
+Workload = BASELINE.json configs[2]: a synthetic random chromosome of M Mb (default 10) per GPU,
+windows 150/75, all four shipped models, stand-in bpp matrices (rmdetect_b200/synth.py; ViennaRNA
+is external to the path and its time is not part of the metric; generation is reported apart).
+One step = one full scan of the chromosome: enumeration + gate + scoring + E-values + ordering +
+duplicate removal + download of the hit list.
+
+  value  inputs (2-bit sequence, bpp lists) resident in HBM before the timed region
+  e2e    the same scan through the C ABI call with HOST buffers (rmd_scan): H2D of sequence and bpp
+         lists and D2H of the hits inside the timed region
+N > 1: one process per GPU (torchrun), every rank scans its own chromosome chunk (weak scaling),
+hit counts are all-gathered over NCCL, time = max over ranks.
+`--impl reference` times the CPU oracle port (oracle/, the reference's algorithm restated in C,
+OpenMP over windows on all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261019
+WIN_LEN, WIN_STEP = 150, 75
+MODEL_FILES = ["cl_1", "tga_1", "gb_1", "kt_1"]         # the order os.listdir gave the reference in the build container
+DATA = os.path.join(ROOT, "tests", "golden", "ref_data", "models")
+LN_UNKNOWN, LN_CUTOFF, MIN_BPP = math.log(1e-4), math.log(0.1), 0.001
+
+
+def load_models():
+    from rmdetect_b200.evalues import parse_evalues
+    from rmdetect_b200.modelfile import parse_model
+    models = [parse_model(os.path.join(DATA, n + ".model")) for n in MODEL_FILES]
+    evs = [parse_evalues(os.path.join(DATA, n + ".evalues")) for n in MODEL_FILES]
+    return models, evs
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([t.strip() for t in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(models, n_threads, target_s):
+    """Oracle port on the host cores over a bounded sample: a prefix of the chromosome sized, from a pilot
+    run, to take about `target_s` seconds.  Returns (nt·model/s, seconds, windows, tries)."""
+    from oracle import pyoracle
+    from rmdetect_b200.synth import synth_sequence
+
+    def run(nwin):
+        seq = synth_sequence(nwin * WIN_STEP + WIN_LEN, SEED)
+        t0 = time.perf_counter()
+        _, tries = pyoracle.bench_scan(models, seq, WIN_LEN, WIN_STEP, 0, nwin, SEED, n_threads, MIN_BPP,
+                                       LN_UNKNOWN, LN_CUTOFF)
+        return time.perf_counter() - t0, tries
+
+    pilot = 64 * n_threads
+    run(pilot)                                                                   # warm the threads
+    dt, _ = run(pilot)
+    nwin = int(max(pilot, min(133333, pilot * target_s / max(dt, 1e-3))))
+    dt, tries = run(nwin)
+    return nwin * WIN_STEP * len(models) / dt, dt, nwin, tries
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    models, _ = load_models()
+    cores = os.cpu_count() or 1
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, dt, sample, tries = cpu_baseline(models, cores, 4.0 if k >= args.warmup else 1.0)
+        if k >= args.warmup:
+            vals.append((v, dt))
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "nt·models scanned/sec", "value": value, "unit": "nt·model/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config3: synthetic %d Mb random chromosome, win 150/75, models CL,TGA,GB,KT, "
+                               "synthetic bpp (gate on)" % args.mb,
+                   "sampled": "first %d windows (%d nt) per step" % (sample, sample * WIN_STEP)},
+        "cpu_baseline": {"value": value, "unit": "nt·model/s", "cores": cores, "kind": "port",
+                         "sample": "oracle/rmd_oracle.c (C restatement of the reference's Python scan), OpenMP over "
+                                   "%d windows incl. its own synthetic-bpp generation" % sample},
+        "e2e": {"value": value, "unit": "nt·model/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from rmdetect_b200 import _native
+    from rmdetect_b200.gcx import gc_table
+    from rmdetect_b200.scanner import ScanEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    models, evs = load_models()
+    eng = ScanEngine(models, evs, LN_UNKNOWN, device=local)
+    ctx = eng.ctx
+    n = args.mb * 1_000_000
+    first = rank * n                                            # every rank scans its own chunk of the stream
+    neutral = gc_table({b: math.log(0.25) for b in "ACGU"})
+    n_win, n_bpp, ms_gen = ctx.synth_job(n, first, SEED, SEED, WIN_LEN, WIN_STEP, MIN_BPP, LN_CUTOFF, neutral)
+    counts = ctx.gc_counts(1)[0]                                # K2: letter counts on the device, logs on the host
+    gc = {b: math.log(float(counts[k]) / n) for k, b in enumerate("ACGU")}
+    cls = []
+    for ev in evs:
+        ev.select_gc(gc)
+        cls.append(ev.selected)
+    ctx.set_gc(gc_table(gc).reshape(1, -1), np.array([cls], dtype=np.int32))
+    units = n * len(models)
+
+    # ---- device-resident scan ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.scan_resident(0, n_win)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = scan_ms = post_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        r = ctx.scan_resident(0, n_win)
+        dev_ms += r["ms_total"]; scan_ms += r["ms_scan"]; post_ms += r["ms_post"]; launches += r["n_launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.summary()
+    n_hits, n_raw, tries = len(r["hits"]), r["n_raw"], r["tries"]
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------
+    off, bi, bj, bp = ctx.download_job(n_win, n_bpp, pinned=True)
+    codes = _native.pinned_array(n, np.uint8)
+    codes[:] = ctx.download_codes(n)
+    job = dict(seq_off=np.array([0, n], dtype=np.int64), codes=codes, gc_log=gc_table(gc).reshape(1, -1),
+               gc_class=np.array([cls], dtype=np.int32), win_len=WIN_LEN, win_step=WIN_STEP, n_win=n_win,
+               bpp_off=off, bpp_i=bi, bpp_j=bj, bpp_p=bp, min_bpp_mean=MIN_BPP, cutoff=LN_CUTOFF)
+    h2d = codes.nbytes + off.nbytes + n_bpp * (2 + 2 + 8) + 16 * 8 + 4 * 4
+    for _ in range(max(1, args.warmup // 2)):
+        e = ctx.scan(job)
+    barrier()
+    t1 = time.perf_counter()
+    e2e_dev_ms = 0.0
+    for _ in range(args.steps):
+        e = ctx.scan(job)
+        e2e_dev_ms += e["ms_total"]
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    assert e["tries"] == tries and len(e["hits"]) == n_hits
+    d2h = len(e["hits"]) * _native.HIT_DTYPE.itemsize + 2 * n_win * len(models) * 4 + 64
+
+    # ---- reduce over ranks: time = max, work = sum ---------------------------------------------------
+    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([n_hits, n_raw, tries[0], tries[1]], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(gathered, cnt)                      # the only collective: small per-rank hit counts
+        cnt = torch.stack(gathered).sum(0)
+    wall, e2e_wall, dev_ms, e2e_dev_ms = t.tolist()
+    total_units = units * world
+    value = total_units * args.steps / wall
+    e2e_value = total_units * args.steps / e2e_wall
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        # algorithmic bytes of one scan-kernel launch: 2-bit letters per window (38 B + offsets), the bpp lists
+        # (12 B per entry + 8 B offset per window), hit records out (32 B) and the two per-group counters
+        algo = n_win * (40 + 8 + 16) + n_bpp * 12 + n_raw * 32 + n_win * len(models) * 8
+        ms_kernel = scan_ms / args.steps
+        achieved = algo / (ms_kernel * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        cpu_val, cpu_dt, cpu_win, _ = cpu_baseline(models, cores, 15.0)
+        line = {
+            "metric": "nt·models scanned/sec", "value": value, "unit": "nt·model/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config3: synthetic %d Mb random chromosome per GPU, win 150/75, models CL,TGA,GB,KT, "
+                                   "synthetic bpp (gate on)" % args.mb,
+                       "windows_per_gpu": n_win, "bpp_entries_per_gpu": n_bpp, "placements_per_step": int(cnt[2]),
+                       "gate_passes_per_step": int(cnt[3]), "hits_before_dedupe": int(cnt[1]), "hits": int(cnt[0]),
+                       "l2": "inputs larger than L2 (%.0f MB of bpp lists per step)" % (n_bpp * 12 / 1e6),
+                       "timing": "wall clock around K synchronous steps bracketed by barrier+synchronize, max over ranks; "
+                                 "device_ms_per_step is the CUDA-event time of the same steps",
+                       "device_ms_per_step": dev_ms / args.steps, "scan_kernel_ms": ms_kernel,
+                       "post_kernels_ms": post_ms / args.steps, "bpp_generation_ms": ms_gen},
+            "e2e": {"value": e2e_value, "unit": "nt·model/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_wall / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
+                    "api": "rmd_scan (C ABI) on pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "scan_fast_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(algo),
+                         "note": "table-lookup / fp64-compare work: issue-bound, not HBM-bound (see DESIGN.md)"},
+            "cpu_baseline": {"value": cpu_val, "unit": "nt·model/s", "cores": cores, "kind": "port",
+                             "sample": "first %d windows (%d nt) of the same chromosome, oracle/rmd_oracle.c with "
+                                       "OpenMP on all cores, %.1f s" % (cpu_win, cpu_win * WIN_STEP, cpu_dt)},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mb", type=int, default=10, help="chromosome length per GPU in Mb")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

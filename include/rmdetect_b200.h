@@ -1,0 +1,194 @@
+/*
+ * rmdetect_b200.h — C ABI of the B200 scan path for RMDetect module models.
+ *
+ * Plain C, plain pointers and sizes; no torch or CUDA types cross this boundary.
+ * Every entry point returns 0 on success or a negative RMD_E_* code; the text of
+ * the last failure is available from rmd_last_error().  There is no CPU path
+ * behind these calls: without a usable CUDA device rmd_create() fails.
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * reference root; the reference is pure Python, so "binding" means the call a
+ * maintainer would redirect — see INTEGRATION.md for the ctypes stubs):
+ *
+ *   rmd_set_models      lib/model.py:13-53,148-209 + lib/node.py:38-117  (model tables, built by
+ *                       the host flattener rmdetect_b200/modelflat.py and copied to the device)
+ *   rmd_set_evalues     lib/evalues.py:38-80 table + :25-36 lookup
+ *   rmd_upload          lib/scanner.py:73-75 (GC over the whole sequence is supplied by the host
+ *                       or by rmd_gc_counts), lib/bpprobs.py:6-15 (matrix store)
+ *   rmd_gc_counts       lib/gcx.py:4-13 (letter histogram; the logs are taken on the host)
+ *   rmd_scan_resident   lib/scanner.py:118-159 (search: odometer, gate, eval, hit creation),
+ *                       :161-193 (pointer_inc), :195-214 (__get_bpp_mean), :216-244
+ *                       (__filter_duplicates), lib/node.py:153-277 (eval / get_solution),
+ *                       lib/candidates.py:360-366 (score, E-value), :508-514 (absolute positions)
+ *   rmd_scan            the same with host buffers: upload + scan + result download
+ *   rmd_eval            lib/node.py:176-277 called directly (rmcalibrate.py:279-281 style)
+ *   rmd_calibrate       rmcalibrate.py:35-62,265-295 (sample scoring into weighted histograms)
+ *   rmd_synth_*         no reference counterpart: synthetic genome / stand-in bpp generators,
+ *                       bit-identical twins of rmdetect_b200/synth.py, for benchmarks
+ */
+#ifndef RMDETECT_B200_H
+#define RMDETECT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMD_OK 0
+#define RMD_E_INVALID (-1)   /* bad argument */
+#define RMD_E_CUDA (-2)      /* CUDA runtime failure (text in rmd_last_error) */
+#define RMD_E_NOMEM (-3)     /* host or device allocation failed */
+#define RMD_E_STATE (-4)     /* call order: models / upload missing */
+#define RMD_E_LIMIT (-5)     /* a model or input exceeds a compiled limit */
+
+#define RMD_MAX_MODELS 16
+#define RMD_N_CODES 16       /* letter codes: 0-3 ACGU, 4 gap, 5..15 other letters of a sequence */
+#define RMD_NSYM 6           /* CPT alphabet: ACGU, gap, other */
+#define RMD_MAX_GATE_PAIRS 256
+#define RMD_MAX_GATE_CFGS 64
+#define RMD_MAX_FIRST_PAIRS 16
+#define RMD_MAX_BRANCH_DEPTH 8
+#define RMD_FAST_WINDOW 160  /* windows up to this length take the shared-memory kernel */
+
+typedef struct rmd_ctx rmd_ctx;
+
+/* search-tree node, DFS preorder (rmdetect_b200/modelflat.py: TREE_DTYPE) */
+typedef struct rmd_tree_node {
+    int8_t chain, oft;              /* oft < 0: gap at this position in this configuration */
+    int8_t par_chain[2], par_oft[2];/* parents on the path; par_oft < 0: the parent is a gap */
+    uint8_t flags;                  /* RMD_F_* */
+    uint8_t bdepth;                 /* save slot (F_SAVE) / restore slot + 1 (F_RESTORE) */
+    uint16_t leaf;                  /* gap configuration id (leaf and distance-check nodes) */
+    uint16_t skip;                  /* index of the first node after this subtree */
+    uint16_t cpt_row;               /* first CPT row of the model node */
+    uint8_t npar, pad_;
+} rmd_tree_node;
+#define RMD_F_LEAF 1
+#define RMD_F_CHECK_DIST 2
+#define RMD_F_SAVE 4
+#define RMD_F_RESTORE 8
+
+typedef struct rmd_gate_pair { int8_t c1, o1, c2, o2; } rmd_gate_pair;
+
+typedef struct rmd_model_desc {
+    int32_t chain_len[2];
+    int32_t symmetric;
+    int32_t n_tree, n_leaves, n_cpt_rows;
+    int32_t n_gate_cfg, n_gate_pairs, n_first;
+    int32_t brute_candidates;           /* 1: every placement is a gate candidate */
+    const rmd_tree_node *tree;          /* [n_tree] */
+    const int32_t *leaf_dist;           /* [n_leaves][2] */
+    const double *cpt;                  /* [n_cpt_rows][6], +inf marks a GC row */
+    const rmd_gate_pair *gate_pairs;    /* [n_gate_pairs] MUST pairs, configurations concatenated */
+    const int32_t *gate_cfg;            /* [n_gate_cfg + 1] */
+    const int8_t *first_pairs;          /* [n_first][2] (offset on chain 0, offset on chain 1) */
+    const int8_t *leaf_offsets;         /* [n_leaves][chain_len[0] + chain_len[1]] offset within its chain, -1: gap */
+} rmd_model_desc;
+
+/* one scan job, host side */
+typedef struct rmd_scan_input {
+    int32_t n_seq;
+    const int64_t *seq_off;     /* [n_seq + 1] letter offsets into codes */
+    const uint8_t *codes;       /* one code per letter */
+    const double *gc_log;       /* [n_seq][16] log frequency per code (slot 4: log 0.25) */
+    const int32_t *gc_class;    /* [n_seq][n_models] selected E-value class, -1: none */
+    int32_t win_len, win_step;  /* either 0: each sequence is one window */
+    int64_t n_win;              /* windows of all sequences, sequence-major */
+    const int64_t *bpp_off;     /* [n_win + 1] entry offsets per window */
+    const uint16_t *bpp_i;      /* upper triangle, window-relative, sorted by (i, j) */
+    const uint16_t *bpp_j;
+    const double *bpp_p;
+    double min_bpp_mean;
+    double cutoff;              /* natural log, e.g. log(0.1) */
+} rmd_scan_input;
+
+/* one hit, final order = window, model (as given to rmd_set_models), p0, p1 */
+typedef struct rmd_hit {
+    int64_t window;             /* index into the job's window list */
+    int64_t start;              /* window start within its sequence */
+    int32_t seq;
+    int32_t wlen;
+    int32_t p0, p1;             /* window-relative chain pointers */
+    int16_t model;
+    int16_t leaf;               /* winning gap configuration (index into the model's OFFSETS) */
+    int32_t keep;               /* 0: dropped by the duplicate rule */
+    double prob_model, prob_rand, score, evalue;
+} rmd_hit;
+
+typedef struct rmd_scan_result {
+    int64_t n_hits;             /* after duplicate removal */
+    const rmd_hit *hits;        /* host memory owned by the context, valid until the next scan call */
+    int64_t n_raw;              /* before duplicate removal */
+    int64_t tries[2];           /* tests_all, tests_pairs */
+    const uint32_t *gate_pass;  /* [n_win][n_models] tests_pairs per window and model */
+    const uint32_t *raw_count;  /* [n_win][n_models] hits before duplicate removal */
+    float ms_scan;              /* device time of the scan kernel(s), CUDA events */
+    float ms_post;              /* device time of ordering, scoring and duplicate removal */
+    float ms_h2d, ms_d2h;
+    float ms_total;             /* device time of the whole call, first enqueue to last copy (CUDA events) */
+    int32_t n_launches;         /* kernels launched by this call */
+} rmd_scan_result;
+
+int rmd_create(int device, rmd_ctx **out);
+void rmd_destroy(rmd_ctx *ctx);
+const char *rmd_last_error(rmd_ctx *ctx);        /* ctx may be NULL: error of a failed rmd_create */
+const char *rmd_version(void);
+
+int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_models);
+/* table: [n_class][n_rows] E-values, row k = score bucket k/10; thresholds: [n_rows] smallest double
+   whose round(x, 1) reaches (k+1)/10 (rmdetect_b200/evalues.py: round_thresholds). n_class 0: no table. */
+int rmd_set_evalues(rmd_ctx *ctx, int model, const double *table, int n_class, int n_rows,
+                    const double *thresholds);
+
+/* stage a job on the device (sequence packed to 2 bits per letter, bpp coordinate lists) */
+int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in);
+/* letter histogram of every uploaded sequence: counts[n_seq][16] */
+int rmd_gc_counts(rmd_ctx *ctx, int64_t *counts);
+/* replace GC tables / classes of the resident job (after rmd_gc_counts) */
+int rmd_set_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class);
+/* 1: rmd_scan* also return the hits removed by the duplicate rule (keep = 0, n_hits = n_raw), which the
+   reference shows to its per-window callbacks before lib/scanner.py:53 filters them; default 0 */
+int rmd_set_return_dropped(rmd_ctx *ctx, int enable);
+/* scan windows [w_begin, w_end) of the resident job */
+int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out);
+/* upload + scan of all windows + download, host buffers in, host buffers out */
+int rmd_scan(rmd_ctx *ctx, const rmd_scan_input *in, rmd_scan_result *out);
+
+/* score n placements: sequence k is codes[seq_off[k] .. seq_off[k+1]) with table gc_log[k][16];
+   leaf[k] = -1 when eval fails */
+int rmd_eval(rmd_ctx *ctx, int model, const uint8_t *codes, const int64_t *seq_off, const double *gc_log,
+             const int32_t *p0, const int32_t *p1, int64_t n, double cutoff,
+             int32_t *leaf, double *prob_model, double *prob_rand);
+
+/* calibration: samples[n][L] codes 0..3, class_log[n_class][4] = log(gc_i[letter]) in ACGU order,
+   hist[n_class][n_bins] is accumulated into (+=).  Returns via n_ok the samples whose eval held. */
+int rmd_calibrate(rmd_ctx *ctx, int model, const uint8_t *samples, int64_t n, int32_t L,
+                  const double *class_log, int32_t n_class, double cutoff,
+                  double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel);
+/* same with samples drawn on the device: letter j of sample s = top two bits of
+   mix64(seed + GOLDEN * (s * L + j + 1)), s in [first, first + n) */
+int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64_t first, int64_t n, int32_t L,
+                        const double *class_log, int32_t n_class, double cutoff,
+                        double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel);
+
+/* synthetic job generated on the device: one sequence of n letters (positions first..first+n-1 of
+   the stream keyed by seq_seed), windows per win_len/win_step, stand-in bpp keyed by bpp_seed */
+int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, uint64_t bpp_seed,
+                  int32_t win_len, int32_t win_step, double min_bpp_mean, double cutoff,
+                  const double *gc_log, const int32_t *gc_class, int64_t *n_win, int64_t *n_bpp,
+                  float *ms_generate);
+/* copy the resident job's sequence codes / one window's bpp list back (tests) */
+int rmd_download_codes(rmd_ctx *ctx, uint8_t *codes, int64_t n);
+int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint16_t *j, double *p, int64_t cap, int64_t *n);
+/* the whole resident bpp store: bpp_off[n_win + 1] and, when the pointers are not NULL, the n_bpp entries */
+int rmd_download_job(rmd_ctx *ctx, int64_t *bpp_off, uint16_t *i, uint16_t *j, double *p);
+
+/* pinned host staging for callers that want full PCIe rate */
+void *rmd_host_alloc(int64_t bytes);
+void rmd_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

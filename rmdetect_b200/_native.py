@@ -1,0 +1,330 @@
+"""ctypes binding of librmdetect_b200.so (include/rmdetect_b200.h).
+
+The library is built in-tree by `make -C rmdetect_b200/csrc` (or
+`__graft_entry__.build()`).  If it is missing, or no CUDA device is usable,
+every entry point raises: there is no CPU fallback behind this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .modelflat import PAIR_DTYPE, TREE_DTYPE, FlatModel
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librmdetect_b200.so")
+N_CODES = 16
+FAST_WINDOW = 160
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("chain_len", C.c_int32 * 2), ("symmetric", C.c_int32),
+                ("n_tree", C.c_int32), ("n_leaves", C.c_int32), ("n_cpt_rows", C.c_int32),
+                ("n_gate_cfg", C.c_int32), ("n_gate_pairs", C.c_int32), ("n_first", C.c_int32),
+                ("brute_candidates", C.c_int32),
+                ("tree", C.c_void_p), ("leaf_dist", C.c_void_p), ("cpt", C.c_void_p),
+                ("gate_pairs", C.c_void_p), ("gate_cfg", C.c_void_p), ("first_pairs", C.c_void_p),
+                ("leaf_offsets", C.c_void_p)]
+
+
+class ScanInput(C.Structure):
+    _fields_ = [("n_seq", C.c_int32), ("seq_off", C.c_void_p), ("codes", C.c_void_p),
+                ("gc_log", C.c_void_p), ("gc_class", C.c_void_p),
+                ("win_len", C.c_int32), ("win_step", C.c_int32), ("n_win", C.c_int64),
+                ("bpp_off", C.c_void_p), ("bpp_i", C.c_void_p), ("bpp_j", C.c_void_p), ("bpp_p", C.c_void_p),
+                ("min_bpp_mean", C.c_double), ("cutoff", C.c_double)]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [("n_hits", C.c_int64), ("hits", C.c_void_p), ("n_raw", C.c_int64),
+                ("tries", C.c_int64 * 2), ("gate_pass", C.c_void_p), ("raw_count", C.c_void_p),
+                ("ms_scan", C.c_float), ("ms_post", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_total", C.c_float), ("n_launches", C.c_int32)]
+
+
+HIT_DTYPE = np.dtype([("window", "<i8"), ("start", "<i8"), ("seq", "<i4"), ("wlen", "<i4"),
+                      ("p0", "<i4"), ("p1", "<i4"), ("model", "<i2"), ("leaf", "<i2"), ("keep", "<i4"),
+                      ("prob_model", "<f8"), ("prob_rand", "<f8"), ("score", "<f8"), ("evalue", "<f8")])
+assert HIT_DTYPE.itemsize == 72
+
+EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
+           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_scan_resident", "rmd_scan", "rmd_eval",
+           "rmd_calibrate", "rmd_calibrate_synth", "rmd_synth_job", "rmd_download_codes", "rmd_download_bpp",
+           "rmd_download_job", "rmd_host_alloc", "rmd_host_free"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library and declare signatures.  Raises NativeError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError("%s is missing: build it with `make -C rmdetect_b200/csrc` "
+                          "(python -c 'import __graft_entry__ as g; g.build()')" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.rmd_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.rmd_destroy.argtypes = [vp]
+    L.rmd_destroy.restype = None
+    L.rmd_last_error.argtypes = [vp]
+    L.rmd_last_error.restype = C.c_char_p
+    L.rmd_version.restype = C.c_char_p
+    L.rmd_set_models.argtypes = [vp, C.POINTER(ModelDesc), C.c_int]
+    L.rmd_set_evalues.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp]
+    L.rmd_upload.argtypes = [vp, C.POINTER(ScanInput)]
+    L.rmd_gc_counts.argtypes = [vp, vp]
+    L.rmd_set_gc.argtypes = [vp, vp, vp]
+    L.rmd_set_return_dropped.argtypes = [vp, C.c_int]
+    L.rmd_scan_resident.argtypes = [vp, i64, i64, C.POINTER(ScanResult)]
+    L.rmd_scan.argtypes = [vp, C.POINTER(ScanInput), C.POINTER(ScanResult)]
+    L.rmd_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
+    L.rmd_calibrate.argtypes = [vp, C.c_int, vp, i64, i32, vp, i32, f64, vp, i32,
+                                C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.rmd_calibrate_synth.argtypes = [vp, C.c_int, C.c_uint64, i64, i64, i32, vp, i32, f64, vp, i32,
+                                      C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.rmd_synth_job.argtypes = [vp, i64, i64, C.c_uint64, C.c_uint64, i32, i32, f64, f64, vp, vp,
+                                C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
+    L.rmd_download_codes.argtypes = [vp, vp, i64]
+    L.rmd_download_bpp.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(i64)]
+    L.rmd_download_job.argtypes = [vp, vp, vp, vp, vp]
+    L.rmd_host_alloc.argtypes = [i64]
+    L.rmd_host_alloc.restype = vp
+    L.rmd_host_free.argtypes = [vp]
+    L.rmd_host_free.restype = None
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One GPU context: models, E-value tables, a resident job, scans."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.rmd_create(device, C.byref(h))
+        if rc != 0:
+            raise NativeError("rmd_create(%d): %s" % (device, self.lib.rmd_last_error(None).decode()))
+        self.h = h
+        self.device = device
+        self.n_models = 0
+        self._keep = []          # numpy arrays the library only needs during a call, kept for safety
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rmd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NativeError("%s failed (%d): %s" % (what, rc, self.lib.rmd_last_error(self.h).decode()))
+
+    # -- models ------------------------------------------------------------------------------
+    def set_models(self, flats):
+        descs = (ModelDesc * len(flats))()
+        keep = []
+        for d, fm in zip(descs, flats):
+            assert isinstance(fm, FlatModel)
+            tree = np.ascontiguousarray(fm.tree, dtype=TREE_DTYPE)
+            ld = np.ascontiguousarray(fm.leaf_dist, dtype=np.int32)
+            cpt = np.ascontiguousarray(fm.cpt, dtype=np.float64)
+            gp = np.ascontiguousarray(fm.gate_pairs, dtype=PAIR_DTYPE)
+            gcfg = np.ascontiguousarray(fm.gate_cfg, dtype=np.int32)
+            fp = np.ascontiguousarray(fm.first_pairs, dtype=np.int8)
+            L = fm.chain_len[0] + fm.chain_len[1]
+            lo = np.full((fm.n_leaves, L), -1, dtype=np.int8)
+            for li, cfg in enumerate(fm.leaf_offsets):
+                flat = list(cfg[0]) + list(cfg[1])
+                lo[li] = [-1 if o is None else o for o in flat]
+            keep += [tree, ld, cpt, gp, gcfg, fp, lo]
+            d.chain_len[0], d.chain_len[1] = fm.chain_len
+            d.symmetric = int(fm.symmetric)
+            d.n_tree, d.n_leaves, d.n_cpt_rows = len(tree), fm.n_leaves, cpt.shape[0]
+            d.n_gate_cfg, d.n_gate_pairs, d.n_first = len(gcfg) - 1, len(gp), len(fp)
+            d.brute_candidates = int(fm.brute_candidates)
+            d.tree, d.leaf_dist, d.cpt = tree.ctypes.data, ld.ctypes.data, cpt.ctypes.data
+            d.gate_pairs, d.gate_cfg, d.first_pairs = gp.ctypes.data, gcfg.ctypes.data, fp.ctypes.data
+            d.leaf_offsets = lo.ctypes.data
+        self._check(self.lib.rmd_set_models(self.h, descs, len(flats)), "rmd_set_models")
+        self.n_models = len(flats)
+        del keep
+
+    def set_evalues(self, model, table, thresholds):
+        if table is None or table.size == 0:
+            self._check(self.lib.rmd_set_evalues(self.h, model, None, 0, 0, None), "rmd_set_evalues")
+            return
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        assert thr.shape[0] == table.shape[1]
+        self._check(self.lib.rmd_set_evalues(self.h, model, table.ctypes.data, table.shape[0], table.shape[1],
+                                             thr.ctypes.data), "rmd_set_evalues")
+
+    # -- jobs --------------------------------------------------------------------------------
+    @staticmethod
+    def _scan_input(job):
+        si = ScanInput()
+        si.n_seq = len(job["seq_off"]) - 1
+        si.seq_off, si.codes = _ptr(job["seq_off"]), _ptr(job["codes"])
+        si.gc_log, si.gc_class = _ptr(job["gc_log"]), _ptr(job.get("gc_class"))
+        si.win_len, si.win_step, si.n_win = job["win_len"], job["win_step"], job["n_win"]
+        si.bpp_off, si.bpp_i, si.bpp_j, si.bpp_p = (_ptr(job["bpp_off"]), _ptr(job["bpp_i"]), _ptr(job["bpp_j"]),
+                                                    _ptr(job["bpp_p"]))
+        si.min_bpp_mean, si.cutoff = job["min_bpp_mean"], job["cutoff"]
+        return si
+
+    def upload(self, job):
+        si = self._scan_input(job)
+        self._check(self.lib.rmd_upload(self.h, C.byref(si)), "rmd_upload")
+
+    def _result(self, res, n_win):
+        hits = np.empty(res.n_hits, dtype=HIT_DTYPE)
+        if res.n_hits:
+            C.memmove(hits.ctypes.data, res.hits, res.n_hits * HIT_DTYPE.itemsize)
+        ng = n_win * self.n_models
+        gate = np.empty((n_win, self.n_models), dtype=np.uint32)
+        raw = np.empty((n_win, self.n_models), dtype=np.uint32)
+        if ng:
+            C.memmove(gate.ctypes.data, res.gate_pass, ng * 4)
+            C.memmove(raw.ctypes.data, res.raw_count, ng * 4)
+        return dict(hits=hits, tries=[res.tries[0], res.tries[1]], gate_pass=gate, raw_count=raw, n_raw=res.n_raw,
+                    ms_scan=res.ms_scan, ms_post=res.ms_post, ms_h2d=res.ms_h2d, ms_d2h=res.ms_d2h,
+                    ms_total=res.ms_total, n_launches=res.n_launches)
+
+    def scan_resident(self, w_begin, w_end):
+        res = ScanResult()
+        self._check(self.lib.rmd_scan_resident(self.h, w_begin, w_end, C.byref(res)), "rmd_scan_resident")
+        return self._result(res, w_end - w_begin)
+
+    def scan(self, job):
+        si = self._scan_input(job)
+        res = ScanResult()
+        self._check(self.lib.rmd_scan(self.h, C.byref(si), C.byref(res)), "rmd_scan")
+        return self._result(res, job["n_win"])
+
+    def gc_counts(self, n_seq):
+        out = np.zeros((n_seq, N_CODES), dtype=np.int64)
+        self._check(self.lib.rmd_gc_counts(self.h, out.ctypes.data), "rmd_gc_counts")
+        return out
+
+    def set_gc(self, gc_log, gc_class=None):
+        gc_log = np.ascontiguousarray(gc_log, dtype=np.float64)
+        gcc = None if gc_class is None else np.ascontiguousarray(gc_class, dtype=np.int32)
+        self._check(self.lib.rmd_set_gc(self.h, gc_log.ctypes.data, _ptr(gcc)), "rmd_set_gc")
+
+    def eval(self, model, codes, seq_off, gc_log, p0, p1, cutoff):
+        n = len(p0)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        gc_log = np.ascontiguousarray(gc_log, dtype=np.float64)
+        p0 = np.ascontiguousarray(p0, dtype=np.int32)
+        p1 = np.ascontiguousarray(p1, dtype=np.int32)
+        leaf = np.zeros(n, dtype=np.int32)
+        pm = np.zeros(n, dtype=np.float64)
+        pr = np.zeros(n, dtype=np.float64)
+        self._check(self.lib.rmd_eval(self.h, model, codes.ctypes.data, seq_off.ctypes.data, gc_log.ctypes.data,
+                                      p0.ctypes.data, p1.ctypes.data, n, cutoff, leaf.ctypes.data, pm.ctypes.data,
+                                      pr.ctypes.data), "rmd_eval")
+        return leaf, pm, pr
+
+    def calibrate(self, model, samples, class_log, cutoff, hist, seed=None, first=0, n=None, L=None):
+        class_log = np.ascontiguousarray(class_log, dtype=np.float64)
+        assert hist.dtype == np.float64 and hist.flags.c_contiguous and hist.shape[0] == class_log.shape[0]
+        n_ok, ovf, ms = C.c_int64(0), C.c_int32(0), C.c_float(0)
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, dtype=np.uint8)
+            n, L = samples.shape
+            rc = self.lib.rmd_calibrate(self.h, model, samples.ctypes.data, n, L, class_log.ctypes.data,
+                                        class_log.shape[0], cutoff, hist.ctypes.data, hist.shape[1],
+                                        C.byref(n_ok), C.byref(ovf), C.byref(ms))
+        else:
+            rc = self.lib.rmd_calibrate_synth(self.h, model, seed, first, n, L, class_log.ctypes.data,
+                                              class_log.shape[0], cutoff, hist.ctypes.data, hist.shape[1],
+                                              C.byref(n_ok), C.byref(ovf), C.byref(ms))
+        self._check(rc, "rmd_calibrate")
+        if ovf.value:
+            raise NativeError("calibration score beyond the histogram range (%d bins)" % hist.shape[1])
+        return n_ok.value, ms.value
+
+    def synth_job(self, n, first, seq_seed, bpp_seed, win_len, win_step, min_bpp_mean, cutoff, gc_log, gc_class=None):
+        gc_log = np.ascontiguousarray(gc_log, dtype=np.float64).reshape(1, N_CODES)
+        gcc = None if gc_class is None else np.ascontiguousarray(gc_class, dtype=np.int32)
+        n_win, n_bpp, ms = C.c_int64(0), C.c_int64(0), C.c_float(0)
+        self._check(self.lib.rmd_synth_job(self.h, n, first, seq_seed, bpp_seed, win_len, win_step, min_bpp_mean,
+                                           cutoff, gc_log.ctypes.data, _ptr(gcc), C.byref(n_win), C.byref(n_bpp),
+                                           C.byref(ms)), "rmd_synth_job")
+        return n_win.value, n_bpp.value, ms.value
+
+    def download_codes(self, n):
+        out = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.rmd_download_codes(self.h, out.ctypes.data, n), "rmd_download_codes")
+        return out
+
+    def download_bpp(self, window, cap=16384):
+        i = np.zeros(cap, dtype=np.uint16)
+        j = np.zeros(cap, dtype=np.uint16)
+        p = np.zeros(cap, dtype=np.float64)
+        n = C.c_int64(0)
+        self._check(self.lib.rmd_download_bpp(self.h, window, i.ctypes.data, j.ctypes.data, p.ctypes.data, cap,
+                                              C.byref(n)), "rmd_download_bpp")
+        return i[:n.value], j[:n.value], p[:n.value]
+
+    def download_job(self, n_win, n_bpp, pinned=False):
+        """(bpp_off, i, j, p) of the resident job as host arrays (page-locked when `pinned`)."""
+        off = np.zeros(n_win + 1, dtype=np.int64)
+        if pinned:
+            i = pinned_array(n_bpp, np.uint16)
+            j = pinned_array(n_bpp, np.uint16)
+            p = pinned_array(n_bpp, np.float64)
+        else:
+            i = np.zeros(max(n_bpp, 1), dtype=np.uint16)
+            j = np.zeros(max(n_bpp, 1), dtype=np.uint16)
+            p = np.zeros(max(n_bpp, 1), dtype=np.float64)
+        self._check(self.lib.rmd_download_job(self.h, off.ctypes.data, i.ctypes.data, j.ctypes.data, p.ctypes.data),
+                    "rmd_download_job")
+        return off, i, j, p
+
+
+class _Pinned:
+    def __init__(self, nbytes):
+        self.lib = load_library()
+        self.ptr = self.lib.rmd_host_alloc(nbytes)
+        if not self.ptr:
+            raise NativeError("rmd_host_alloc(%d) failed" % nbytes)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.lib.rmd_host_free(self.ptr)
+            self.ptr = None
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray view that keeps its page-locked allocation alive."""
+    _owner = None
+
+
+def pinned_array(n, dtype):
+    """numpy array over page-locked host memory (released when the array is collected)."""
+    dtype = np.dtype(dtype)
+    n = max(int(n), 1)
+    owner = _Pinned(n * dtype.itemsize)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(owner.ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).view(_PinnedArray)
+    arr._owner = owner
+    return arr

@@ -1,0 +1,191 @@
+// device_common.cuh — structures and device helpers shared by every kernel of the scan path.
+//
+// Reference semantics restated here (paths relative to the reference root):
+//   window geometry      lib/scanner.py:80-111 (slide)            -> window_geom()
+//   letter codes          lib/gcx.py:4-13 (one log-frequency per distinct character)
+//   Bayesian-net scoring  lib/node.py:176-277 (NodeSearch.eval)    -> eval_placement()
+//
+// fp64 throughout, additions issued one by one in the reference's order with explicit
+// round-to-nearest intrinsics so the compiler cannot contract or reassociate them.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include "../../include/rmdetect_b200.h"
+
+#define FULL_MASK 0xffffffffu
+
+// Per-model data in constant memory: everything that is read warp-uniformly (gate program,
+// first pairs, sizes, table pointers).  Trees and CPTs are read per lane and live in global memory
+// behind the read-only path.
+struct CModel {
+    int chain_len[2];
+    int symmetric, n_tree, n_cfg, n_first, brute, n_leaves;
+    const rmd_tree_node *tree;
+    const int2 *leaf_dist;
+    const double *cpt;
+    const int8_t *leaf_offsets; // [n_leaves][chain_len[0] + chain_len[1]]
+    const double *ev_table;     // [ev_nclass][ev_nrows]
+    const double *ev_thr;       // [ev_nrows]
+    int ev_nclass, ev_nrows;
+    unsigned short cfg_begin[RMD_MAX_GATE_CFGS + 1];
+    rmd_gate_pair pairs[RMD_MAX_GATE_PAIRS];
+    char2 first[RMD_MAX_FIRST_PAIRS];
+};
+__constant__ CModel c_models[RMD_MAX_MODELS];
+
+// A resident scan job (device pointers).
+struct DevJob {
+    int n_seq, n_models, win_len, win_step;
+    long long n_win;
+    const long long *seq_off;    // [n_seq+1]
+    const long long *win_base;   // [n_seq+1] first window index of each sequence
+    const uint32_t *codes2;      // 2 bits per letter, 16 letters per word (valid when codes8 == nullptr)
+    const uint8_t *codes8;       // one byte per letter, kept only if some letter is not ACGU
+    const double *gc_log;        // [n_seq][16]
+    const int *gc_class;         // [n_seq][n_models]
+    const long long *bpp_off;    // [n_win+1]
+    const uint16_t *bpp_i, *bpp_j;
+    const double *bpp_p;
+    double min_bpp, cutoff;
+};
+
+// Unordered hit record written by the scan kernels; `rank` is its position inside its
+// (window, model) group in odometer order, so the ordering pass is a plain scatter.
+struct RawHit {
+    uint32_t window;     // relative to the scanned range
+    uint16_t p0, p1;
+    uint16_t model, leaf;
+    uint32_t rank;
+    double pm, pr;
+};
+static_assert(sizeof(RawHit) == 32, "RawHit layout");
+
+struct ScanOut {
+    RawHit *raw;
+    unsigned long long *raw_count;   // [0] records appended, [1] tests_all, [2] tests_pairs
+    long long raw_cap;
+    uint32_t *gate_pass;             // [n_win_range][n_models]
+    uint32_t *group_hits;            // [n_win_range][n_models]
+};
+
+__device__ __forceinline__ int get_code(const DevJob &J, long long g) {
+    if (J.codes8) return J.codes8[g];
+    return (__ldg(J.codes2 + (g >> 4)) >> (2 * (int)(g & 15))) & 3;
+}
+
+// lib/scanner.py:80-111: window k of a sequence starts at k*step, the last one is re-anchored at
+// max(0, len - W); in whole-sequence mode (W or step 0, :43-44) the sequence is its only window.
+__device__ __forceinline__ void window_geom(const DevJob &J, long long w, int &seq, long long &start, int &wlen) {
+    int lo = 0, hi = J.n_seq;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (J.win_base[mid] <= w) lo = mid; else hi = mid;
+    }
+    seq = lo;
+    long long len = J.seq_off[lo + 1] - J.seq_off[lo];
+    if (J.win_len == 0 || J.win_step == 0) {
+        start = 0;
+        wlen = (int)len;
+    } else {
+        long long k = w - J.win_base[lo], nwin = J.win_base[lo + 1] - J.win_base[lo];
+        start = (k == nwin - 1) ? (len > J.win_len ? len - J.win_len : 0) : k * (long long)J.win_step;
+        long long rest = len - start;
+        wlen = (int)(rest < J.win_len ? rest : J.win_len);
+    }
+}
+
+// Number of placements the odometer visits (lib/scanner.py:137-157,161-193): p0 = 0 is always
+// tried; p0 >= 1 needs p0 + L0 < W; for each p0, p1 starts at 0 (at p0 when SYMMETRIC) and is
+// tried once unconditionally, then while p1 + L1 < W.
+__device__ __forceinline__ int rows_of(int wlen, int L0) { return wlen - L0 > 1 ? wlen - L0 : 1; }
+__device__ __forceinline__ int p1_last(int wlen, int L1, int p1_first) {
+    int hi = wlen - L1 - 1;
+    return hi > p1_first ? hi : p1_first;
+}
+
+struct EvalOut { int leaf; double pm, pr; };
+
+// NodeSearch.eval + the winner of get_solution (lib/node.py:153-277) on the flattened tree.
+// LETTER(pos) yields the code (0..15) at a window-relative position.
+template <class LetterFn>
+__device__ __forceinline__ EvalOut eval_placement(const CModel &M, LetterFn letter, const double *gc,
+                                                  int p0, int p1, double cutoff) {
+    EvalOut out;
+    out.leaf = -1; out.pm = -500.0; out.pr = -500.0;            // lib/node.py:250-251
+    if (!(0.0 >= __dadd_rn(0.0, cutoff))) return out;            // the root's own test (:248)
+    double sp[RMD_MAX_BRANCH_DEPTH + 1], sr[RMD_MAX_BRANCH_DEPTH + 1];
+    sp[0] = 0.0; sr[0] = 0.0;
+    double pm = 0.0, pr = 0.0;
+    const uint4 *tree = reinterpret_cast<const uint4 *>(M.tree);
+    const int n = M.n_tree;
+    int t = 0;
+    while (t < n) {
+        const uint4 raw = __ldg(tree + t);
+        const int chain = (int)(int8_t)(raw.x & 0xff), oft = (int)(int8_t)((raw.x >> 8) & 0xff);
+        const int flags = (raw.y >> 16) & 0xff, bdepth = raw.y >> 24;
+        const int skip = raw.z >> 16;
+        if (flags & RMD_F_RESTORE) { pm = sp[bdepth - 1]; pr = sr[bdepth - 1]; }
+        if (flags & RMD_F_CHECK_DIST) {                           // lib/node.py:184-192
+            const int2 dd = __ldg(M.leaf_dist + (raw.z & 0xffff));
+            const int d = p1 - p0;
+            if ((d >= 0 && d < dd.x) || (d <= 0 && -d < dd.y)) { t = skip; continue; }
+        }
+        const int nt = oft < 0 ? 4 : letter((chain ? p1 : p0) + oft);   // :199-204
+        int row = 0;
+        const int npar = (raw.w >> 16) & 0xff;
+        if (npar > 0) {                                           // :207-213
+            const int pc0 = (int)(int8_t)((raw.x >> 16) & 0xff), po0 = (int)(int8_t)(raw.y & 0xff);
+            int c = po0 < 0 ? 4 : letter((pc0 ? p1 : p0) + po0);
+            row = c < 5 ? c : 5;
+            if (npar > 1) {
+                const int pc1 = (int)(int8_t)(raw.x >> 24), po1 = (int)(int8_t)((raw.y >> 8) & 0xff);
+                c = po1 < 0 ? 4 : letter((pc1 ? p1 : p0) + po1);
+                row = row * RMD_NSYM + (c < 5 ? c : 5);
+            }
+        }
+        double v = __ldg(M.cpt + ((raw.w & 0xffff) + row) * RMD_NSYM + (nt < 5 ? nt : 5));
+        const double g = gc[nt];                                  // :223 (slot 4 holds log 0.25)
+        if (v == CUDART_INF) v = g;                               // GC-sentinel row (:217-218)
+        pm = __dadd_rn(pm, v);                                    // :227-228
+        pr = __dadd_rn(pr, g);
+        if (!(pm >= __dadd_rn(pr, cutoff))) { t = skip; continue; }   // :248
+        if (flags & RMD_F_LEAF) {
+            if (pm > out.pm) { out.pm = pm; out.pr = pr; out.leaf = raw.z & 0xffff; }   // :265-275
+        } else if (flags & RMD_F_SAVE) {
+            sp[bdepth] = pm; sr[bdepth] = pr;
+        }
+        t++;
+    }
+    return out;
+}
+
+// exclusive scan of one value per thread over a block of NT threads (NT multiple of 32, <= 1024);
+// returns the exclusive prefix and writes the block total to *total.  `tmp` holds NT/32 + 1 words.
+template <int NT>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *tmp, uint32_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < NT / 32 ? tmp[lane] : 0, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(FULL_MASK, winc, o);
+            if (lane >= o) winc += n;
+        }
+        if (lane < NT / 32) tmp[lane] = winc - w;
+        if (lane == 31) tmp[NT / 32] = winc;
+    }
+    __syncthreads();
+    const uint32_t res = tmp[wid] + inc - v;
+    *total = tmp[NT / 32];
+    __syncthreads();
+    return res;
+}

@@ -1,0 +1,704 @@
+// rmd_lib.cu — the C ABI declared in include/rmdetect_b200.h: context, device memory, launches.
+//
+// One context = one GPU, one compute stream, one copy stream.  Calls on a context are serialised
+// by the caller (the reference itself is single-threaded and not re-entrant, lib/node.py:178-181).
+// Nothing here computes on the host: without a CUDA device rmd_create() fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "scan_kernels.cuh"
+#include "post_kernels.cuh"
+#include "calib_kernels.cuh"
+#include "synth_kernels.cuh"
+
+static thread_local std::string g_error;
+
+struct DBuf {                      // grow-only device buffer
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct rmd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[12] = {};
+    std::string error;
+    // models
+    int n_models = 0;
+    std::vector<CModel> hmodels;
+    std::vector<void *> model_allocs;
+    std::vector<void *> ev_allocs[RMD_MAX_MODELS];
+    int max_chain = 0;
+    // resident job
+    bool have_job = false;
+    DevJob job{};
+    long long n_letters = 0, n_bpp = 0;
+    int max_wlen = 0;
+    bool any_other = false;
+    std::vector<long long> h_seq_off, h_win_base;
+    DBuf d_seq_off, d_win_base, d_codes8, d_codes2, d_gc_log, d_gc_class, d_bpp_off, d_bpp_i, d_bpp_j, d_bpp_p;
+    DBuf d_flag, d_counts, d_bpp_cnt;
+    // scan outputs
+    DBuf d_raw, d_counters, d_gate_pass, d_group_hits, d_group_off, d_scan_sums, d_final, d_keep, d_keep_off, d_compact;
+    rmd_hit *h_hits = nullptr;
+    size_t h_hits_cap = 0;
+    uint32_t *h_gate = nullptr, *h_group = nullptr;
+    size_t h_gate_cap = 0;
+    long long raw_cap = 0;
+    bool return_dropped = false;
+    // eval / calibrate scratch
+    DBuf d_e0, d_e1, d_e2, d_e3, d_e4, d_e5, d_e6, d_e7;
+};
+
+static int fail(rmd_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, RMD_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int reserve(rmd_ctx *ctx, DBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return RMD_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(ctx, RMD_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    b.cap = want;
+    return RMD_OK;
+}
+#define RESERVE(buf, bytes) do { int r_ = reserve(ctx, buf, bytes); if (r_) return r_; } while (0)
+
+extern "C" const char *rmd_version(void) { return "rmdetect_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char *rmd_last_error(rmd_ctx *ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+extern "C" int rmd_create(int device, rmd_ctx **out) {
+    rmd_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, RMD_E_INVALID, "rmd_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RMD_E_CUDA, "no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, RMD_E_INVALID, "device %d out of range (%d present)", device, count);
+    ctx = new rmd_ctx();
+    ctx->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
+    *out = ctx;
+    return RMD_OK;
+}
+
+static void free_models(rmd_ctx *ctx) {
+    for (void *p : ctx->model_allocs) cudaFree(p);
+    ctx->model_allocs.clear();
+    for (auto &v : ctx->ev_allocs) { for (void *p : v) cudaFree(p); v.clear(); }
+    ctx->hmodels.clear();
+    ctx->n_models = 0;
+}
+
+extern "C" void rmd_destroy(rmd_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_models(ctx);
+    DBuf *bufs[] = {&ctx->d_seq_off, &ctx->d_win_base, &ctx->d_codes8, &ctx->d_codes2, &ctx->d_gc_log, &ctx->d_gc_class,
+                    &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt,
+                    &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
+                    &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact,
+                    &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
+    for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
+    if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
+    if (ctx->h_group) cudaFreeHost(ctx->h_group);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" void *rmd_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, (size_t)(bytes > 0 ? bytes : 1)) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void rmd_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+template <class T>
+static int to_device(rmd_ctx *ctx, const T *src, size_t n, T **dst, std::vector<void *> &owner) {
+    void *p = nullptr;
+    CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    owner.push_back(p);
+    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (T *)p;
+    return RMD_OK;
+}
+
+extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_models) {
+    if (!ctx || !models || n_models < 1) return fail(ctx, RMD_E_INVALID, "rmd_set_models: bad arguments");
+    if (n_models > RMD_MAX_MODELS) return fail(ctx, RMD_E_LIMIT, "at most %d models per context", RMD_MAX_MODELS);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    free_models(ctx);
+    ctx->hmodels.assign(n_models, CModel{});
+    ctx->max_chain = 0;
+    for (int m = 0; m < n_models; m++) {
+        const rmd_model_desc &d = models[m];
+        CModel &c = ctx->hmodels[m];
+        if (d.n_gate_pairs > RMD_MAX_GATE_PAIRS || d.n_gate_cfg > RMD_MAX_GATE_CFGS || d.n_first > RMD_MAX_FIRST_PAIRS)
+            return fail(ctx, RMD_E_LIMIT, "model %d: gate program too large (%d pairs, %d configurations, %d first pairs)",
+                        m, d.n_gate_pairs, d.n_gate_cfg, d.n_first);
+        if (d.n_tree < 1 || d.n_tree > 65535 || d.chain_len[0] < 1 || d.chain_len[1] < 1 || d.chain_len[0] > 100 || d.chain_len[1] > 100)
+            return fail(ctx, RMD_E_LIMIT, "model %d: tree size %d / chain lengths %d,%d out of range", m, d.n_tree, d.chain_len[0], d.chain_len[1]);
+        c.chain_len[0] = d.chain_len[0]; c.chain_len[1] = d.chain_len[1];
+        ctx->max_chain = std::max(ctx->max_chain, std::max(d.chain_len[0], d.chain_len[1]));
+        c.symmetric = d.symmetric; c.n_tree = d.n_tree; c.n_cfg = d.n_gate_cfg; c.n_first = d.n_first;
+        c.brute = d.brute_candidates; c.n_leaves = d.n_leaves;
+        for (int k = 0; k <= d.n_gate_cfg; k++) c.cfg_begin[k] = (unsigned short)d.gate_cfg[k];
+        for (int k = 0; k < d.n_gate_pairs; k++) {
+            c.pairs[k] = d.gate_pairs[k];
+            if ((c.pairs[k].c1 | c.pairs[k].c2) & ~1) return fail(ctx, RMD_E_INVALID, "model %d: gate pair names chain > 1", m);
+        }
+        for (int k = 0; k < d.n_first; k++) c.first[k] = make_char2(d.first_pairs[2 * k], d.first_pairs[2 * k + 1]);
+        int r;
+        rmd_tree_node *tree = nullptr; int32_t *ld = nullptr; double *cpt = nullptr; int8_t *lo = nullptr;
+        if ((r = to_device(ctx, d.tree, d.n_tree, &tree, ctx->model_allocs))) return r;
+        if ((r = to_device(ctx, d.leaf_dist, (size_t)d.n_leaves * 2, &ld, ctx->model_allocs))) return r;
+        if ((r = to_device(ctx, d.cpt, (size_t)d.n_cpt_rows * RMD_NSYM, &cpt, ctx->model_allocs))) return r;
+        if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, ctx->model_allocs))) return r;
+        c.tree = tree; c.leaf_dist = (const int2 *)ld; c.cpt = cpt; c.leaf_offsets = lo;
+        c.ev_table = nullptr; c.ev_thr = nullptr; c.ev_nclass = 0; c.ev_nrows = 0;
+    }
+    ctx->n_models = n_models;
+    CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * n_models));
+    ctx->have_job = false;
+    return RMD_OK;
+}
+
+extern "C" int rmd_set_evalues(rmd_ctx *ctx, int model, const double *table, int n_class, int n_rows, const double *thresholds) {
+    if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_set_evalues: bad model index");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (void *p : ctx->ev_allocs[model]) cudaFree(p);
+    ctx->ev_allocs[model].clear();
+    CModel &c = ctx->hmodels[model];
+    c.ev_table = nullptr; c.ev_thr = nullptr; c.ev_nclass = 0; c.ev_nrows = 0;
+    if (n_class > 0 && n_rows > 0) {
+        if (!table || !thresholds) return fail(ctx, RMD_E_INVALID, "rmd_set_evalues: NULL table");
+        double *t = nullptr, *th = nullptr; int r;
+        if ((r = to_device(ctx, table, (size_t)n_class * n_rows, &t, ctx->ev_allocs[model]))) return r;
+        if ((r = to_device(ctx, thresholds, (size_t)n_rows, &th, ctx->ev_allocs[model]))) return r;
+        c.ev_table = t; c.ev_thr = th; c.ev_nclass = n_class; c.ev_nrows = n_rows;
+    }
+    CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * ctx->n_models));
+    return RMD_OK;
+}
+
+// ---- window bookkeeping (lib/scanner.py:80-111) ----------------------------------------------
+static long long windows_of(long long len, int win_len, int win_step) {
+    if (win_len == 0 || win_step == 0) return 1;
+    if (len <= win_len) return 1;
+    return 1 + (len - win_len + win_step - 1) / win_step;
+}
+
+static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win_len, int win_step, long long expect_win) {
+    if (n_seq < 1 || !seq_off) return fail(ctx, RMD_E_INVALID, "job needs at least one sequence");
+    if (win_len < 0 || win_step < 0) return fail(ctx, RMD_E_INVALID, "negative window length or step");
+    ctx->h_seq_off.assign(seq_off, seq_off + n_seq + 1);
+    ctx->h_win_base.assign(n_seq + 1, 0);
+    ctx->max_wlen = 0;
+    for (int s = 0; s < n_seq; s++) {
+        long long len = seq_off[s + 1] - seq_off[s];
+        if (len < 0) return fail(ctx, RMD_E_INVALID, "seq_off is not monotone");
+        ctx->h_win_base[s + 1] = ctx->h_win_base[s] + windows_of(len, win_len, win_step);
+        long long wl = (win_len == 0 || win_step == 0) ? len : std::min<long long>(len, win_len);
+        if (wl > 65535) return fail(ctx, RMD_E_LIMIT, "window of %lld letters exceeds the 65535 limit", wl);
+        ctx->max_wlen = std::max(ctx->max_wlen, (int)wl);
+    }
+    if (expect_win >= 0 && ctx->h_win_base[n_seq] != expect_win)
+        return fail(ctx, RMD_E_INVALID, "n_win is %lld but the sequences yield %lld windows", expect_win, ctx->h_win_base[n_seq]);
+    ctx->n_letters = seq_off[n_seq];
+    RESERVE(ctx->d_seq_off, sizeof(long long) * (n_seq + 1));
+    RESERVE(ctx->d_win_base, sizeof(long long) * (n_seq + 1));
+    CK(cudaMemcpyAsync(ctx->d_seq_off.p, ctx->h_seq_off.data(), sizeof(long long) * (n_seq + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_win_base.p, ctx->h_win_base.data(), sizeof(long long) * (n_seq + 1), cudaMemcpyHostToDevice, ctx->stream));
+    DevJob &J = ctx->job;
+    J.n_seq = n_seq; J.n_models = ctx->n_models; J.win_len = win_len; J.win_step = win_step;
+    J.n_win = ctx->h_win_base[n_seq];
+    J.seq_off = (const long long *)ctx->d_seq_off.p; J.win_base = (const long long *)ctx->d_win_base.p;
+    return RMD_OK;
+}
+
+static int stage_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class) {
+    DevJob &J = ctx->job;
+    RESERVE(ctx->d_gc_log, sizeof(double) * RMD_N_CODES * J.n_seq);
+    RESERVE(ctx->d_gc_class, sizeof(int) * (size_t)J.n_seq * J.n_models);
+    if (gc_log) CK(cudaMemcpyAsync(ctx->d_gc_log.p, gc_log, sizeof(double) * RMD_N_CODES * J.n_seq, cudaMemcpyHostToDevice, ctx->stream));
+    if (gc_class) CK(cudaMemcpyAsync(ctx->d_gc_class.p, gc_class, sizeof(int) * (size_t)J.n_seq * J.n_models, cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(ctx->d_gc_class.p, 0xff, sizeof(int) * (size_t)J.n_seq * J.n_models, ctx->stream));
+    J.gc_log = (const double *)ctx->d_gc_log.p; J.gc_class = (const int *)ctx->d_gc_class.p;
+    return RMD_OK;
+}
+
+extern "C" int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in) {
+    if (!ctx || !in) return fail(ctx, RMD_E_INVALID, "rmd_upload: NULL argument");
+    if (ctx->n_models == 0) return fail(ctx, RMD_E_STATE, "rmd_upload: call rmd_set_models first");
+    if (!in->gc_log) return fail(ctx, RMD_E_INVALID, "rmd_upload: gc_log is required (use rmd_gc_counts + rmd_set_gc to derive it on the device)");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_job = false;
+    int r;
+    if ((r = stage_layout(ctx, in->n_seq, in->seq_off, in->win_len, in->win_step, in->n_win))) return r;
+    if ((r = stage_gc(ctx, in->gc_log, in->gc_class))) return r;
+    DevJob &J = ctx->job;
+    const long long n = ctx->n_letters;
+    const long long nb = in->bpp_off ? in->bpp_off[in->n_win] : 0;
+    ctx->n_bpp = nb;
+    RESERVE(ctx->d_codes8, (size_t)n + 16);
+    RESERVE(ctx->d_codes2, sizeof(uint32_t) * ((size_t)n / 16 + 2));
+    RESERVE(ctx->d_flag, 64);
+    RESERVE(ctx->d_bpp_off, sizeof(long long) * (in->n_win + 1));
+    RESERVE(ctx->d_bpp_i, sizeof(uint16_t) * (size_t)std::max<long long>(nb, 1));
+    RESERVE(ctx->d_bpp_j, sizeof(uint16_t) * (size_t)std::max<long long>(nb, 1));
+    RESERVE(ctx->d_bpp_p, sizeof(double) * (size_t)std::max<long long>(nb, 1));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[4], st));
+    if (n) CK(cudaMemcpyAsync(ctx->d_codes8.p, in->codes, (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_flag.p, 0, 64, st));
+    if (n) {
+        const long long words = (n + 15) / 16;
+        pack_codes_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>((const uint8_t *)ctx->d_codes8.p, n, (uint32_t *)ctx->d_codes2.p, (int *)ctx->d_flag.p);
+    }
+    if (in->bpp_off) CK(cudaMemcpyAsync(ctx->d_bpp_off.p, in->bpp_off, sizeof(long long) * (in->n_win + 1), cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(ctx->d_bpp_off.p, 0, sizeof(long long) * (in->n_win + 1), st));
+    if (nb) {
+        CK(cudaMemcpyAsync(ctx->d_bpp_i.p, in->bpp_i, sizeof(uint16_t) * nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_bpp_j.p, in->bpp_j, sizeof(uint16_t) * nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_bpp_p.p, in->bpp_p, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+    }
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->any_other = flag != 0;
+    J.codes2 = (const uint32_t *)ctx->d_codes2.p;
+    J.codes8 = ctx->any_other ? (const uint8_t *)ctx->d_codes8.p : nullptr;
+    J.bpp_off = (const long long *)ctx->d_bpp_off.p;
+    J.bpp_i = (const uint16_t *)ctx->d_bpp_i.p; J.bpp_j = (const uint16_t *)ctx->d_bpp_j.p; J.bpp_p = (const double *)ctx->d_bpp_p.p;
+    J.min_bpp = in->min_bpp_mean; J.cutoff = in->cutoff;
+    ctx->have_job = true;
+    return RMD_OK;
+}
+
+extern "C" int rmd_gc_counts(rmd_ctx *ctx, int64_t *counts) {
+    if (!ctx || !counts) return fail(ctx, RMD_E_INVALID, "rmd_gc_counts: NULL argument");
+    if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_gc_counts: no resident job");
+    CK(cudaSetDevice(ctx->device));
+    const DevJob &J = ctx->job;
+    RESERVE(ctx->d_counts, sizeof(unsigned long long) * RMD_N_CODES * J.n_seq);
+    CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * RMD_N_CODES * J.n_seq, ctx->stream));
+    long long longest = 0;
+    for (int s = 0; s < J.n_seq; s++) longest = std::max(longest, ctx->h_seq_off[s + 1] - ctx->h_seq_off[s]);
+    unsigned gx = (unsigned)std::min<long long>(std::max<long long>((longest + 256 * 16 - 1) / (256 * 16), 1), 148 * 8);
+    for (int s0 = 0; s0 < J.n_seq; s0 += 65535) {
+        DevJob part = J;
+        part.seq_off = J.seq_off + s0;
+        unsigned gy = (unsigned)std::min(65535, J.n_seq - s0);
+        count_letters_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(part, (unsigned long long *)ctx->d_counts.p + (size_t)s0 * RMD_N_CODES);
+    }
+    CK(cudaMemcpyAsync(counts, ctx->d_counts.p, sizeof(unsigned long long) * RMD_N_CODES * J.n_seq, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return RMD_OK;
+}
+
+extern "C" int rmd_set_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class) {
+    if (!ctx || !gc_log) return fail(ctx, RMD_E_INVALID, "rmd_set_gc: NULL argument");
+    if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_set_gc: no resident job");
+    CK(cudaSetDevice(ctx->device));
+    int r = stage_gc(ctx, gc_log, gc_class);
+    if (r) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RMD_OK;
+}
+
+extern "C" int rmd_set_return_dropped(rmd_ctx *ctx, int enable) {
+    if (!ctx) return fail(ctx, RMD_E_INVALID, "rmd_set_return_dropped: NULL context");
+    ctx->return_dropped = enable != 0;
+    return RMD_OK;
+}
+
+// exclusive scan helper: out has n + 1 slots
+static int device_scan(rmd_ctx *ctx, const uint32_t *in, long long n, uint32_t *out, int *launches) {
+    if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(uint32_t), ctx->stream)); return RMD_OK; }
+    const int nblocks = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    RESERVE(ctx->d_scan_sums, sizeof(uint32_t) * (nblocks + 2));
+    uint32_t *sums = (uint32_t *)ctx->d_scan_sums.p;
+    scan_block_sums_kernel<<<nblocks, SCAN_BT, 0, ctx->stream>>>(in, n, sums);
+    scan_sums_kernel<<<1, SCAN_BT, 0, ctx->stream>>>(sums, nblocks, sums + nblocks);
+    scan_apply_kernel<<<nblocks, SCAN_BT, 0, ctx->stream>>>(in, n, sums, out);
+    *launches += 3;
+    return RMD_OK;
+}
+
+static int ensure_host(rmd_ctx *ctx, size_t hits, size_t groups) {
+    if (hits > ctx->h_hits_cap) {
+        if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
+        ctx->h_hits = nullptr; ctx->h_hits_cap = 0;
+        size_t want = hits + hits / 4 + 1024;
+        CK(cudaMallocHost((void **)&ctx->h_hits, want * sizeof(rmd_hit)));
+        ctx->h_hits_cap = want;
+    }
+    if (groups > ctx->h_gate_cap) {
+        if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
+        if (ctx->h_group) cudaFreeHost(ctx->h_group);
+        ctx->h_gate = ctx->h_group = nullptr; ctx->h_gate_cap = 0;
+        size_t want = groups + groups / 4 + 1024;
+        CK(cudaMallocHost((void **)&ctx->h_gate, want * sizeof(uint32_t)));
+        CK(cudaMallocHost((void **)&ctx->h_group, want * sizeof(uint32_t)));
+        ctx->h_gate_cap = want;
+    }
+    return RMD_OK;
+}
+
+extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out) {
+    if (!ctx || !out) return fail(ctx, RMD_E_INVALID, "rmd_scan_resident: NULL argument");
+    if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_scan_resident: no resident job");
+    const DevJob &J = ctx->job;
+    if (w_begin < 0 || w_end > J.n_win || w_begin > w_end) return fail(ctx, RMD_E_INVALID, "window range [%lld, %lld) outside [0, %lld)", (long long)w_begin, (long long)w_end, J.n_win);
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof *out);
+    const long long nwin = w_end - w_begin;
+    const long long ngroups = nwin * J.n_models;
+    if (ngroups >= (1LL << 31)) return fail(ctx, RMD_E_LIMIT, "window range too large for one call (%lld windows x %d models)", nwin, J.n_models);
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[8], st));
+    RESERVE(ctx->d_counters, 64);
+    RESERVE(ctx->d_gate_pass, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
+    RESERVE(ctx->d_group_hits, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
+    RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(ngroups + 1));
+    if (ctx->raw_cap == 0) ctx->raw_cap = std::max<long long>(1 << 16, 24 * nwin);
+    const bool use_fast = ctx->max_chain <= 32;
+    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW;
+    unsigned long long counters[8];
+    int launches = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        RESERVE(ctx->d_raw, sizeof(RawHit) * (size_t)ctx->raw_cap);
+        launches = 0;
+        CK(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        CK(cudaMemsetAsync(ctx->d_gate_pass.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
+        CK(cudaMemsetAsync(ctx->d_group_hits.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
+        ScanOut O;
+        O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.raw_cap = ctx->raw_cap;
+        O.gate_pass = (uint32_t *)ctx->d_gate_pass.p; O.group_hits = (uint32_t *)ctx->d_group_hits.p;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        if (nwin > 0) {
+            if (use_fast) {
+                scan_fast_kernel<<<(unsigned)nwin, SCAN_THREADS, 0, st>>>(J, w_begin, w_end, O);
+                launches++;
+            }
+            if (need_generic) {
+                scan_generic_kernel<<<(unsigned)ngroups, GEN_THREADS, 0, st>>>(J, w_begin, w_end, O, use_fast ? 0 : 1);
+                launches++;
+            }
+        }
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if ((long long)counters[0] <= ctx->raw_cap) break;
+        if (attempt == 1) return fail(ctx, RMD_E_NOMEM, "hit buffer overflow persisted (%llu records)", counters[0]);
+        ctx->raw_cap = (long long)counters[0] + (long long)counters[0] / 8 + 1024;   // rerun with room for every record
+    }
+    const long long n_raw = (long long)counters[0];
+    out->n_raw = n_raw;
+    out->tries[0] = (int64_t)counters[1];
+    out->tries[1] = (int64_t)counters[2];
+    // ---- ordering, scoring, duplicate removal, compaction ---------------------------------------
+    RESERVE(ctx->d_final, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));
+    RESERVE(ctx->d_compact, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));
+    RESERVE(ctx->d_keep, sizeof(uint32_t) * (size_t)std::max<long long>(n_raw, 1));
+    RESERVE(ctx->d_keep_off, sizeof(uint32_t) * (size_t)(n_raw + 1));
+    CK(cudaEventRecord(ctx->ev[2], st));
+    int r;
+    if ((r = device_scan(ctx, (const uint32_t *)ctx->d_group_hits.p, ngroups, (uint32_t *)ctx->d_group_off.p, &launches))) return r;
+    uint32_t n_keep = 0;
+    if (n_raw > 0) {
+        const unsigned blocks = (unsigned)((n_raw + 255) / 256);
+        finalize_hits_kernel<<<blocks, 256, 0, st>>>(J, w_begin, (const RawHit *)ctx->d_raw.p, n_raw, (const uint32_t *)ctx->d_group_off.p,
+                                                     std::log(2.0), (rmd_hit *)ctx->d_final.p);
+        dedupe_kernel<<<blocks, 256, 0, st>>>(J, w_begin, w_end, (rmd_hit *)ctx->d_final.p, n_raw, (const uint32_t *)ctx->d_group_off.p,
+                                              (uint32_t *)ctx->d_keep.p);
+        launches += 2;
+        if ((r = device_scan(ctx, (const uint32_t *)ctx->d_keep.p, n_raw, (uint32_t *)ctx->d_keep_off.p, &launches))) return r;
+        compact_hits_kernel<<<blocks, 256, 0, st>>>((const rmd_hit *)ctx->d_final.p, n_raw, (const uint32_t *)ctx->d_keep.p,
+                                                    (const uint32_t *)ctx->d_keep_off.p, (rmd_hit *)ctx->d_compact.p);
+        launches++;
+        CK(cudaMemcpyAsync(&n_keep, (uint32_t *)ctx->d_keep_off.p + n_raw, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const long long n_out = ctx->return_dropped ? n_raw : (long long)n_keep;
+    if ((r = ensure_host(ctx, (size_t)n_out, (size_t)ngroups))) return r;
+    CK(cudaEventRecord(ctx->ev[6], st));
+    if (n_out) CK(cudaMemcpyAsync(ctx->h_hits, ctx->return_dropped ? ctx->d_final.p : ctx->d_compact.p, sizeof(rmd_hit) * n_out, cudaMemcpyDeviceToHost, st));
+    if (ngroups) {
+        CK(cudaMemcpyAsync(ctx->h_gate, ctx->d_gate_pass.p, sizeof(uint32_t) * ngroups, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_group, ctx->d_group_hits.p, sizeof(uint32_t) * ngroups, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaEventRecord(ctx->ev[9], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&out->ms_total, ctx->ev[8], ctx->ev[9]));
+    out->n_hits = n_out;
+    out->hits = ctx->h_hits;
+    out->gate_pass = ctx->h_gate;
+    out->raw_count = ctx->h_group;
+    CK(cudaEventElapsedTime(&out->ms_scan, ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&out->ms_post, ctx->ev[2], ctx->ev[3]));
+    CK(cudaEventElapsedTime(&out->ms_d2h, ctx->ev[6], ctx->ev[7]));
+    out->n_launches = launches;
+    return RMD_OK;
+}
+
+extern "C" int rmd_scan(rmd_ctx *ctx, const rmd_scan_input *in, rmd_scan_result *out) {
+    int r = rmd_upload(ctx, in);
+    if (r) return r;
+    r = rmd_scan_resident(ctx, 0, ctx->job.n_win, out);
+    if (r) return r;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    out->ms_h2d = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[9]));
+    out->ms_total = ms;
+    out->n_launches += 1;
+    return RMD_OK;
+}
+
+extern "C" int rmd_eval(rmd_ctx *ctx, int model, const uint8_t *codes, const int64_t *seq_off, const double *gc_log,
+                        const int32_t *p0, const int32_t *p1, int64_t n, double cutoff,
+                        int32_t *leaf, double *prob_model, double *prob_rand) {
+    if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_eval: bad model index");
+    if (n <= 0) return RMD_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const long long nl = seq_off[n];
+    const CModel &M = ctx->hmodels[model];
+    for (int64_t k = 0; k < n; k++) {            // the reference would raise IndexError past the end
+        const long long len = seq_off[k + 1] - seq_off[k];
+        if (p0[k] < 0 || p1[k] < 0 || p0[k] + M.chain_len[0] > len || p1[k] + M.chain_len[1] > len)
+            return fail(ctx, RMD_E_INVALID, "rmd_eval: placement %lld reaches outside its sequence", (long long)k);
+    }
+    RESERVE(ctx->d_e0, (size_t)nl + 16);
+    RESERVE(ctx->d_e1, sizeof(long long) * (n + 1));
+    RESERVE(ctx->d_e2, sizeof(double) * RMD_N_CODES * n);
+    RESERVE(ctx->d_e3, sizeof(int) * n);
+    RESERVE(ctx->d_e4, sizeof(int) * n);
+    RESERVE(ctx->d_e5, sizeof(int) * n);
+    RESERVE(ctx->d_e6, sizeof(double) * n);
+    RESERVE(ctx->d_e7, sizeof(double) * n);
+    CK(cudaMemcpyAsync(ctx->d_e0.p, codes, (size_t)nl, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e1.p, seq_off, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e2.p, gc_log, sizeof(double) * RMD_N_CODES * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e3.p, p0, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e4.p, p1, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    eval_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(model, (const uint8_t *)ctx->d_e0.p, (const long long *)ctx->d_e1.p,
+                                                                   (const double *)ctx->d_e2.p, (const int *)ctx->d_e3.p, (const int *)ctx->d_e4.p,
+                                                                   n, cutoff, (int *)ctx->d_e5.p, (double *)ctx->d_e6.p, (double *)ctx->d_e7.p);
+    CK(cudaMemcpyAsync(leaf, ctx->d_e5.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(prob_model, ctx->d_e6.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(prob_rand, ctx->d_e7.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return RMD_OK;
+}
+
+static int calibrate_common(rmd_ctx *ctx, int model, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n, int32_t L,
+                            const double *class_log, int32_t n_class, double cutoff, double *hist, int32_t n_bins,
+                            int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
+    if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: bad model index");
+    const CModel &M = ctx->hmodels[model];
+    if (L != M.chain_len[0] + M.chain_len[1]) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: L is %d, the model has %d positions", L, M.chain_len[0] + M.chain_len[1]);
+    if (L > 32) return fail(ctx, RMD_E_LIMIT, "rmd_calibrate: at most 32 positions");
+    if (n_class < 1 || n_class > CAL_MAX_CLASS || n_bins < 2) return fail(ctx, RMD_E_LIMIT, "rmd_calibrate: class count %d / bin count %d out of range", n_class, n_bins);
+    if (n <= 0) return RMD_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<double> thr(n_bins);
+    // thresholds of Python's round(x, 1): computed by the caller-independent exact rule on the host
+    for (int k = 0; k < n_bins; k++) {
+        // smallest double whose decimal rounding to one place reaches (k+1)/10: probe around the midpoint
+        double mid = (2.0 * k + 1.0) / 20.0, lo = nextafter(mid, 0.0), best = nextafter(mid, 1e300);
+        char a[32];
+        for (double c : {lo, mid}) {
+            snprintf(a, sizeof a, "%.1f", c);
+            if (lround(strtod(a, nullptr) * 10.0) >= k + 1) { best = c; break; }
+        }
+        thr[k] = best;
+    }
+    RESERVE(ctx->d_e0, samples ? (size_t)n * L : 16);
+    RESERVE(ctx->d_e1, sizeof(double) * 4 * n_class);
+    RESERVE(ctx->d_e2, sizeof(double) * n_bins);
+    RESERVE(ctx->d_e3, sizeof(double) * (size_t)n_class * n_bins);
+    RESERVE(ctx->d_e4, 64);
+    if (samples) CK(cudaMemcpyAsync(ctx->d_e0.p, samples, (size_t)n * L, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e1.p, class_log, sizeof(double) * 4 * n_class, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e2.p, thr.data(), sizeof(double) * n_bins, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_e3.p, 0, sizeof(double) * (size_t)n_class * n_bins, st));
+    CK(cudaMemsetAsync(ctx->d_e4.p, 0, 64, st));
+    CalibArgs A;
+    A.model = model; A.L = L; A.n_class = n_class; A.n_bins = n_bins; A.n = n; A.first = first;
+    A.samples = samples ? (const uint8_t *)ctx->d_e0.p : nullptr; A.seed = seed;
+    A.class_log = (const double *)ctx->d_e1.p; A.thr = (const double *)ctx->d_e2.p;
+    A.cutoff = cutoff; A.ln2 = std::log(2.0); A.K = L * std::log(4.0);
+    A.hist = (double *)ctx->d_e3.p;
+    A.n_ok = (unsigned long long *)ctx->d_e4.p; A.overflow = (int *)((char *)ctx->d_e4.p + 8);
+    CK(cudaEventRecord(ctx->ev[0], st));
+    calibrate_kernel<<<(unsigned)((n + CAL_THREADS - 1) / CAL_THREADS), CAL_THREADS, 0, st>>>(A);
+    CK(cudaEventRecord(ctx->ev[1], st));
+    std::vector<double> h((size_t)n_class * n_bins);
+    unsigned long long small[2] = {0, 0};
+    CK(cudaMemcpyAsync(h.data(), ctx->d_e3.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(small, ctx->d_e4.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (size_t k = 0; k < h.size(); k++) hist[k] += h[k];
+    if (n_ok) *n_ok = (int64_t)small[0];
+    if (overflow) *overflow = (int32_t)(small[1] & 0xffffffffu);
+    if (ms_kernel) CK(cudaEventElapsedTime(ms_kernel, ctx->ev[0], ctx->ev[1]));
+    return RMD_OK;
+}
+
+extern "C" int rmd_calibrate(rmd_ctx *ctx, int model, const uint8_t *samples, int64_t n, int32_t L,
+                             const double *class_log, int32_t n_class, double cutoff,
+                             double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
+    if (!samples) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: samples is NULL");
+    return calibrate_common(ctx, model, samples, 0, 0, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
+}
+
+extern "C" int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64_t first, int64_t n, int32_t L,
+                                   const double *class_log, int32_t n_class, double cutoff,
+                                   double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
+    return calibrate_common(ctx, model, nullptr, seed, first, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
+}
+
+extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, uint64_t bpp_seed,
+                             int32_t win_len, int32_t win_step, double min_bpp_mean, double cutoff,
+                             const double *gc_log, const int32_t *gc_class, int64_t *n_win, int64_t *n_bpp, float *ms_generate) {
+    if (!ctx || n < 1) return fail(ctx, RMD_E_INVALID, "rmd_synth_job: bad arguments");
+    if (ctx->n_models == 0) return fail(ctx, RMD_E_STATE, "rmd_synth_job: call rmd_set_models first");
+    if (win_len < 1 || win_len > RMD_FAST_WINDOW || win_step < 1) return fail(ctx, RMD_E_LIMIT, "rmd_synth_job: window length must be 1..%d", RMD_FAST_WINDOW);
+    if (!gc_log) return fail(ctx, RMD_E_INVALID, "rmd_synth_job: gc_log is required");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_job = false;
+    int64_t seq_off[2] = {0, n};
+    int r;
+    if ((r = stage_layout(ctx, 1, seq_off, win_len, win_step, -1))) return r;
+    if ((r = stage_gc(ctx, gc_log, gc_class))) return r;
+    DevJob &J = ctx->job;
+    cudaStream_t st = ctx->stream;
+    RESERVE(ctx->d_codes2, sizeof(uint32_t) * ((size_t)n / 16 + 2));
+    RESERVE(ctx->d_bpp_cnt, sizeof(uint32_t) * (size_t)J.n_win);
+    RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(J.n_win + 1));
+    RESERVE(ctx->d_bpp_off, sizeof(long long) * (size_t)(J.n_win + 1));
+    J.codes2 = (const uint32_t *)ctx->d_codes2.p; J.codes8 = nullptr; ctx->any_other = false;
+    J.min_bpp = min_bpp_mean; J.cutoff = cutoff;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    const long long words = (n + 15) / 16;
+    synth_codes_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(seq_seed, first, n, (uint32_t *)ctx->d_codes2.p);
+    synth_bpp_kernel<false><<<(unsigned)J.n_win, SYN_THREADS, 0, st>>>(J, bpp_seed, (uint32_t *)ctx->d_bpp_cnt.p, nullptr, nullptr, nullptr, nullptr);
+    // offsets: 32-bit scan per window, widened on the host (lists stay far below 4 G entries per job)
+    int launches = 0;
+    if ((r = device_scan(ctx, (const uint32_t *)ctx->d_bpp_cnt.p, J.n_win, (uint32_t *)ctx->d_group_off.p, &launches))) return r;
+    std::vector<uint32_t> off32((size_t)J.n_win + 1);
+    CK(cudaMemcpyAsync(off32.data(), ctx->d_group_off.p, sizeof(uint32_t) * off32.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    std::vector<long long> off64(off32.begin(), off32.end());
+    const long long nb = off64.back();
+    ctx->n_bpp = nb;
+    RESERVE(ctx->d_bpp_i, sizeof(uint16_t) * (size_t)std::max<long long>(nb, 1));
+    RESERVE(ctx->d_bpp_j, sizeof(uint16_t) * (size_t)std::max<long long>(nb, 1));
+    RESERVE(ctx->d_bpp_p, sizeof(double) * (size_t)std::max<long long>(nb, 1));
+    CK(cudaMemcpyAsync(ctx->d_bpp_off.p, off64.data(), sizeof(long long) * off64.size(), cudaMemcpyHostToDevice, st));
+    J.bpp_off = (const long long *)ctx->d_bpp_off.p;
+    J.bpp_i = (const uint16_t *)ctx->d_bpp_i.p; J.bpp_j = (const uint16_t *)ctx->d_bpp_j.p; J.bpp_p = (const double *)ctx->d_bpp_p.p;
+    synth_bpp_kernel<true><<<(unsigned)J.n_win, SYN_THREADS, 0, st>>>(J, bpp_seed, nullptr, J.bpp_off, (uint16_t *)ctx->d_bpp_i.p,
+                                                                      (uint16_t *)ctx->d_bpp_j.p, (double *)ctx->d_bpp_p.p);
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (ms_generate) CK(cudaEventElapsedTime(ms_generate, ctx->ev[0], ctx->ev[1]));
+    if (n_win) *n_win = J.n_win;
+    if (n_bpp) *n_bpp = nb;
+    ctx->have_job = true;
+    return RMD_OK;
+}
+
+extern "C" int rmd_download_codes(rmd_ctx *ctx, uint8_t *codes, int64_t n) {
+    if (!ctx || !codes) return fail(ctx, RMD_E_INVALID, "rmd_download_codes: NULL argument");
+    if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_codes: no resident job");
+    if (n > ctx->n_letters) n = ctx->n_letters;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->any_other) {
+        CK(cudaMemcpy(codes, ctx->d_codes8.p, (size_t)n, cudaMemcpyDeviceToHost));
+        return RMD_OK;
+    }
+    std::vector<uint32_t> words((size_t)(n + 15) / 16);
+    CK(cudaMemcpy(words.data(), ctx->d_codes2.p, words.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < n; k++) codes[k] = (words[k >> 4] >> (2 * (k & 15))) & 3;
+    return RMD_OK;
+}
+
+extern "C" int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint16_t *j, double *p, int64_t cap, int64_t *n) {
+    if (!ctx || !n) return fail(ctx, RMD_E_INVALID, "rmd_download_bpp: NULL argument");
+    if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_bpp: no resident job");
+    if (window < 0 || window >= ctx->job.n_win) return fail(ctx, RMD_E_INVALID, "rmd_download_bpp: window out of range");
+    CK(cudaSetDevice(ctx->device));
+    long long off[2];
+    CK(cudaMemcpy(off, (const long long *)ctx->d_bpp_off.p + window, sizeof off, cudaMemcpyDeviceToHost));
+    const long long cnt = off[1] - off[0];
+    *n = cnt;
+    const long long take = std::min<long long>(cnt, cap);
+    if (take > 0) {
+        CK(cudaMemcpy(i, (const uint16_t *)ctx->d_bpp_i.p + off[0], sizeof(uint16_t) * take, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(j, (const uint16_t *)ctx->d_bpp_j.p + off[0], sizeof(uint16_t) * take, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(p, (const double *)ctx->d_bpp_p.p + off[0], sizeof(double) * take, cudaMemcpyDeviceToHost));
+    }
+    return RMD_OK;
+}
+
+extern "C" int rmd_download_job(rmd_ctx *ctx, int64_t *bpp_off, uint16_t *i, uint16_t *j, double *p) {
+    if (!ctx || !bpp_off) return fail(ctx, RMD_E_INVALID, "rmd_download_job: NULL argument");
+    if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_job: no resident job");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(bpp_off, ctx->d_bpp_off.p, sizeof(long long) * (ctx->job.n_win + 1), cudaMemcpyDeviceToHost));
+    const long long nb = ctx->n_bpp;
+    if (i && j && p && nb > 0) {
+        CK(cudaMemcpy(i, ctx->d_bpp_i.p, sizeof(uint16_t) * nb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(j, ctx->d_bpp_j.p, sizeof(uint16_t) * nb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(p, ctx->d_bpp_p.p, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    }
+    return RMD_OK;
+}

@@ -264,18 +264,18 @@ def walk_flat(fm: FlatModel, codes, p0, p1, gc_log, cutoff):
         nd = fm.tree[t]
         flags = int(nd["flags"])
         if flags & F_RESTORE:
-            pm, pr = sp[nd["bdepth"] - 1], sr[nd["bdepth"] - 1]
+            pm, pr = sp[int(nd["bdepth"]) - 1], sr[int(nd["bdepth"]) - 1]
         if flags & F_CHECK_DIST:
-            d01, d10 = fm.leaf_dist[nd["leaf"]]
+            d01, d10 = (int(v) for v in fm.leaf_dist[int(nd["leaf"])])
             d = p1 - p0
             if (0 <= d < d01) or (0 <= -d < d10):
                 t = int(nd["skip"])
                 continue
-        nt = CODE_GAP if nd["oft"] < 0 else int(codes[ptr[nd["chain"]] + nd["oft"]])
+        nt = CODE_GAP if nd["oft"] < 0 else int(codes[ptr[int(nd["chain"])] + int(nd["oft"])])
         row = 0
         for k in range(int(nd["npar"])):
             po = int(nd["par_oft"][k])
-            pc = CODE_GAP if po < 0 else int(codes[ptr[nd["par_chain"][k]] + po])
+            pc = CODE_GAP if po < 0 else int(codes[ptr[int(nd["par_chain"][k])] + po])
             row = row * NSYM + min(pc, CODE_OTHER)
         v = fm.cpt[int(nd["cpt_row"]) + row, min(nt, CODE_OTHER)]
         if v == GC_MARK:
@@ -290,6 +290,6 @@ def walk_flat(fm: FlatModel, codes, p0, p1, gc_log, cutoff):
             if pm > best_p:
                 best_p, best_r, best_leaf = pm, pr, int(nd["leaf"])
         elif flags & F_SAVE:
-            sp[nd["bdepth"]], sr[nd["bdepth"]] = pm, pr
+            sp[int(nd["bdepth"])], sr[int(nd["bdepth"])] = pm, pr
         t += 1
     return best_leaf >= 0, best_leaf, best_p, best_r

@@ -1,0 +1,240 @@
+"""GPU parity: the CUDA path through the C ABI against the reference's golden outputs and the oracle.
+
+Bit-exact for hit sets, positions, gap configurations, tests_all / tests_pairs and (fp64, same
+addition order) log-probabilities, scores and E-values.  Calibration histograms are sums of ~1e4-1e6
+positive weights accumulated in a different order: relative tolerance 1e-9 (north star allows 1e-6).
+"""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+from helpers import (LN_CUTOFF, LN_UNKNOWN, MODEL_FILES, MODEL_ORDER, REF_DATA, Cfg, SeqList, evalues_path,
+                     fresh_models, golden, load_evalues, load_model)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine_all():
+    from rmdetect_b200.scanner import ScanEngine
+    names = sorted(MODEL_FILES)
+    eng = ScanEngine([load_model(n) for n in names], [load_evalues(n) for n in names], LN_UNKNOWN)
+    yield names, eng
+    eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_FILES))
+def test_eval_vectors(engine_all, name):
+    from rmdetect_b200.gcx import encode_sequence, gc_table
+    names, eng = engine_all
+    mi = names.index(name)
+    cases = [c for c in golden("eval_vectors")[name] if c["unknown_prob"] == LN_UNKNOWN]
+    assert len(cases) == 400
+    for cutoff in sorted({c["cutoff"] for c in cases}):
+        sub = [c for c in cases if c["cutoff"] == cutoff]
+        codes, off, gcs = [], [0], []
+        for c in sub:
+            cd, others = encode_sequence(c["seq"])
+            codes.append(cd)
+            off.append(off[-1] + len(cd))
+            gcs.append(gc_table(c["gc"], others))
+        leaf, pm, pr = eng.ctx.eval(mi, np.concatenate(codes), off, np.array(gcs), [c["p"][0] for c in sub],
+                                    [c["p"][1] for c in sub], cutoff)
+        for c, lf, a, b in zip(sub, leaf, pm, pr):
+            assert (lf >= 0) == c["ok"]
+            if c["ok"]:
+                assert a == c["prob_model"] and b == c["prob_rand"]
+                offs = eng.flats[mi].leaf_offsets[lf]
+                seqs = ["".join("." if o is None else c["seq"][c["p"][k] + o] for o in offs[k]) for k in range(2)]
+                assert seqs == c["seqs"]
+
+
+def run_case(case):
+    from rmdetect_b200.scanner import Scanner
+    from rmdetect_b200.synth import SynthFold
+    models, evs = fresh_models(case["models"])
+    cfg = Cfg(models, evs, case["win_len"], case["win_step"], case["min_bpp"], case["cutoff"], case["unknown"])
+    sc = Scanner(cfg)
+    sc.rna_tools = SynthFold(case["seed"])
+    events = []
+    sc.cback_before_scan = lambda n: events.append(["before_scan", n])
+    sc.cback_before_sequence = lambda n, i, k: events.append(["before_sequence", n, i, k])
+    sc.cback_before_window = lambda n, p: events.append(["before_window", n, p])
+    sc.cback_after_window = lambda c, t: events.append(["after_window", len(c), list(t)])
+    sc.cback_after_sequence = lambda c, t: events.append(["after_sequence", len(c), list(t)])
+    sc.cback_after_scan = lambda c, t: events.append(["after_scan", len(c), list(t)])
+    cands, tries = sc.scan(SeqList(case["seqs"]))
+    sc._engine.close()
+    return cands, tries, events
+
+
+@pytest.mark.parametrize("idx", range(15))
+def test_scan_cases_match_reference(idx):
+    """Scanner.scan on the GPU == the reference's Scanner.scan (golden), field by field."""
+    case = golden("scan_cases")[idx]
+    cands, tries, events = run_case(case)
+    assert tries == case["tries"]
+    assert len(cands) == len(case["cands"])
+    for got, want in zip(cands, case["cands"]):
+        assert got.model.full_name() == want["model"] and got.key == want["key"]
+        assert list(got.coords) == want["coords"]
+        assert ["".join(s) for s in got.chains_seqs] == want["seqs"]
+        assert got.chains_pos == want["pos"] and got.chains_cols == want["cols"]
+        assert got.score == want["score"] and got.evalue == want["evalue"]
+    if case["events"]:
+        assert events == case["events"]
+
+
+def test_real_bpp_windows_through_c_abi():
+    """The two real RNAfold matrices shipped with the reference."""
+    from rmdetect_b200.dotps import read_dot_ps
+    from rmdetect_b200.scanner import ScanEngine
+
+    class Fold:
+        def __init__(self, table):
+            self.table = table
+
+        def coo(self, win):
+            z = np.zeros(0, np.uint16)
+            return self.table.get(win, (z, z, np.zeros(0)))
+
+    key = "ABCZ01000009.1/166331-166512"
+    seq = next(s for k, s, _ in golden("seqsets")["lys.stk"] if k == key)
+    wseq, i, j, p = read_dot_ps(os.path.join(REF_DATA, "lys_dot.ps"))
+    eng = ScanEngine([load_model(n) for n in MODEL_ORDER], [load_evalues(n) for n in MODEL_ORDER], LN_UNKNOWN)
+    job = eng.build_job([(key, seq, None)], 150, 75, Fold({wseq: (i, j, p)}), "", 0.001, LN_CUTOFF)
+    res = eng.scan_job(job)
+    assert res["gate_pass"].sum(axis=1).tolist() == [0, 1806]
+    assert res["tries"] == [2 * 70939, 1806]
+    got = {(MODEL_ORDER[h["model"]], int(h["start"] + h["p0"]), int(h["start"] + h["p1"])): h for h in res["hits"]}
+    kt = got[("KT_1.0", 164, 81)]
+    assert ("%.5E" % kt["score"], "%.5E" % kt["evalue"]) == ("1.04455E+01", "3.04000E-05")
+    tga = got[("TGA_1.0", 40, 56)]
+    assert ("%.5E" % tga["score"], "%.5E" % tga["evalue"]) == ("8.21393E+00", "1.04900E-03")
+    eng.close()
+
+    wseq, i, j, p = read_dot_ps(os.path.join(REF_DATA, "arich", "dot.ps"))
+    eng = ScanEngine([load_model("ARICH_1.0")], [load_evalues("ARICH_1.0")], LN_UNKNOWN)
+    res = eng.scan_job(eng.build_job([("a", wseq, None)], 150, 75, Fold({wseq: (i, j, p)}), "", 0.001, LN_CUTOFF))
+    assert res["tries"] == [9506, 452]
+    strong = sorted(((int(h["p0"]), int(h["p1"]), "%.6G" % h["score"]) for h in res["hits"] if h["score"] > 5),
+                    key=lambda t: -float(t[2]))
+    assert strong == [(43, 69, "15.0855"), (43, 70, "11.6195"), (17, 70, "8.52062")]
+    eng.close()
+
+
+def _oracle_scan(names, seq, win_len, win_step, seed, min_bpp=0.001):
+    from oracle import pyoracle
+    from rmdetect_b200.synth import SynthFold
+    oms = [pyoracle.OracleModel(load_model(n)) for n in names]
+    oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+    fold = SynthFold(seed)
+    starts = pyoracle.windows(len(seq), win_len, win_step)
+    bpp = [pyoracle.synth_bpp(seq[s:s + win_len], seed) for s in starts]
+    return pyoracle.scan_sequence(oms, oes, 0, seq, win_len, win_step, bpp, min_bpp, LN_UNKNOWN, LN_CUTOFF)
+
+
+def test_synthetic_job_generated_on_device_matches_oracle():
+    """Device-side genome + stand-in bpp are bit-identical to the host twins; the scan of a 30 kb
+    synthetic chromosome matches the oracle hit for hit."""
+    from rmdetect_b200.gcx import gc_table
+    from rmdetect_b200.scanner import ScanEngine, gc_of_codes
+    from rmdetect_b200.synth import synth_bpp_coo, synth_codes, synth_sequence
+    n, seed = 30000, 20261019
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    codes = synth_codes(n, seed)
+    seq = synth_sequence(n, seed)
+    gc = gc_of_codes(codes, "")
+    cls = []
+    for ev in eng.evalues:
+        ev.select_gc(gc)
+        cls.append(ev.selected)
+    n_win, n_bpp, _ = eng.ctx.synth_job(n, 0, seed, seed, 150, 75, 0.001, LN_CUTOFF, gc_table(gc), cls)
+    assert n_win == 399
+    assert np.array_equal(eng.ctx.download_codes(n), codes)
+    counts = eng.ctx.gc_counts(1)
+    assert counts[0, :4].tolist() == np.bincount(codes, minlength=4).tolist() and counts[0, 4:].sum() == 0
+    for w in (0, 1, 57, 398):
+        s = w * 75 if w < 398 else n - 150
+        a = synth_bpp_coo(seq[s:s + 150], seed)
+        b = eng.ctx.download_bpp(w)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    res = eng.ctx.scan_resident(0, n_win)
+    hits, tries, _ = _oracle_scan(MODEL_ORDER, seq, 150, 75, seed)
+    assert res["tries"] == tries
+    assert len(res["hits"]) == len(hits)
+    for g, w in zip(res["hits"], hits):
+        assert (g["model"], g["start"], g["start"] + g["wlen"], g["p0"], g["p1"], g["leaf"]) == \
+               (w["model"], w["coords"][0], w["coords"][1], w["p"][0], w["p"][1], w["cfg"])
+        assert (g["prob_model"], g["prob_rand"], g["score"], g["evalue"]) == \
+               (w["prob_model"], w["prob_rand"], w["score"], w["evalue"])
+    # splitting the window range must only lose the seam's duplicate removal
+    a = eng.ctx.scan_resident(0, 200)
+    b = eng.ctx.scan_resident(200, n_win)
+    assert a["tries"][0] + b["tries"][0] == tries[0] and a["tries"][1] + b["tries"][1] == tries[1]
+    assert a["n_raw"] + b["n_raw"] == res["n_raw"]
+    eng.close()
+
+
+def test_letters_outside_acgu_and_gc_counts():
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    s = list(synth_sequence(400, 5))
+    for pos in (3, 150, 151, 152, 299):
+        s[pos] = "N"
+    s[200] = "Y"
+    seq = "".join(s)
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    job = eng.build_job([("x", seq, None), ("y", seq[:90], None)], 150, 75, SynthFold(9), "", 0.001, LN_CUTOFF)
+    eng.ctx.upload(job)
+    counts = eng.ctx.gc_counts(2)
+    assert counts[0].tolist()[:7] == [seq.count("A"), seq.count("C"), seq.count("G"), seq.count("U"), 0, 5, 1]
+    assert counts[1, :4].sum() + counts[1, 5:].sum() == 90
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["KT_1.0", "GB_1.0", "CL_1.0", "TGA_1.0"])
+def test_calibration_histograms(name):
+    """rmd_calibrate on the reference's own seeded sample stream vs the reference's histograms."""
+    from rmdetect_b200.calibrate import class_logs, draw_samples
+    from rmdetect_b200.gcx import GC
+    from rmdetect_b200.scanner import ScanEngine
+    g = golden("calibrate")[name]
+    m = load_model(name)
+    L = len(m.nodes)
+    n = min(g["samples"], 4 ** L)
+    samples = draw_samples(n, L, g["seed"])
+    eng = ScanEngine([m], [None], LN_UNKNOWN)
+    classes = GC.get_classes(5, 15, 85)
+    hist = np.zeros((len(classes), 512))
+    n_ok, _ = eng.ctx.calibrate(0, samples, class_logs(classes), LN_CUTOFF, hist)
+    for ci, want in enumerate(g["hists"]):
+        got = {k / 10.0: v for k, v in enumerate(hist[ci]) if v != 0.0}
+        assert sorted(got) == [k for k, _ in want]            # exactly the same score buckets
+        for k, v in want:
+            assert got[k] == pytest.approx(v, rel=1e-9)
+    eng.close()
+
+
+def test_one_megabase_counts_match_oracle():
+    """1 Mb synthetic chromosome, all four models: tests_all, tests_pairs and the number of hits
+    before duplicate removal equal the oracle's (13 332 windows, 9.46e8 placements)."""
+    from oracle import pyoracle
+    from rmdetect_b200.gcx import gc_table
+    from rmdetect_b200.scanner import ScanEngine, gc_of_codes
+    from rmdetect_b200.synth import synth_codes, synth_sequence
+    n, seed = 1_000_000, 77
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [None] * 4, LN_UNKNOWN)
+    gc = gc_of_codes(synth_codes(n, seed), "")
+    n_win, _, _ = eng.ctx.synth_job(n, 0, seed, seed, 150, 75, 0.001, LN_CUTOFF, gc_table(gc))
+    res = eng.ctx.scan_resident(0, n_win)
+    nh, tries = pyoracle.bench_scan([load_model(m) for m in MODEL_ORDER], synth_sequence(n, seed), 150, 75, 0, n_win,
+                                    seed, os.cpu_count() or 1, 0.001, LN_UNKNOWN, LN_CUTOFF)
+    assert res["tries"] == tries
+    assert res["n_raw"] == nh
+    assert tries[0] == n_win * 70939
+    eng.close()
