@@ -18,6 +18,8 @@
 // Per-model data in constant memory: everything that is read warp-uniformly (gate program,
 // first pairs, sizes, table pointers).  Trees and CPTs are read per lane and live in global memory
 // behind the read-only path.
+struct TrieNode { int8_t ro, co; short parent; };   // pair as (row offset from p0, column offset from p1)
+
 struct CModel {
     int chain_len[2];
     int symmetric, n_tree, n_cfg, n_first, brute, n_leaves;
@@ -30,7 +32,11 @@ struct CModel {
     int ev_nclass, ev_nrows;
     unsigned short cfg_begin[RMD_MAX_GATE_CFGS + 1];
     rmd_gate_pair pairs[RMD_MAX_GATE_PAIRS];
-    char2 first[RMD_MAX_FIRST_PAIRS];
+    // prefix trie of the configurations' pair sequences: a node stands for "this pair is summed", which
+    // requires every ancestor pair to be non-zero (the reference's `break`, lib/scanner.py:204-206)
+    int n_trie;
+    unsigned int trie_magic;             // floor(2^32 / n_trie) + 1: exact division of small indices
+    TrieNode trie[RMD_MAX_GATE_PAIRS];
 };
 __constant__ CModel c_models[RMD_MAX_MODELS];
 
@@ -48,6 +54,7 @@ struct DevJob {
     const uint16_t *bpp_i, *bpp_j;
     const double *bpp_p;
     double min_bpp, cutoff;
+    int debug;                   // profiling experiments only (RMD_DEBUG): 1 skip scoring, 2 skip the exact gate
 };
 
 // Unordered hit record written by the scan kernels; `rank` is its position inside its
@@ -108,11 +115,15 @@ struct EvalOut { int leaf; double pm, pr; };
 
 // NodeSearch.eval + the winner of get_solution (lib/node.py:153-277) on the flattened tree.
 // LETTER(pos) yields the code (0..15) at a window-relative position.
+// `budget` bounds the number of tree nodes visited; *finished tells whether the walk completed
+// (an unfinished walk is simply repeated later with no bound — see the two-stage scoring in K1).
 template <class LetterFn>
 __device__ __forceinline__ EvalOut eval_placement(const CModel &M, LetterFn letter, const double *gc,
-                                                  int p0, int p1, double cutoff) {
+                                                  int p0, int p1, double cutoff,
+                                                  int budget = 0x7fffffff, bool *finished = nullptr) {
     EvalOut out;
     out.leaf = -1; out.pm = -500.0; out.pr = -500.0;            // lib/node.py:250-251
+    if (finished) *finished = true;
     if (!(0.0 >= __dadd_rn(0.0, cutoff))) return out;            // the root's own test (:248)
     double sp[RMD_MAX_BRANCH_DEPTH + 1], sr[RMD_MAX_BRANCH_DEPTH + 1];
     sp[0] = 0.0; sr[0] = 0.0;
@@ -121,6 +132,7 @@ __device__ __forceinline__ EvalOut eval_placement(const CModel &M, LetterFn lett
     const int n = M.n_tree;
     int t = 0;
     while (t < n) {
+        if (budget-- <= 0) { if (finished) *finished = false; break; }
         const uint4 raw = __ldg(tree + t);
         const int chain = (int)(int8_t)(raw.x & 0xff), oft = (int)(int8_t)((raw.x >> 8) & 0xff);
         const int flags = (raw.y >> 16) & 0xff, bdepth = raw.y >> 24;

@@ -71,13 +71,30 @@ __device__ __forceinline__ double evalue_of(const CModel &M, int cls, double sco
 }
 
 // ---- K3: order raw records (window, model, odometer), fill in score / E-value / coordinates ----
-__global__ void finalize_hits_kernel(const DevJob J, long long w_begin, const RawHit *raw, long long n_raw,
-                                     const uint32_t *group_off, double ln2, rmd_hit *out) {
+// Records arrive in completion order.  place_hits_kernel buckets them by (window, model) group;
+// finalize_hits_kernel ranks each record inside its group by (p0, p1) — the odometer order of
+// lib/scanner.py:161-193 — by counting smaller keys (groups hold a handful of hits; the count is
+// O(group size) per record), and writes the finished hit at its final position.
+__global__ void place_hits_kernel(const RawHit *raw, long long n_raw, int n_models, const uint32_t *group_off,
+                                  uint32_t *group_fill, RawHit *placed) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_raw) return;
     const RawHit h = raw[r];
+    const long long grp = (long long)h.window * n_models + h.model;
+    placed[group_off[grp] + atomicAdd(&group_fill[grp], 1u)] = h;
+}
+
+__global__ void finalize_hits_kernel(const DevJob J, long long w_begin, const RawHit *placed, long long n_raw,
+                                     const uint32_t *group_off, double ln2, rmd_hit *out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_raw) return;
+    const RawHit h = placed[r];
     const long long grp = (long long)h.window * J.n_models + h.model;
-    const long long dst = (long long)group_off[grp] + h.rank;
+    const uint32_t lo = group_off[grp], hi = group_off[grp + 1];
+    const uint32_t key = ((uint32_t)h.p0 << 16) | h.p1;
+    uint32_t rank = 0;
+    for (uint32_t q = lo; q < hi; q++) rank += (((uint32_t)placed[q].p0 << 16) | placed[q].p1) < key;
+    const long long dst = (long long)lo + rank;
     int seq, wlen;
     long long start;
     window_geom(J, w_begin + h.window, seq, start, wlen);

@@ -172,14 +172,35 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
             return fail(ctx, RMD_E_LIMIT, "model %d: tree size %d / chain lengths %d,%d out of range", m, d.n_tree, d.chain_len[0], d.chain_len[1]);
         c.chain_len[0] = d.chain_len[0]; c.chain_len[1] = d.chain_len[1];
         ctx->max_chain = std::max(ctx->max_chain, std::max(d.chain_len[0], d.chain_len[1]));
-        c.symmetric = d.symmetric; c.n_tree = d.n_tree; c.n_cfg = d.n_gate_cfg; c.n_first = d.n_first;
+        c.symmetric = d.symmetric; c.n_tree = d.n_tree; c.n_cfg = d.n_gate_cfg;
         c.brute = d.brute_candidates; c.n_leaves = d.n_leaves;
         for (int k = 0; k <= d.n_gate_cfg; k++) c.cfg_begin[k] = (unsigned short)d.gate_cfg[k];
         for (int k = 0; k < d.n_gate_pairs; k++) {
             c.pairs[k] = d.gate_pairs[k];
             if ((c.pairs[k].c1 | c.pairs[k].c2) & ~1) return fail(ctx, RMD_E_INVALID, "model %d: gate pair names chain > 1", m);
         }
-        for (int k = 0; k < d.n_first; k++) c.first[k] = make_char2(d.first_pairs[2 * k], d.first_pairs[2 * k + 1]);
+        c.n_first = d.n_first;
+        c.n_trie = 0;                                    // prefix trie over the configurations' pair sequences
+        for (int g = 0; g < d.n_gate_cfg; g++) {
+            if (d.gate_cfg[g + 1] <= d.gate_cfg[g]) return fail(ctx, RMD_E_INVALID, "model %d: empty gate configuration", m);
+            int parent = -1;
+            for (int k = d.gate_cfg[g]; k < d.gate_cfg[g + 1]; k++) {
+                const rmd_gate_pair q = d.gate_pairs[k];
+                int ro, co;
+                if (q.c1 == q.c2) { c.brute = 1; ro = co = 0; }          // same-chain pair: no anchor for candidates
+                else if (q.c1 == 0) { ro = q.o1; co = q.o2; }
+                else { ro = q.o2; co = q.o1; }
+                int node = -1;
+                for (int t = 0; t < c.n_trie; t++)
+                    if (c.trie[t].parent == parent && c.trie[t].ro == ro && c.trie[t].co == co) { node = t; break; }
+                if (node < 0) {
+                    node = c.n_trie++;
+                    c.trie[node].ro = (int8_t)ro; c.trie[node].co = (int8_t)co; c.trie[node].parent = (short)parent;
+                }
+                parent = node;
+            }
+        }
+        c.trie_magic = (unsigned int)(0x100000000ULL / (unsigned long long)c.n_trie) + 1u;
         int r;
         rmd_tree_node *tree = nullptr; int32_t *ld = nullptr; double *cpt = nullptr; int8_t *lo = nullptr;
         if ((r = to_device(ctx, d.tree, d.n_tree, &tree, ctx->model_allocs))) return r;
@@ -188,6 +209,11 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, ctx->model_allocs))) return r;
         c.tree = tree; c.leaf_dist = (const int2 *)ld; c.cpt = cpt; c.leaf_offsets = lo;
         c.ev_table = nullptr; c.ev_thr = nullptr; c.ev_nclass = 0; c.ev_nrows = 0;
+    }
+    {
+        int nt = 0;
+        for (const CModel &c : ctx->hmodels) nt += c.n_trie;
+        if (nt > TRIE_CAP) return fail(ctx, RMD_E_LIMIT, "gate programs of the model set too large for shared memory (%d trie nodes, limit %d)", nt, TRIE_CAP);
     }
     ctx->n_models = n_models;
     CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * n_models));
@@ -245,6 +271,7 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
     DevJob &J = ctx->job;
     J.n_seq = n_seq; J.n_models = ctx->n_models; J.win_len = win_len; J.win_step = win_step;
     J.n_win = ctx->h_win_base[n_seq];
+    J.debug = getenv("RMD_DEBUG") ? atoi(getenv("RMD_DEBUG")) : 0;
     J.seq_off = (const long long *)ctx->d_seq_off.p; J.win_base = (const long long *)ctx->d_win_base.p;
     return RMD_OK;
 }
@@ -434,6 +461,7 @@ extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, r
     out->n_raw = n_raw;
     out->tries[0] = (int64_t)counters[1];
     out->tries[1] = (int64_t)counters[2];
+    if (getenv("RMD_DEBUG")) fprintf(stderr, "[rmd debug] gate candidates %llu, tree visits %llu in %llu warp iterations\n", counters[3], counters[4], counters[5]);
     // ---- ordering, scoring, duplicate removal, compaction ---------------------------------------
     RESERVE(ctx->d_final, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));
     RESERVE(ctx->d_compact, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));
@@ -445,8 +473,14 @@ extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, r
     uint32_t n_keep = 0;
     if (n_raw > 0) {
         const unsigned blocks = (unsigned)((n_raw + 255) / 256);
-        finalize_hits_kernel<<<blocks, 256, 0, st>>>(J, w_begin, (const RawHit *)ctx->d_raw.p, n_raw, (const uint32_t *)ctx->d_group_off.p,
+        // d_keep doubles as the per-group fill counters, d_compact as the bucketed record list
+        RESERVE(ctx->d_keep, sizeof(uint32_t) * (size_t)std::max<long long>(std::max(n_raw, ngroups), 1));
+        CK(cudaMemsetAsync(ctx->d_keep.p, 0, sizeof(uint32_t) * (size_t)ngroups, st));
+        place_hits_kernel<<<blocks, 256, 0, st>>>((const RawHit *)ctx->d_raw.p, n_raw, J.n_models, (const uint32_t *)ctx->d_group_off.p,
+                                                  (uint32_t *)ctx->d_keep.p, (RawHit *)ctx->d_compact.p);
+        finalize_hits_kernel<<<blocks, 256, 0, st>>>(J, w_begin, (const RawHit *)ctx->d_compact.p, n_raw, (const uint32_t *)ctx->d_group_off.p,
                                                      std::log(2.0), (rmd_hit *)ctx->d_final.p);
+        launches++;
         dedupe_kernel<<<blocks, 256, 0, st>>>(J, w_begin, w_end, (rmd_hit *)ctx->d_final.p, n_raw, (const uint32_t *)ctx->d_group_off.p,
                                               (uint32_t *)ctx->d_keep.p);
         launches += 2;

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Small driver for profiling: synthetic chromosome of --mb Mb generated on the device, --steps scans.
+
+Used under ncu (launch list / --set full) and for phase-breakdown experiments (RMD_DEBUG bits:
+1 = skip scoring, 2 = skip the exact gate; results are then wrong on purpose).
+"""
+import argparse
+import math
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import LN_CUTOFF, LN_UNKNOWN, MIN_BPP, SEED, WIN_LEN, WIN_STEP, load_models   # noqa: E402
+from rmdetect_b200.gcx import gc_table                                                    # noqa: E402
+from rmdetect_b200.scanner import ScanEngine                                              # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--mb", type=float, default=1.0)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--models", default="")
+args = ap.parse_args()
+models, evs = load_models()
+if args.models:
+    keep = [i for i, m in enumerate(models) if m.name in args.models.split(",")]
+    models, evs = [models[i] for i in keep], [evs[i] for i in keep]
+eng = ScanEngine(models, evs, LN_UNKNOWN)
+n = int(args.mb * 1e6)
+gc = gc_table({b: math.log(0.25) for b in "ACGU"})
+n_win, n_bpp, ms_gen = eng.ctx.synth_job(n, 0, SEED, SEED, WIN_LEN, WIN_STEP, MIN_BPP, LN_CUTOFF, gc)
+for k in range(args.steps):
+    r = eng.ctx.scan_resident(0, n_win)
+print("models %s windows %d bpp %d gen %.2f ms | scan %.3f ms post %.3f ms total %.3f ms | tries %s raw %d hits %d | %.1f M nt·model/s"
+      % ([m.name for m in models], n_win, n_bpp, ms_gen, r["ms_scan"], r["ms_post"], r["ms_total"], r["tries"], r["n_raw"],
+         len(r["hits"]), n * len(models) / r["ms_scan"] / 1e3))
+eng.close()
