@@ -164,7 +164,7 @@ def run_ours(args):
 
     # ---- device-resident scan ------------------------------------------------------------------
     for _ in range(args.warmup):
-        ctx.scan_resident(0, n_win)
+        ctx.scan_resident(0, n_win, copy=False)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -172,7 +172,7 @@ def run_ours(args):
     dev_ms = scan_ms = post_ms = 0.0
     launches = 0
     for _ in range(args.steps):
-        r = ctx.scan_resident(0, n_win)
+        r = ctx.scan_resident(0, n_win, copy=False)
         dev_ms += r["ms_total"]; scan_ms += r["ms_scan"]; post_ms += r["ms_post"]; launches += r["n_launches"]
     barrier()
     wall = time.perf_counter() - t0
@@ -188,12 +188,12 @@ def run_ours(args):
                bpp_off=off, bpp_i=bi, bpp_j=bj, bpp_p=bp, min_bpp_mean=MIN_BPP, cutoff=LN_CUTOFF)
     h2d = codes.nbytes + off.nbytes + n_bpp * (2 + 2 + 8) + 16 * 8 + 4 * 4
     for _ in range(max(1, args.warmup // 2)):
-        e = ctx.scan(job)
+        e = ctx.scan(job, copy=False)
     barrier()
     t1 = time.perf_counter()
     e2e_dev_ms = 0.0
     for _ in range(args.steps):
-        e = ctx.scan(job)
+        e = ctx.scan(job, copy=False)
         e2e_dev_ms += e["ms_total"]
     barrier()
     e2e_wall = time.perf_counter() - t1

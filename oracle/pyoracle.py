@@ -84,7 +84,7 @@ def lib():
                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_double, C.c_double, C.c_double,
                                         C.POINTER(C.POINTER(Hit)), C.POINTER(C.c_int64), C.c_void_p,
-                                        C.POINTER(C.c_int)]
+                                        C.POINTER(C.c_int), C.c_void_p]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_window_key.restype = C.c_uint64
         L.orc_window_key.argtypes = [C.c_char_p, C.c_int, C.c_uint64]
@@ -213,7 +213,7 @@ def synth_bpp(seq, seed):
 
 
 def scan_sequence(omodels, oevalues, seq_id, seq, win_len, win_step, bpp_list,
-                  min_bpp_mean, unknown_prob, cutoff):
+                  min_bpp_mean, unknown_prob, cutoff, gc=None):
     """Scan one sequence.  `bpp_list[k]` = (i, j, p) arrays of window k (one entry in whole-sequence mode).
 
     Returns (hits: list of dict, tries [all, pairs], tries per window int64[nwin][2]).
@@ -233,10 +233,11 @@ def scan_sequence(omodels, oevalues, seq_id, seq, win_len, win_step, bpp_list,
     tpw = np.zeros((max(1, len(bpp_list)), 2), dtype=np.int64)
     fault = C.c_int(0)
     b = seq.encode("latin-1")
+    g = GcDict.from_dict(gc) if gc is not None else None
     n = lib().orc_scan_sequence(marr, earr, nm, seq_id, b, len(b), win_len, win_step,
                                 off.ctypes.data, bi.ctypes.data, bj.ctypes.data, bp.ctypes.data,
                                 min_bpp_mean, unknown_prob, cutoff, C.byref(out), tries, tpw.ctypes.data,
-                                C.byref(fault))
+                                C.byref(fault), C.addressof(g) if g is not None else None)
     if fault.value:
         lib().orc_free(out)
         raise IndexError("the reference would raise on this input")

@@ -643,12 +643,14 @@ int64_t orc_scan_sequence(void **models, void **evalues, int nmodels, int seq_id
                           const char *seq, int64_t seqlen, int win_len, int win_step,
                           const int64_t *bpp_off, const uint16_t *bi, const uint16_t *bj, const double *bp,
                           double min_bpp_mean, double unknown_prob, double cutoff,
-                          orc_hit **out, int64_t tries[2], int64_t *tries_per_window, int *fault) {
+                          orc_hit **out, int64_t tries[2], int64_t *tries_per_window, int *fault,
+                          const gcdict *gc_given /* Scanner.scan(seqs, gc): lib/scanner.py:29,74-75 */) {
     hitvec hv = {0};
     gcdict gc;
     tries[0] = tries[1] = 0; *fault = 0;
     int nch = nmodels ? ((omodel *)models[0])->nchains : 2;
-    if (seqlen > 0) orc_gc_compute(seq, seqlen, &gc); else memset(&gc, 0, sizeof gc);
+    if (gc_given) gc = *gc_given;
+    else if (seqlen > 0) orc_gc_compute(seq, seqlen, &gc); else memset(&gc, 0, sizeof gc);
     if (win_len == 0 || win_step == 0) {
         if (seqlen > 0) {
             double *mat = malloc(sizeof(double) * (size_t)seqlen * seqlen);

@@ -14,7 +14,7 @@ import numpy as np
 from .modelflat import PAIR_DTYPE, TREE_DTYPE, FlatModel
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librmdetect_b200.so")
+LIB_PATH = os.environ.get("RMD_LIB") or os.path.join(HERE, "librmdetect_b200.so")   # RMD_LIB: A/B runs of two builds
 N_CODES = 16
 FAST_WINDOW = 160
 
@@ -193,30 +193,33 @@ class Context:
         si = self._scan_input(job)
         self._check(self.lib.rmd_upload(self.h, C.byref(si)), "rmd_upload")
 
-    def _result(self, res, n_win):
-        hits = np.empty(res.n_hits, dtype=HIT_DTYPE)
-        if res.n_hits:
-            C.memmove(hits.ctypes.data, res.hits, res.n_hits * HIT_DTYPE.itemsize)
+    def _result(self, res, n_win, copy):
+        """Wrap the library's result.  The arrays are views of page-locked buffers the context owns and are
+        overwritten by its next scan call; `copy=True` detaches them."""
+        def view(ptr, count, dtype):
+            if count == 0 or not ptr:
+                return np.empty(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            arr = np.frombuffer(buf, dtype=dtype, count=count)
+            return arr.copy() if copy else arr
         ng = n_win * self.n_models
-        gate = np.empty((n_win, self.n_models), dtype=np.uint32)
-        raw = np.empty((n_win, self.n_models), dtype=np.uint32)
-        if ng:
-            C.memmove(gate.ctypes.data, res.gate_pass, ng * 4)
-            C.memmove(raw.ctypes.data, res.raw_count, ng * 4)
+        hits = view(res.hits, res.n_hits, HIT_DTYPE)
+        gate = view(res.gate_pass, ng, np.uint32).reshape(n_win, self.n_models)
+        raw = view(res.raw_count, ng, np.uint32).reshape(n_win, self.n_models)
         return dict(hits=hits, tries=[res.tries[0], res.tries[1]], gate_pass=gate, raw_count=raw, n_raw=res.n_raw,
                     ms_scan=res.ms_scan, ms_post=res.ms_post, ms_h2d=res.ms_h2d, ms_d2h=res.ms_d2h,
                     ms_total=res.ms_total, n_launches=res.n_launches)
 
-    def scan_resident(self, w_begin, w_end):
+    def scan_resident(self, w_begin, w_end, copy=True):
         res = ScanResult()
         self._check(self.lib.rmd_scan_resident(self.h, w_begin, w_end, C.byref(res)), "rmd_scan_resident")
-        return self._result(res, w_end - w_begin)
+        return self._result(res, w_end - w_begin, copy)
 
-    def scan(self, job):
+    def scan(self, job, copy=True):
         si = self._scan_input(job)
         res = ScanResult()
         self._check(self.lib.rmd_scan(self.h, C.byref(si), C.byref(res)), "rmd_scan")
-        return self._result(res, job["n_win"])
+        return self._result(res, job["n_win"], copy)
 
     def gc_counts(self, n_seq):
         out = np.zeros((n_seq, N_CODES), dtype=np.int64)

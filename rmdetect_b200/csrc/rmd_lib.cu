@@ -39,7 +39,7 @@ struct rmd_ctx {
     bool have_job = false;
     DevJob job{};
     long long n_letters = 0, n_bpp = 0;
-    int max_wlen = 0;
+    int max_wlen = 0, min_wlen = 0;
     bool any_other = false;
     std::vector<long long> h_seq_off, h_win_base;
     DBuf d_seq_off, d_win_base, d_codes8, d_codes2, d_gc_log, d_gc_class, d_bpp_off, d_bpp_i, d_bpp_j, d_bpp_p;
@@ -203,7 +203,10 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         c.trie_magic = (unsigned int)(0x100000000ULL / (unsigned long long)c.n_trie) + 1u;
         int r;
         rmd_tree_node *tree = nullptr; int32_t *ld = nullptr; double *cpt = nullptr; int8_t *lo = nullptr;
-        if ((r = to_device(ctx, d.tree, d.n_tree, &tree, ctx->model_allocs))) return r;
+        for (int t = 0; t < d.n_tree; t++)
+            if (d.tree[t].npar > 2 || d.tree[t].bdepth > RMD_MAX_BRANCH_DEPTH || d.tree[t].leaf >= d.n_leaves)
+                return fail(ctx, RMD_E_LIMIT, "model %d: tree node %d out of range", m, t);
+        if ((r = to_device(ctx, d.tree, (size_t)d.n_tree, &tree, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.leaf_dist, (size_t)d.n_leaves * 2, &ld, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.cpt, (size_t)d.n_cpt_rows * RMD_NSYM, &cpt, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, ctx->model_allocs))) return r;
@@ -253,6 +256,7 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
     ctx->h_seq_off.assign(seq_off, seq_off + n_seq + 1);
     ctx->h_win_base.assign(n_seq + 1, 0);
     ctx->max_wlen = 0;
+    ctx->min_wlen = 0x7fffffff;
     for (int s = 0; s < n_seq; s++) {
         long long len = seq_off[s + 1] - seq_off[s];
         if (len < 0) return fail(ctx, RMD_E_INVALID, "seq_off is not monotone");
@@ -260,6 +264,8 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
         long long wl = (win_len == 0 || win_step == 0) ? len : std::min<long long>(len, win_len);
         if (wl > 65535) return fail(ctx, RMD_E_LIMIT, "window of %lld letters exceeds the 65535 limit", wl);
         ctx->max_wlen = std::max(ctx->max_wlen, (int)wl);
+        // shortest window of the sequence: the whole sequence if it fits one window, else the tail window is full length
+        ctx->min_wlen = std::min(ctx->min_wlen, (int)wl);
     }
     if (expect_win >= 0 && ctx->h_win_base[n_seq] != expect_win)
         return fail(ctx, RMD_E_INVALID, "n_win is %lld but the sequences yield %lld windows", expect_win, ctx->h_win_base[n_seq]);
@@ -287,7 +293,9 @@ static int stage_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class)
     return RMD_OK;
 }
 
-extern "C" int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in) {
+// Stage a job.  with_entries == false leaves the bpp entry arrays (i, j, p) to the caller, which
+// streams them in window chunks while earlier chunks are being scanned (rmd_scan).
+static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries) {
     if (!ctx || !in) return fail(ctx, RMD_E_INVALID, "rmd_upload: NULL argument");
     if (ctx->n_models == 0) return fail(ctx, RMD_E_STATE, "rmd_upload: call rmd_set_models first");
     if (!in->gc_log) return fail(ctx, RMD_E_INVALID, "rmd_upload: gc_log is required (use rmd_gc_counts + rmd_set_gc to derive it on the device)");
@@ -317,7 +325,7 @@ extern "C" int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in) {
     }
     if (in->bpp_off) CK(cudaMemcpyAsync(ctx->d_bpp_off.p, in->bpp_off, sizeof(long long) * (in->n_win + 1), cudaMemcpyHostToDevice, st));
     else CK(cudaMemsetAsync(ctx->d_bpp_off.p, 0, sizeof(long long) * (in->n_win + 1), st));
-    if (nb) {
+    if (nb && with_entries) {
         CK(cudaMemcpyAsync(ctx->d_bpp_i.p, in->bpp_i, sizeof(uint16_t) * nb, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(ctx->d_bpp_j.p, in->bpp_j, sizeof(uint16_t) * nb, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(ctx->d_bpp_p.p, in->bpp_p, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
@@ -336,6 +344,8 @@ extern "C" int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in) {
     ctx->have_job = true;
     return RMD_OK;
 }
+
+extern "C" int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in) { return upload_job(ctx, in, true); }
 
 extern "C" int rmd_gc_counts(rmd_ctx *ctx, int64_t *counts) {
     if (!ctx || !counts) return fail(ctx, RMD_E_INVALID, "rmd_gc_counts: NULL argument");
@@ -408,7 +418,11 @@ static int ensure_host(rmd_ctx *ctx, size_t hits, size_t groups) {
     return RMD_OK;
 }
 
-extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out) {
+// Scan windows [w_begin, w_end) of the resident job.  When `stream_in` is given its bpp entry arrays
+// are not on the device yet: they are copied in window chunks on the copy stream while the compute
+// stream scans the chunks already there.
+#define STREAM_CHUNKS 12
+static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out, const rmd_scan_input *stream_in) {
     if (!ctx || !out) return fail(ctx, RMD_E_INVALID, "rmd_scan_resident: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_scan_resident: no resident job");
     const DevJob &J = ctx->job;
@@ -425,8 +439,10 @@ extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, r
     RESERVE(ctx->d_group_hits, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(ngroups + 1));
     if (ctx->raw_cap == 0) ctx->raw_cap = std::max<long long>(1 << 16, 24 * nwin);
+    // the shared-memory kernel takes windows longer than every chain and up to 160 letters
     const bool use_fast = ctx->max_chain <= 32;
-    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW;
+    const int min_fast_wlen = use_fast ? ctx->max_chain + 1 : 0x7fffffff;
+    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen;
     unsigned long long counters[8];
     int launches = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -439,13 +455,26 @@ extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, r
         O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.raw_cap = ctx->raw_cap;
         O.gate_pass = (uint32_t *)ctx->d_gate_pass.p; O.group_hits = (uint32_t *)ctx->d_group_hits.p;
         CK(cudaEventRecord(ctx->ev[0], st));
-        if (nwin > 0) {
+        const int n_chunks = (stream_in && attempt == 0 && ctx->n_bpp > 0) ? (int)std::min<long long>(STREAM_CHUNKS, std::max<long long>(nwin / 2048, 1)) : 1;
+        for (int ch = 0; ch < n_chunks && nwin > 0; ch++) {
+            const long long c0 = w_begin + nwin * ch / n_chunks, c1 = w_begin + nwin * (ch + 1) / n_chunks;
+            if (stream_in && attempt == 0 && ctx->n_bpp > 0) {        // entries of windows [c0, c1): copy stream, then let the scan wait for them
+                const long long e0 = stream_in->bpp_off[c0], e1 = stream_in->bpp_off[c1];
+                if (e1 > e0) {
+                    CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_i.p + e0, stream_in->bpp_i + e0, sizeof(uint16_t) * (e1 - e0), cudaMemcpyHostToDevice, ctx->copy_stream));
+                    CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_j.p + e0, stream_in->bpp_j + e0, sizeof(uint16_t) * (e1 - e0), cudaMemcpyHostToDevice, ctx->copy_stream));
+                    CK(cudaMemcpyAsync((double *)ctx->d_bpp_p.p + e0, stream_in->bpp_p + e0, sizeof(double) * (e1 - e0), cudaMemcpyHostToDevice, ctx->copy_stream));
+                }
+                CK(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
+                CK(cudaStreamWaitEvent(st, ctx->ev[10], 0));
+            }
+            if (c1 <= c0) continue;
             if (use_fast) {
-                scan_fast_kernel<<<(unsigned)nwin, SCAN_THREADS, 0, st>>>(J, w_begin, w_end, O);
+                scan_fast_kernel<<<(unsigned)(c1 - c0), SCAN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
                 launches++;
             }
             if (need_generic) {
-                scan_generic_kernel<<<(unsigned)ngroups, GEN_THREADS, 0, st>>>(J, w_begin, w_end, O, use_fast ? 0 : 1);
+                scan_generic_kernel<<<(unsigned)((c1 - c0) * J.n_models), GEN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
                 launches++;
             }
         }
@@ -516,10 +545,15 @@ extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, r
     return RMD_OK;
 }
 
+extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out) {
+    return scan_core(ctx, w_begin, w_end, out, nullptr);
+}
+
 extern "C" int rmd_scan(rmd_ctx *ctx, const rmd_scan_input *in, rmd_scan_result *out) {
-    int r = rmd_upload(ctx, in);
+    int r = upload_job(ctx, in, false);
     if (r) return r;
-    r = rmd_scan_resident(ctx, 0, ctx->job.n_win, out);
+    // the copy stream must not start before the staging above has been issued ... it has been synchronised
+    r = scan_core(ctx, 0, ctx->job.n_win, out, in);
     if (r) return r;
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));

@@ -33,13 +33,13 @@
 
 #define FAST_W RMD_FAST_WINDOW          // 160
 #define FAST_WORDS (FAST_W / 32)        // 5
-#define S_ROWS (FAST_W + 32)            // rows reachable by p0 + o1 in degenerate short windows
-#define S_STRIDE (FAST_WORDS + 1)       // one spare word per row
-#define VAL_CAP 1024                    // bpp values kept in shared memory; beyond that they are read from global
+#define S_ROWS FAST_W                   // windows no longer than a chain go to the generic kernel, so p + o < 160
+#define S_STRIDE FAST_WORDS
+#define VAL_CAP 896                     // bpp values kept in shared memory; beyond that they are read from global
 #define SCAN_THREADS 128
 #define SCAN_WARPS (SCAN_THREADS / 32)
 #define QCAP 64
-#define TRIE_CAP 512                    // trie nodes of all resident models (checked by rmd_set_models)
+#define TRIE_CAP 128                    // trie nodes of all resident models (checked by rmd_set_models)
 #define WORDS_PER_THREAD ((FAST_W * FAST_WORDS + SCAN_THREADS - 1) / SCAN_THREADS)   // 7
 #define LANE_NONE 0xffffffffu
 
@@ -57,9 +57,9 @@ struct FastSmem {
     double gc[RMD_N_CODES];
     uint32_t CB[2][FAST_W * FAST_WORDS]; // candidates already queued, alternating between models
     SmModel model[RMD_MAX_MODELS];
-    TrieNode trie[TRIE_CAP];
     uint32_t q1[SCAN_WARPS][QCAP];       // gate candidates (p0 | p1 << 16)
     uint32_t q2[SCAN_WARPS][QCAP];       // gate survivors  (p0 | p1 << 16), model in q2m
+    TrieNode trie[TRIE_CAP];
     uint32_t big[SCAN_WARPS][32];        // big entries of the current chunk (i | j << 16)
     uint8_t q2m[SCAN_WARPS][QCAP];
     uint32_t scan_tmp[SCAN_WARPS + 1];
@@ -105,8 +105,9 @@ __device__ __forceinline__ bool gate_pass(const CModel &M, Lookup lookup, bool a
 // With no pair summed the reference's mean is 0.0 and is still compared with min_bpp_mean, so a
 // non-positive threshold lets every placement through; every placement is then a candidate.
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const ScanOut O) {
+__global__ void __launch_bounds__(SCAN_THREADS, 8)
+scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
+                 const ScanOut O, const int min_wlen) {       // windows [w_begin, w_end); records are relative to w_base
     __shared__ FastSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1;
@@ -115,12 +116,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     int seq, wlen;
     long long start;
     window_geom(J, w, seq, start, wlen);
-    if (wlen <= 0 || wlen > FAST_W) return;                 // long windows: scan_generic_kernel
+    if (wlen < min_wlen || wlen > FAST_W) return;           // long or degenerate windows: scan_generic_kernel
     const long long gbase = J.seq_off[seq] + start;
     const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
     const int nnz = (int)(b1 - b0);
     const double *vals = nnz <= VAL_CAP ? sm.vals : J.bpp_p + b0;
-    const uint32_t win_local = (uint32_t)(w - w_begin);
+    const uint32_t win_local = (uint32_t)(w - w_base);
 
     // ---- stage the window: letters, GC table, bit matrices, model table and tries ------------------
     for (int k = tid; k < S_ROWS * S_STRIDE; k += SCAN_THREADS) sm.S[k] = 0;
@@ -143,14 +144,25 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         }
     }
     __syncthreads();
-    for (int e = tid; e < nnz; e += SCAN_THREADS) {
-        const int i = J.bpp_i[b0 + e], j = J.bpp_j[b0 + e];
-        if (i < j && j < wlen) {
-            atomicOr(&sm.S[i * S_STRIDE + (j >> 5)], 1u << (j & 31));
-            atomicOr(&sm.S[j * S_STRIDE + (i >> 5)], 1u << (i & 31));
-            atomicOr(&sm.U[i * FAST_WORDS + (j >> 5)].x, 1u << (j & 31));
+    for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) {     // four entries per thread in flight
+        int ei[4], ej[4];
+        double ep[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int e = e0 + k * SCAN_THREADS + tid;
+            ei[k] = ej[k] = 0; ep[k] = 0.0;
+            if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; ep[k] = J.bpp_p[b0 + e]; }
         }
-        if (e < VAL_CAP) sm.vals[e] = J.bpp_p[b0 + e];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int e = e0 + k * SCAN_THREADS + tid, i = ei[k], j = ej[k];
+            if (e < nnz && i < j && j < wlen) {
+                atomicOr(&sm.S[i * S_STRIDE + (j >> 5)], 1u << (j & 31));
+                atomicOr(&sm.S[j * S_STRIDE + (i >> 5)], 1u << (i & 31));
+                atomicOr(&sm.U[i * FAST_WORDS + (j >> 5)].x, 1u << (j & 31));
+            }
+            if (e < nnz && e < VAL_CAP) sm.vals[e] = ep[k];
+        }
     }
     __syncthreads();
     {   // rank of the first bit of every U word = its position in the (i, j)-sorted list
@@ -412,8 +424,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         if (lane == 0 && npass) atomicAdd(&sm.gate_pass[m], npass);
         if (lane == 0 && n_cand && J.debug) atomicAdd(&O.raw_count[3], (unsigned long long)n_cand);
         if (tid == 0) {                                         // tests_all: closed form of the odometer
-            if (M.symmetric) {
-                for (int p0 = 0; p0 < n0; p0++) tests_all += (unsigned long long)(p1_last(wlen, L1, p0) - p0 + 1);
+            if (M.symmetric) {                                  // sum over p0 < n0 of max(1, A - p0), A = wlen - L1
+                const long long A = wlen - L1, k = A > 0 ? (A < n0 ? A : n0) : 0;
+                tests_all += (unsigned long long)(k * A - k * (k - 1) / 2 + (n0 - k));
             } else {
                 tests_all += (unsigned long long)n0 * (unsigned long long)(p1_last(wlen, L1, 0) + 1);
             }
@@ -452,8 +465,8 @@ __device__ __forceinline__ double bpp_search(const DevJob &J, long long b0, int 
 }
 
 __global__ void __launch_bounds__(GEN_THREADS)
-scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_end, const ScanOut O,
-                    const int take_short) {
+scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
+                    const ScanOut O, const int min_fast_wlen) {
     __shared__ uint32_t scan_tmp[GEN_THREADS / 32 + 1];
     __shared__ double gc[RMD_N_CODES];
     __shared__ unsigned long long s_base;
@@ -466,7 +479,7 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     int seq, wlen;
     long long start;
     window_geom(J, w, seq, start, wlen);
-    if (wlen <= 0 || (wlen <= FAST_W && !take_short)) return;    // short windows: scan_fast_kernel
+    if (wlen <= 0 || (wlen >= min_fast_wlen && wlen <= FAST_W)) return;    // those windows: scan_fast_kernel
     const CModel &M = c_models[m];
     const long long gbase = J.seq_off[seq] + start;
     const long long b0 = J.bpp_off[w];
@@ -497,7 +510,7 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
                 const unsigned long long slot = s_base + rank;
                 if (r.leaf >= 0 && (long long)slot < O.raw_cap) {
                     RawHit h;
-                    h.window = (uint32_t)(w - w_begin);
+                    h.window = (uint32_t)(w - w_base);
                     h.p0 = (uint16_t)p0; h.p1 = (uint16_t)p1;
                     h.model = (uint16_t)m; h.leaf = (uint16_t)r.leaf;
                     h.rank = group_rank + rank;
@@ -512,7 +525,7 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     if (npass) atomicAdd(&s_pass, npass);
     __syncthreads();
     if (tid == 0) {
-        const long long grp = (w - w_begin) * J.n_models + m;
+        const long long grp = (w - w_base) * J.n_models + m;
         O.gate_pass[grp] = s_pass;
         O.group_hits[grp] = group_rank;
         atomicAdd(&O.raw_count[1], tests_all);
