@@ -9,8 +9,8 @@
 //
 // Design (one CTA of 128 threads per window, windows up to 160 letters):
 //   * the window's bpp coordinate list becomes, in shared memory, a symmetric bit matrix S
-//     ("is this pair non-zero"), an upper-triangle bit matrix with per-word ranks U (value lookup
-//     by popcount rank) and the fp64 values in list order;
+//     ("is this pair non-zero") and an upper-triangle bit matrix with per-word ranks U: the value of
+//     pair (i, j) is entry rank + popc(bits below) of the window's list, read through L1;
 //   * candidates come from the matrix, not from the 70 000 placements.  The gate mean can reach
 //     min_bpp_mean only if one of the summed values is (within 1e-12) at least min_bpp_mean, and a
 //     pair is summed only if the pairs before it in its configuration are non-zero (the
@@ -35,7 +35,6 @@
 #define FAST_WORDS (FAST_W / 32)        // 5
 #define S_ROWS FAST_W                   // windows no longer than a chain go to the generic kernel, so p + o < 160
 #define S_STRIDE FAST_WORDS
-#define VAL_CAP 896                     // bpp values kept in shared memory; beyond that they are read from global
 #define SCAN_THREADS 128
 #define SCAN_WARPS (SCAN_THREADS / 32)
 #define QCAP 64
@@ -53,7 +52,6 @@ struct SmModel {                        // per-model fields the scoring engine r
 struct FastSmem {
     uint32_t S[S_ROWS * S_STRIDE];
     uint2 U[FAST_W * FAST_WORDS];        // .x = bits (j > i), .y = entries before this word in list order
-    double vals[VAL_CAP];
     double gc[RMD_N_CODES];
     uint32_t CB[2][FAST_W * FAST_WORDS]; // candidates already queued, alternating between models
     SmModel model[RMD_MAX_MODELS];
@@ -75,7 +73,7 @@ __device__ __forceinline__ double bpp_fast(const FastSmem &sm, const double *val
     const uint2 e = sm.U[lo * FAST_WORDS + (hi >> 5)];
     const uint32_t bit = 1u << (hi & 31);
     if (!(e.x & bit)) return 0.0;
-    return vals[e.y + __popc(e.x & (bit - 1))];
+    return __ldg(vals + e.y + __popc(e.x & (bit - 1)));
 }
 
 // __get_bpp_mean (lib/scanner.py:195-214) for one placement per lane: warp-uniform loops over the
@@ -105,7 +103,7 @@ __device__ __forceinline__ bool gate_pass(const CModel &M, Lookup lookup, bool a
 // With no pair summed the reference's mean is 0.0 and is still compared with min_bpp_mean, so a
 // non-positive threshold lets every placement through; every placement is then a candidate.
 
-__global__ void __launch_bounds__(SCAN_THREADS, 8)
+__global__ void __launch_bounds__(SCAN_THREADS, 9)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen) {       // windows [w_begin, w_end); records are relative to w_base
     __shared__ FastSmem sm;
@@ -120,7 +118,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const long long gbase = J.seq_off[seq] + start;
     const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
     const int nnz = (int)(b1 - b0);
-    const double *vals = nnz <= VAL_CAP ? sm.vals : J.bpp_p + b0;
+    const double *vals = J.bpp_p + b0;                        // values stay in global memory (L1): keeping them out
+                                                              // of shared memory buys a ninth resident CTA per SM
     const uint32_t win_local = (uint32_t)(w - w_base);
 
     // ---- stage the window: letters, GC table, bit matrices, model table and tries ------------------
@@ -146,12 +145,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     __syncthreads();
     for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) {     // four entries per thread in flight
         int ei[4], ej[4];
-        double ep[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int e = e0 + k * SCAN_THREADS + tid;
-            ei[k] = ej[k] = 0; ep[k] = 0.0;
-            if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; ep[k] = J.bpp_p[b0 + e]; }
+            ei[k] = ej[k] = 0;
+            if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -161,7 +159,6 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 atomicOr(&sm.S[j * S_STRIDE + (i >> 5)], 1u << (i & 31));
                 atomicOr(&sm.U[i * FAST_WORDS + (j >> 5)].x, 1u << (j & 31));
             }
-            if (e < nnz && e < VAL_CAP) sm.vals[e] = ep[k];
         }
     }
     __syncthreads();
@@ -379,7 +376,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 bool isbig = false;
                 if (e < nnz) {
                     const int i = J.bpp_i[b0 + e], j = J.bpp_j[b0 + e];
-                    const double p = e < VAL_CAP ? sm.vals[e] : J.bpp_p[b0 + e];
+                    const double p = __ldg(vals + e);
                     isbig = p >= big_min && i < j && j < wlen;
                     // i < 160 and j < 160: bit 15 of the i half flags "passes for certain"
                     ij = (uint32_t)i | ((uint32_t)j << 16) | (__ddiv_rn(p, n_slots) >= J.min_bpp ? 0x8000u : 0u);
