@@ -34,6 +34,7 @@ WIN_LEN, WIN_STEP = 150, 75
 MODEL_FILES = ["cl_1", "tga_1", "gb_1", "kt_1"]         # the order os.listdir gave the reference in the build container
 DATA = os.path.join(ROOT, "tests", "golden", "ref_data", "models")
 LN_UNKNOWN, LN_CUTOFF, MIN_BPP = math.log(1e-4), math.log(0.1), 0.001
+NCU_DRAM_BYTES_PER_LAUNCH = 1049848000 + 30227968        # one scan_fast_kernel launch over the 10 Mb workload
 
 
 def load_models():
@@ -176,7 +177,6 @@ def run_ours(args):
         dev_ms += r["ms_total"]; scan_ms += r["ms_scan"]; post_ms += r["ms_post"]; launches += r["n_launches"]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.summary()
     n_hits, n_raw, tries = len(r["hits"]), r["n_raw"], r["tries"]
 
     # ---- end to end through the C ABI with host buffers --------------------------------------------
@@ -197,6 +197,7 @@ def run_ours(args):
         e2e_dev_ms += e["ms_total"]
     barrier()
     e2e_wall = time.perf_counter() - t1
+    clocks = sampler.summary()                                  # sampled over both timed regions
     assert e["tries"] == tries and len(e["hits"]) == n_hits
     d2h = len(e["hits"]) * _native.HIT_DTYPE.itemsize + 2 * n_win * len(models) * 4 + 64
 
@@ -247,7 +248,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_fast_kernel", "peak_source": peak_src,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if args.mb == 10 else None,
+                         "traffic_source": "profiles/r01_scan_fast_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                           "ncu --set full of this command)",
+                         "kernel": "scan_fast_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo),
                          "note": "table-lookup / fp64-compare work: issue-bound, not HBM-bound (see DESIGN.md)"},
             "cpu_baseline": {"value": cpu_val, "unit": "nt·model/s", "cores": cores, "kind": "port",
