@@ -15,11 +15,8 @@
 
 #define FULL_MASK 0xffffffffu
 
-// Per-model data in constant memory: everything that is read warp-uniformly (gate program,
-// first pairs, sizes, table pointers).  Trees and CPTs are read per lane and live in global memory
-// behind the read-only path.
-struct TrieNode { int8_t ro, co; short parent; };   // pair as (row offset from p0, column offset from p1)
-
+// Per-model data in constant memory: everything that is read warp-uniformly (gate program, sizes,
+// table pointers).  Trees and CPTs are read per lane and live in global memory behind the read-only path.
 struct CModel {
     int chain_len[2];
     int symmetric, n_tree, n_cfg, n_first, brute, n_leaves;
@@ -30,15 +27,43 @@ struct CModel {
     const double *ev_table;     // [ev_nclass][ev_nrows]
     const double *ev_thr;       // [ev_nrows]
     int ev_nclass, ev_nrows;
+    int trie0, n_trie;          // this model's nodes in c_trie
+    int xnode0;                 // this model's first node in the concatenated XNode array
     unsigned short cfg_begin[RMD_MAX_GATE_CFGS + 1];
     rmd_gate_pair pairs[RMD_MAX_GATE_PAIRS];
-    // prefix trie of the configurations' pair sequences: a node stands for "this pair is summed", which
-    // requires every ancestor pair to be non-zero (the reference's `break`, lib/scanner.py:204-206)
-    int n_trie;
-    unsigned int trie_magic;             // floor(2^32 / n_trie) + 1: exact division of small indices
-    TrieNode trie[RMD_MAX_GATE_PAIRS];
 };
 __constant__ CModel c_models[RMD_MAX_MODELS];
+
+// Prefix trie of a model's gate configurations (pair sequences), DFS preorder.  A node stands for "this
+// pair is summed", which requires every ancestor pair to be non-zero (the reference's `break`,
+// lib/scanner.py:204-206); `mult` configurations run through it, so its value enters the reference's
+// sum `mult` times.  Indices (parent, skip) are absolute positions in c_trie.
+struct TrieNode {
+    int8_t ro, co;            // pair as (row offset from p0, column offset from p1)
+    uint8_t mult, model;
+    short parent;             // -1: first pair of a configuration
+    unsigned short skip;      // first node after this subtree
+};
+static_assert(sizeof(TrieNode) == 8, "TrieNode layout");
+#define TRIE_CAP 128          // trie nodes of all resident models (checked by rmd_set_models)
+__constant__ TrieNode c_trie[TRIE_CAP];
+
+// Search-tree node as the scoring engine reads it (32 bytes, built by rmd_set_models from
+// rmd_tree_node; all models concatenated, indices absolute).  A letter selector is
+// sh | oft << 8: position = ((p0 | p1 << 16) >> sh & 0xffff) + oft with sh = 0 / 16 for chain 0 / 1;
+// a gap (and an absent parent) has sh = 32 and oft = the sentinel slot that holds the gap code.
+struct XNode {
+    int32_t own, par0, par1;
+    uint32_t cpt;             // index of the node's first CPT entry in the concatenated table
+    uint16_t m0, m1;          // CPT strides of the parents' letters (0: no such parent)
+    uint16_t skip, next;      // node after the subtree / next node in preorder; XNODE_END ends the walk
+    uint16_t leaf;
+    uint8_t model, fb;        // fb = flags | bdepth << 4
+    int16_t ddx, ddy;         // separation distances of a CHECK_DIST node (lib/node.py:184-192), else 0
+};
+static_assert(sizeof(XNode) == 32, "XNode layout");
+#define XNODE_END 0xffffu
+#define LETTER_GAP_SLOT RMD_FAST_WINDOW      // letters[LETTER_GAP_SLOT] holds the gap code (4)
 
 // A resident scan job (device pointers).
 struct DevJob {
@@ -54,6 +79,8 @@ struct DevJob {
     const uint16_t *bpp_i, *bpp_j;
     const double *bpp_p;
     double min_bpp, cutoff;
+    const XNode *xnodes;         // all models' search trees (scoring engine format)
+    const double *xcpt;          // all models' CPTs, concatenated
     int debug;                   // profiling experiments only (RMD_DEBUG): 1 skip scoring, 2 skip the exact gate
 };
 

@@ -35,6 +35,8 @@ struct rmd_ctx {
     std::vector<void *> model_allocs;
     std::vector<void *> ev_allocs[RMD_MAX_MODELS];
     int max_chain = 0;
+    bool any_brute = false;             // some model gives no anchor for candidates: scan_fast_kernel<true>
+    DBuf d_xnodes, d_xcpt;
     // resident job
     bool have_job = false;
     DevJob job{};
@@ -126,7 +128,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
                     &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt,
                     &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
                     &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact,
-                    &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
+                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
     for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
@@ -162,6 +164,12 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     free_models(ctx);
     ctx->hmodels.assign(n_models, CModel{});
     ctx->max_chain = 0;
+    ctx->any_brute = false;
+    int trie_total = 0;
+    TrieNode htrie[TRIE_CAP];
+    memset(htrie, 0, sizeof htrie);
+    std::vector<XNode> hx;
+    std::vector<double> hcpt;
     for (int m = 0; m < n_models; m++) {
         const rmd_model_desc &d = models[m];
         CModel &c = ctx->hmodels[m];
@@ -180,27 +188,53 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
             if ((c.pairs[k].c1 | c.pairs[k].c2) & ~1) return fail(ctx, RMD_E_INVALID, "model %d: gate pair names chain > 1", m);
         }
         c.n_first = d.n_first;
-        c.n_trie = 0;                                    // prefix trie over the configurations' pair sequences
-        for (int g = 0; g < d.n_gate_cfg; g++) {
-            if (d.gate_cfg[g + 1] <= d.gate_cfg[g]) return fail(ctx, RMD_E_INVALID, "model %d: empty gate configuration", m);
-            int parent = -1;
-            for (int k = d.gate_cfg[g]; k < d.gate_cfg[g + 1]; k++) {
-                const rmd_gate_pair q = d.gate_pairs[k];
-                int ro, co;
-                if (q.c1 == q.c2) { c.brute = 1; ro = co = 0; }          // same-chain pair: no anchor for candidates
-                else if (q.c1 == 0) { ro = q.o1; co = q.o2; }
-                else { ro = q.o2; co = q.o1; }
-                int node = -1;
-                for (int t = 0; t < c.n_trie; t++)
-                    if (c.trie[t].parent == parent && c.trie[t].ro == ro && c.trie[t].co == co) { node = t; break; }
-                if (node < 0) {
-                    node = c.n_trie++;
-                    c.trie[node].ro = (int8_t)ro; c.trie[node].co = (int8_t)co; c.trie[node].parent = (short)parent;
+        {   // prefix trie over the configurations' pair sequences, emitted in DFS preorder
+            struct Tmp { int ro, co, parent, mult; std::vector<int> kids; };
+            std::vector<Tmp> tmp;
+            std::vector<int> roots;
+            for (int g = 0; g < d.n_gate_cfg; g++) {
+                if (d.gate_cfg[g + 1] <= d.gate_cfg[g]) return fail(ctx, RMD_E_INVALID, "model %d: empty gate configuration", m);
+                int parent = -1;
+                for (int k = d.gate_cfg[g]; k < d.gate_cfg[g + 1]; k++) {
+                    const rmd_gate_pair q = d.gate_pairs[k];
+                    int ro, co;
+                    if (q.c1 == q.c2) { c.brute = 1; ro = co = 0; }          // same-chain pair: no anchor for candidates
+                    else if (q.c1 == 0) { ro = q.o1; co = q.o2; }
+                    else { ro = q.o2; co = q.o1; }
+                    std::vector<int> &sibs = parent < 0 ? roots : tmp[parent].kids;
+                    int node = -1;
+                    for (int t : sibs) if (tmp[t].ro == ro && tmp[t].co == co) { node = t; break; }
+                    if (node < 0) {
+                        node = (int)tmp.size();
+                        tmp.push_back(Tmp{ro, co, parent, 0, {}});
+                        (parent < 0 ? roots : tmp[parent].kids).push_back(node);
+                    }
+                    tmp[node].mult++;
+                    parent = node;
                 }
-                parent = node;
+            }
+            if (trie_total + (int)tmp.size() > TRIE_CAP)
+                return fail(ctx, RMD_E_LIMIT, "gate programs of the model set too large for shared memory (%d trie nodes, limit %d)", trie_total + (int)tmp.size(), TRIE_CAP);
+            c.trie0 = trie_total; c.n_trie = (int)tmp.size();
+            std::vector<int> pos(tmp.size(), -1);
+            std::vector<std::pair<int, int>> stack;               // (node, next child)
+            for (int rt : roots) {
+                stack.push_back({rt, 0});
+                while (!stack.empty()) {
+                    auto &top = stack.back();
+                    const int nd = top.first;
+                    if (top.second == 0) {
+                        pos[nd] = trie_total++;
+                        TrieNode &tn = htrie[pos[nd]];
+                        if (tmp[nd].mult > 255) return fail(ctx, RMD_E_LIMIT, "model %d: more than 255 configurations share a pair", m);
+                        tn.ro = (int8_t)tmp[nd].ro; tn.co = (int8_t)tmp[nd].co; tn.mult = (uint8_t)tmp[nd].mult; tn.model = (uint8_t)m;
+                        tn.parent = (short)(tmp[nd].parent < 0 ? -1 : pos[tmp[nd].parent]);
+                    }
+                    if (top.second < (int)tmp[nd].kids.size()) { const int kid = tmp[nd].kids[top.second++]; stack.push_back({kid, 0}); }
+                    else { htrie[pos[nd]].skip = (unsigned short)trie_total; stack.pop_back(); }
+                }
             }
         }
-        c.trie_magic = (unsigned int)(0x100000000ULL / (unsigned long long)c.n_trie) + 1u;
         int r;
         rmd_tree_node *tree = nullptr; int32_t *ld = nullptr; double *cpt = nullptr; int8_t *lo = nullptr;
         for (int t = 0; t < d.n_tree; t++)
@@ -210,14 +244,47 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         if ((r = to_device(ctx, d.leaf_dist, (size_t)d.n_leaves * 2, &ld, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.cpt, (size_t)d.n_cpt_rows * RMD_NSYM, &cpt, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, ctx->model_allocs))) return r;
+        {   // the scoring engine's view: pre-decoded nodes, absolute indices, all models concatenated
+            const size_t x0 = hx.size(), cpt0 = hcpt.size();
+            if (x0 + (size_t)d.n_tree >= XNODE_END) return fail(ctx, RMD_E_LIMIT, "search trees of the model set exceed %u nodes", XNODE_END - 1);
+            if (d.n_leaves > 65535) return fail(ctx, RMD_E_LIMIT, "model %d: too many gap configurations", m);
+            c.xnode0 = (int)x0;
+            hcpt.insert(hcpt.end(), d.cpt, d.cpt + (size_t)d.n_cpt_rows * RMD_NSYM);
+            auto selector = [](int chain, int oft) -> int32_t {
+                if (oft < 0) return (int32_t)(32 | (LETTER_GAP_SLOT << 8));            // a gap reads the sentinel slot
+                return (int32_t)((chain ? 16 : 0) | (oft << 8));
+            };
+            for (int t = 0; t < d.n_tree; t++) {
+                const rmd_tree_node &n = d.tree[t];
+                XNode x;
+                memset(&x, 0, sizeof x);
+                x.own = selector(n.chain, n.oft);
+                x.par0 = n.npar > 0 ? selector(n.par_chain[0], n.par_oft[0]) : selector(0, -1);
+                x.par1 = n.npar > 1 ? selector(n.par_chain[1], n.par_oft[1]) : selector(0, -1);
+                x.cpt = (uint32_t)(cpt0 + (size_t)n.cpt_row * RMD_NSYM);
+                x.m0 = n.npar == 1 ? RMD_NSYM : n.npar == 2 ? RMD_NSYM * RMD_NSYM : 0;     // row = c0, or c0 * 6 + c1
+                x.m1 = n.npar == 2 ? RMD_NSYM : 0;
+                x.skip = n.skip >= d.n_tree ? (uint16_t)XNODE_END : (uint16_t)(x0 + n.skip);
+                x.next = t + 1 >= d.n_tree ? (uint16_t)XNODE_END : (uint16_t)(x0 + t + 1);
+                x.leaf = n.leaf; x.model = (uint8_t)m;
+                x.fb = (uint8_t)((n.flags & 0xf) | (n.bdepth << 4));
+                if (n.flags & RMD_F_CHECK_DIST) {
+                    const int dx = d.leaf_dist[2 * n.leaf], dy = d.leaf_dist[2 * n.leaf + 1];
+                    if (dx > 32767 || dy > 32767 || dx < 0 || dy < 0) return fail(ctx, RMD_E_LIMIT, "model %d: separation out of range", m);
+                    x.ddx = (int16_t)dx; x.ddy = (int16_t)dy;
+                }
+                hx.push_back(x);
+            }
+        }
         c.tree = tree; c.leaf_dist = (const int2 *)ld; c.cpt = cpt; c.leaf_offsets = lo;
         c.ev_table = nullptr; c.ev_thr = nullptr; c.ev_nclass = 0; c.ev_nrows = 0;
     }
-    {
-        int nt = 0;
-        for (const CModel &c : ctx->hmodels) nt += c.n_trie;
-        if (nt > TRIE_CAP) return fail(ctx, RMD_E_LIMIT, "gate programs of the model set too large for shared memory (%d trie nodes, limit %d)", nt, TRIE_CAP);
-    }
+    for (const CModel &c : ctx->hmodels) if (c.brute) ctx->any_brute = true;
+    RESERVE(ctx->d_xnodes, sizeof(XNode) * std::max<size_t>(hx.size(), 1));
+    RESERVE(ctx->d_xcpt, sizeof(double) * std::max<size_t>(hcpt.size(), 1));
+    CK(cudaMemcpy(ctx->d_xnodes.p, hx.data(), sizeof(XNode) * hx.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_xcpt.p, hcpt.data(), sizeof(double) * hcpt.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyToSymbol(c_trie, htrie, sizeof htrie));
     ctx->n_models = n_models;
     CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * n_models));
     ctx->have_job = false;
@@ -279,6 +346,7 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
     J.n_win = ctx->h_win_base[n_seq];
     J.debug = getenv("RMD_DEBUG") ? atoi(getenv("RMD_DEBUG")) : 0;
     J.seq_off = (const long long *)ctx->d_seq_off.p; J.win_base = (const long long *)ctx->d_win_base.p;
+    J.xnodes = (const XNode *)ctx->d_xnodes.p; J.xcpt = (const double *)ctx->d_xcpt.p;
     return RMD_OK;
 }
 
@@ -470,7 +538,10 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             }
             if (c1 <= c0) continue;
             if (use_fast) {
-                scan_fast_kernel<<<(unsigned)(c1 - c0), SCAN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
+                if (ctx->any_brute || !(J.min_bpp > 0.0))
+                    scan_fast_kernel<true><<<(unsigned)(c1 - c0), SCAN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
+                else
+                    scan_fast_kernel<false><<<(unsigned)(c1 - c0), SCAN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
                 launches++;
             }
             if (need_generic) {
@@ -482,6 +553,8 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+        if (counters[7] & ERR_BAD_LIST) return fail(ctx, RMD_E_INVALID, "a window's bpp list is not a sorted, duplicate-free upper triangle (i < j < window length)");
+        if (counters[7] & ERR_BAD_VALUE) return fail(ctx, RMD_E_INVALID, "a bpp value is negative or not a number");
         if ((long long)counters[0] <= ctx->raw_cap) break;
         if (attempt == 1) return fail(ctx, RMD_E_NOMEM, "hit buffer overflow persisted (%llu records)", counters[0]);
         ctx->raw_cap = (long long)counters[0] + (long long)counters[0] / 8 + 1024;   // rerun with room for every record

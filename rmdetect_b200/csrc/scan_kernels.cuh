@@ -8,72 +8,89 @@
 //   lib/node.py:176-277     NodeSearch.eval (tree walk, see also eval_placement in device_common.cuh)
 //
 // Design (one CTA of 128 threads per window, windows up to 160 letters):
-//   * the window's bpp coordinate list becomes, in shared memory, a symmetric bit matrix S
-//     ("is this pair non-zero") and an upper-triangle bit matrix with per-word ranks U: the value of
-//     pair (i, j) is entry rank + popc(bits below) of the window's list, read through L1;
+//   * the window's bpp coordinate list becomes, in shared memory, an upper-triangle bit matrix with
+//     per-word ranks: the value of pair (i, j) is entry rank + popc(bits below) of the window's list,
+//     read through L1;
 //   * candidates come from the matrix, not from the 70 000 placements.  The gate mean can reach
 //     min_bpp_mean only if one of the summed values is (within 1e-12) at least min_bpp_mean, and a
 //     pair is summed only if the pairs before it in its configuration are non-zero (the
-//     reference's `break`, lib/scanner.py:204-206).  So every "big" entry (i, j) is matched
-//     against every node of the configurations' prefix trie: the node's pair offsets turn (i, j)
-//     into a placement (p0, p1), its ancestors are checked in S, and a bitmap removes placements
-//     found twice.  Placements never produced this way fail the gate with no work at all;
-//   * candidates go through the reference's exact fp64 gate sum, 32 at a time, the program read
-//     warp-uniformly from constant memory;
+//     reference's `break`, lib/scanner.py:204-206).  So every "big" entry (i, j), in both
+//     orientations, is matched against every node of the configurations' prefix trie: the node's
+//     pair offsets turn (i, j) into a placement (p0, p1), its ancestors are checked in the bit
+//     matrix, and a bitmap removes placements found twice.  A lane owns one (entry, orientation)
+//     and the warp steps through the trie nodes together, so node data are warp-uniform.
+//     Placements never produced this way fail the gate with no work at all;
+//   * a candidate whose generating value alone lifts the mean over the threshold passes for certain;
+//     the others walk the trie lane by lane (depth-first, skipping the subtree of a zero pair) and
+//     form the mean from value x multiplicity.  That sum differs from the reference's
+//     configuration-by-configuration sum only in rounding (< 1e-13 relative), so only a mean within
+//     1e-12 of the threshold is re-summed in the reference's exact order;
 //   * gate survivors are scored by a lane-level engine: every lane carries its own placement and
-//     tree-walk state, visits one tree node per warp iteration, and takes the next placement from
-//     a per-warp shared-memory queue (ballot + popc compaction) the moment it finishes — lanes
-//     never wait for the slowest walk of a batch.  The engine pauses (state kept in registers)
-//     when its queue runs dry and resumes later; it is model-agnostic and drains once per window;
+//     tree-walk state, visits one tree node per warp iteration with branch-free code on a
+//     pre-decoded 32-byte node, and takes the next placement from a per-warp shared-memory queue
+//     the moment it finishes — lanes never wait for the slowest walk of a batch.  The engine
+//     pauses (state kept in registers) when its queue runs dry and resumes later; it is
+//     model-agnostic and drains once per window;
 //   * a hit is appended to the global record list at once; the ordering pass (post_kernels.cuh)
 //     ranks records inside their (window, model) group.
+// scan_fast_kernel<true> is the fallback for a non-positive threshold or a model whose MUST pairs
+// give no anchor (same-chain pair): every placement is a candidate and goes through the exact gate.
 #pragma once
 #include <math_constants.h>
 #include "device_common.cuh"
 
 #define FAST_W RMD_FAST_WINDOW          // 160
 #define FAST_WORDS (FAST_W / 32)        // 5
-#define S_ROWS FAST_W                   // windows no longer than a chain go to the generic kernel, so p + o < 160
-#define S_STRIDE FAST_WORDS
+#define UWORDS (FAST_W * FAST_WORDS)    // 800
 #define SCAN_THREADS 128
 #define SCAN_WARPS (SCAN_THREADS / 32)
-#define QCAP 64
-#define TRIE_CAP 128                    // trie nodes of all resident models (checked by rmd_set_models)
-#define WORDS_PER_THREAD ((FAST_W * FAST_WORDS + SCAN_THREADS - 1) / SCAN_THREADS)   // 7
-#define LANE_NONE 0xffffffffu
-
-struct SmModel {                        // per-model fields the scoring engine reads with a per-lane index
-    const uint4 *tree;
-    const double *cpt;
-    const int2 *leaf_dist;
-    int n_tree, trie_base;
-};
+#define Q1_CAP 64                       // gate candidates per warp: < 32 waiting + 32 pushed at once
+#define Q2_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
+#ifndef BIG_CAP
+#define BIG_CAP 512                     // entries looked at per round of candidate generation
+#endif
+#ifndef CB_MODELS
+#define CB_MODELS 4                     // models whose duplicate bitmaps are resident together
+#endif
+#ifndef SCAN_MIN_CTAS
+#define SCAN_MIN_CTAS 9
+#endif
+#define WORDS_PER_THREAD ((UWORDS + SCAN_THREADS - 1) / SCAN_THREADS)   // 7
+#define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a sorted, unique upper triangle
+#define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
 struct FastSmem {
-    uint32_t S[S_ROWS * S_STRIDE];
-    uint2 U[FAST_W * FAST_WORDS];        // .x = bits (j > i), .y = entries before this word in list order
-    double gc[RMD_N_CODES];
-    uint32_t CB[2][FAST_W * FAST_WORDS]; // candidates already queued, alternating between models
-    SmModel model[RMD_MAX_MODELS];
-    uint32_t q1[SCAN_WARPS][QCAP];       // gate candidates (p0 | p1 << 16)
-    uint32_t q2[SCAN_WARPS][QCAP];       // gate survivors  (p0 | p1 << 16), model in q2m
+    uint32_t Ub[UWORDS];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
+    uint16_t Ur[UWORDS];                 // entries before this word in list order
+    uint32_t CB[CB_MODELS][UWORDS];      // placements already queued, per model of the current group
+    uint32_t big[BIG_CAP];               // big entries of the round: i | j << 8 | sure-mask << 16
+    uint32_t q1[SCAN_WARPS][Q1_CAP];     // gate candidates  p0 | p1 << 8 | model << 16
+    uint32_t q2[SCAN_WARPS][Q2_CAP];     // gate survivors, same format
     TrieNode trie[TRIE_CAP];
-    uint32_t big[SCAN_WARPS][32];        // big entries of the current chunk (i | j << 16)
-    uint8_t q2m[SCAN_WARPS][QCAP];
-    uint32_t scan_tmp[SCAN_WARPS + 1];
+    double gc[RMD_N_CODES];
+    double sure_min[RMD_MAX_MODELS];     // a generating value >= this passes the gate for certain
+    uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
-    uint8_t letters[S_ROWS];
+    uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
+    uint32_t scan_tmp[SCAN_WARPS + 1];
+    uint32_t nbig[2];
+    uint8_t letters[FAST_W + 16];        // slot LETTER_GAP_SLOT holds the gap code
 };
 
-// bpp lookup by popcount rank (lib/bpprobs.py:17-18): 0.0 unless the pair is stored.  The diagonal
-// is never stored, so b1 == b2 needs no test of its own.
+// is pair (b1, b2) stored?  (lib/bpprobs.py:17-18; the diagonal is never stored)
+__device__ __forceinline__ bool bpp_present(const FastSmem &sm, int wlen, int b1, int b2) {
+    const int lo = min(b1, b2), hi = max(b1, b2);
+    return hi < wlen && ((sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u);
+}
+
+// bpp lookup by popcount rank: 0.0 unless the pair is stored
 __device__ __forceinline__ double bpp_fast(const FastSmem &sm, const double *vals, int wlen, int b1, int b2) {
-    const int lo = b1 < b2 ? b1 : b2, hi = b1 < b2 ? b2 : b1;
+    const int lo = min(b1, b2), hi = max(b1, b2);
     if (hi >= wlen) return 0.0;
-    const uint2 e = sm.U[lo * FAST_WORDS + (hi >> 5)];
-    const uint32_t bit = 1u << (hi & 31);
-    if (!(e.x & bit)) return 0.0;
-    return __ldg(vals + e.y + __popc(e.x & (bit - 1)));
+    const int k = lo * FAST_WORDS + (hi >> 5);
+    const uint32_t w = sm.Ub[k], bit = 1u << (hi & 31);
+    if (!(w & bit)) return 0.0;
+    return __ldg(vals + sm.Ur[k] + __popc(w & (bit - 1)));
 }
 
 // __get_bpp_mean (lib/scanner.py:195-214) for one placement per lane: warp-uniform loops over the
@@ -103,7 +120,8 @@ __device__ __forceinline__ bool gate_pass(const CModel &M, Lookup lookup, bool a
 // With no pair summed the reference's mean is 0.0 and is still compared with min_bpp_mean, so a
 // non-positive threshold lets every placement through; every placement is then a candidate.
 
-__global__ void __launch_bounds__(SCAN_THREADS, 9)
+template <bool BRUTE>
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen) {       // windows [w_begin, w_end); records are relative to w_base
     __shared__ FastSmem sm;
@@ -118,29 +136,34 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const long long gbase = J.seq_off[seq] + start;
     const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
     const int nnz = (int)(b1 - b0);
-    const double *vals = J.bpp_p + b0;                        // values stay in global memory (L1): keeping them out
-                                                              // of shared memory buys a ninth resident CTA per SM
+    const double *vals = J.bpp_p + b0;                        // values stay in global memory (L1)
     const uint32_t win_local = (uint32_t)(w - w_base);
+    const int n_models = J.n_models;
 
-    // ---- stage the window: letters, GC table, bit matrices, model table and tries ------------------
-    for (int k = tid; k < S_ROWS * S_STRIDE; k += SCAN_THREADS) sm.S[k] = 0;
-    for (int k = tid; k < FAST_W * FAST_WORDS; k += SCAN_THREADS) { sm.U[k] = make_uint2(0, 0); sm.CB[0][k] = 0; }
-    for (int k = tid; k < S_ROWS; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
+    // ---- stage the window: letters, GC table, bit matrix with ranks, model tables ------------------
+    for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
+    for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+    for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS)
+        sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : (k == LETTER_GAP_SLOT ? 4 : 0);
     if (tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
-    if (tid < RMD_MAX_MODELS) sm.gate_pass[tid] = 0;
+    if (tid < n_models) {
+        const CModel &M = c_models[tid];
+        sm.gate_pass[tid] = 0;
+        sm.xnode0[tid] = (uint16_t)M.xnode0;
+        sm.trie0[tid] = (uint16_t)M.trie0;
+        sm.trie_end[tid] = (uint16_t)(M.trie0 + M.n_trie);
+        // odometer ranges (lib/scanner.py:161-193): p0 < n0; p1 from lo (p0 when SYMMETRIC) to max(hi, lo)
+        sm.bounds[tid] = (uint32_t)rows_of(wlen, M.chain_len[0]) | ((uint32_t)max(wlen - M.chain_len[1] - 1, 0) << 8) |
+                         (M.symmetric ? 1u << 16 : 0u);
+        // mean = sum / count >= p / slots: sum >= p (positive terms, monotone rounding), count <= slots,
+        // division monotone; the factor covers the rounding of the product and of that division
+        const double slots = (double)M.cfg_begin[M.n_cfg];
+        sm.sure_min[tid] = J.min_bpp * slots * (1.0 + 1e-12);
+    }
+    if (tid < 2) sm.nbig[tid] = 0;
     {
-        int tb = 0;                                           // same layout for every thread
-        for (int m = 0; m < J.n_models; m++) {
-            const CModel &M = c_models[m];
-            for (int k = tid; k < M.n_trie; k += SCAN_THREADS) sm.trie[tb + k] = M.trie[k];
-            if (tid == 0) {
-                SmModel r;
-                r.tree = reinterpret_cast<const uint4 *>(M.tree); r.cpt = M.cpt; r.leaf_dist = M.leaf_dist;
-                r.n_tree = M.n_tree; r.trie_base = tb;
-                sm.model[m] = r;
-            }
-            tb += M.n_trie;
-        }
+        const int nt = c_models[n_models - 1].trie0 + c_models[n_models - 1].n_trie;
+        for (int k = tid; k < nt; k += SCAN_THREADS) sm.trie[k] = c_trie[k];
     }
     __syncthreads();
     for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) {     // four entries per thread in flight
@@ -154,114 +177,88 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int e = e0 + k * SCAN_THREADS + tid, i = ei[k], j = ej[k];
-            if (e < nnz && i < j && j < wlen) {
-                atomicOr(&sm.S[i * S_STRIDE + (j >> 5)], 1u << (j & 31));
-                atomicOr(&sm.S[j * S_STRIDE + (i >> 5)], 1u << (i & 31));
-                atomicOr(&sm.U[i * FAST_WORDS + (j >> 5)].x, 1u << (j & 31));
-            }
+            if (e < nnz && i < j && j < wlen) atomicOr(&sm.Ub[i * FAST_WORDS + (j >> 5)], 1u << (j & 31));
         }
     }
     __syncthreads();
-    {   // rank of the first bit of every U word = its position in the (i, j)-sorted list
+    {   // rank of the first bit of every word = its position in the (i, j)-sorted list
         uint32_t mine = 0;
         const int k0 = tid * WORDS_PER_THREAD;
 #pragma unroll
         for (int k = 0; k < WORDS_PER_THREAD; k++)
-            if (k0 + k < FAST_W * FAST_WORDS) mine += __popc(sm.U[k0 + k].x);
+            if (k0 + k < UWORDS) mine += __popc(sm.Ub[k0 + k]);
         uint32_t total, run = block_exclusive_scan<SCAN_THREADS>(mine, sm.scan_tmp, &total);
 #pragma unroll
         for (int k = 0; k < WORDS_PER_THREAD; k++)
-            if (k0 + k < FAST_W * FAST_WORDS) { sm.U[k0 + k].y = run; run += __popc(sm.U[k0 + k].x); }
+            if (k0 + k < UWORDS) { sm.Ur[k0 + k] = (uint16_t)run; run += __popc(sm.Ub[k0 + k]); }
+        // the ranks are list positions only if every entry set its own bit
+        if (tid == 0 && total != (uint32_t)nnz) atomicOr(&O.raw_count[7], ERR_BAD_LIST);
     }
-    // a mean of values all below big_min stays below min_bpp: (1 + 2^-53)^256 < 1 + 1e-12
-    const bool all_candidates = !(J.min_bpp > 0.0);
-    const double big_min = J.min_bpp - J.min_bpp * 1e-12;
+    __syncthreads();
 
     auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
-    uint32_t *q1 = sm.q1[wid], *q2 = sm.q2[wid], *bigl = sm.big[wid];
-    uint8_t *q2m = sm.q2m[wid];
+    uint32_t *q1 = sm.q1[wid], *q2 = sm.q2[wid];
     int qn1 = 0, qn2 = 0;                                   // warp-uniform queue fills
+    const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (lib/node.py:248)
+    const bool no_score = !root_ok || (J.debug & 1);
 
     // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ----------
-    uint32_t e_c = LANE_NONE;                               // placement in flight (p0 | p1 << 16)
-    int e_m = 0, e_t = 0, e_leaf = -1;
+    const uint4 *xn = reinterpret_cast<const uint4 *>(J.xnodes);
+    uint32_t e_c = 0, e_t = XNODE_END;                      // placement p0 | p1 << 16; node (XNODE_END: lane idle)
+    int e_leaf = -1;                                        // best leaf | model << 16
     double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
-    double e_sp[RMD_MAX_BRANCH_DEPTH + 1], e_sr[RMD_MAX_BRANCH_DEPTH + 1];
-    const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (:248)
+    double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
     unsigned long long dbg_iter = 0, dbg_visits = 0;        // RMD_DEBUG & 8: engine statistics
 
-    auto eval_engine = [&](const bool drain) {
-        uint32_t bm = __ballot_sync(FULL_MASK, e_c != LANE_NONE);      // busy lanes, kept current below
+    auto engine = [&](const bool drain) {
+        uint32_t bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);     // busy lanes, kept current below
         for (;;) {
             if (qn2 > 0 && bm != FULL_MASK) {                // hand queued survivors to idle lanes
                 const uint32_t im = ~bm;
                 const int r = __popc(im & lt_mask);
-                const bool take = (im >> lane & 1) && r < qn2;
-                if (take) {
-                    e_c = q2[qn2 - 1 - r]; e_m = q2m[qn2 - 1 - r];
-                    e_t = 0; e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;
-                    e_sp[0] = 0.0; e_sr[0] = 0.0;
+                if ((im >> lane & 1) && r < qn2) {
+                    const uint32_t c = q2[qn2 - 1 - r];
+                    e_c = (c & 0xffu) | ((c & 0xff00u) << 8);
+                    e_t = sm.xnode0[c >> 16];
+                    e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
+                    e_stk[0] = make_double2(0.0, 0.0);
                 }
                 qn2 -= min(qn2, __popc(im));
-                bm = __ballot_sync(FULL_MASK, e_c != LANE_NONE);
+                bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
             }
             if (bm == 0) break;
             if (!drain && qn2 == 0 && bm != FULL_MASK) break;   // pause: nothing left to keep every lane fed
             if (J.debug & 8) { dbg_iter++; dbg_visits += __popc(bm); }
-            const bool busy = bm >> lane & 1;
-            bool done = false;
+            const bool busy = e_t != XNODE_END;
             if (busy) {
-                const SmModel R = sm.model[e_m];
-                const int p0 = e_c & 0xffff, p1 = e_c >> 16;
-                if (e_t >= R.n_tree || !root_ok) done = true;
-                else {
-                    const uint4 raw = __ldg(R.tree + e_t);
-                    const int chain = (int)(int8_t)(raw.x & 0xff), oft = (int)(int8_t)((raw.x >> 8) & 0xff);
-                    const int flags = (raw.y >> 16) & 0xff, bdepth = raw.y >> 24;
-                    const int skip = raw.z >> 16;
-                    bool dead = false;
-                    if (flags & RMD_F_RESTORE) { e_pm = e_sp[bdepth - 1]; e_pr = e_sr[bdepth - 1]; }
-                    if (flags & RMD_F_CHECK_DIST) {                           // lib/node.py:184-192
-                        const int2 dd = __ldg(R.leaf_dist + (raw.z & 0xffff));
-                        const int d = p1 - p0;
-                        dead = (d >= 0 && d < dd.x) || (d <= 0 && -d < dd.y);
-                    }
-                    if (!dead) {
-                        const int nt = oft < 0 ? 4 : sm.letters[(chain ? p1 : p0) + oft];     // :199-204
-                        int row = 0;
-                        const int npar = (raw.w >> 16) & 0xff;
-                        if (npar > 0) {                                       // :207-213
-                            const int pc0 = (int)(int8_t)((raw.x >> 16) & 0xff), po0 = (int)(int8_t)(raw.y & 0xff);
-                            int c = po0 < 0 ? 4 : sm.letters[(pc0 ? p1 : p0) + po0];
-                            row = c < 5 ? c : 5;
-                            if (npar > 1) {
-                                const int pc1 = (int)(int8_t)(raw.x >> 24), po1 = (int)(int8_t)((raw.y >> 8) & 0xff);
-                                c = po1 < 0 ? 4 : sm.letters[(pc1 ? p1 : p0) + po1];
-                                row = row * RMD_NSYM + (c < 5 ? c : 5);
-                            }
-                        }
-                        double v = __ldg(R.cpt + ((raw.w & 0xffff) + row) * RMD_NSYM + (nt < 5 ? nt : 5));
-                        const double g = sm.gc[nt];                           // :223 (slot 4 holds log 0.25)
-                        if (v == CUDART_INF) v = g;                           // GC-sentinel row (:217-218)
-                        e_pm = __dadd_rn(e_pm, v);                            // :227-228
-                        e_pr = __dadd_rn(e_pr, g);
-                        dead = !(e_pm >= __dadd_rn(e_pr, J.cutoff));          // :248
-                    }
-                    if (dead) e_t = skip;
-                    else {
-                        if (flags & RMD_F_LEAF) {
-                            if (e_pm > e_bpm) { e_bpm = e_pm; e_bpr = e_pr; e_leaf = raw.z & 0xffff; }   // :265-275
-                        } else if (flags & RMD_F_SAVE) {
-                            e_sp[bdepth] = e_pm; e_sr[bdepth] = e_pr;
-                        }
-                        e_t++;
-                    }
-                    done = e_t >= R.n_tree;
+                const uint4 a = __ldg(xn + 2 * e_t), b = __ldg(xn + 2 * e_t + 1);
+                auto letter = [&](const uint32_t sel) {
+                    return (int)sm.letters[(__funnelshift_rc(e_c, 0u, sel & 0xffu) & 0xffffu) + ((int)sel >> 8)];
+                };
+                const int nt = letter(a.x), c0 = letter(a.y), c1 = letter(a.z);         // :199-213
+                const uint32_t idx = a.w + min(nt, 5) + min(c0, 5) * (b.x & 0xffffu) + min(c1, 5) * (b.x >> 16);
+                double v = __ldg(J.xcpt + idx);
+                const double g = sm.gc[nt];                           // :223 (slot 4 holds log 0.25)
+                if (v == CUDART_INF) v = g;                           // GC-sentinel row (:217-218)
+                const uint32_t fl = b.z;                              // leaf | model << 16 | flags << 24 | bdepth << 28
+                const int bdepth = fl >> 28;
+                if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
+                const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);                   // :184-192 (0, 0 unless CHECK_DIST)
+                const int ddx = (int)(short)(b.w & 0xffffu), ddy = (int)(short)(b.w >> 16);
+                const bool apart = !((d >= 0 && d < ddx) || (d <= 0 && -d < ddy));
+                e_pm = __dadd_rn(e_pm, v);                            // :227-228
+                e_pr = __dadd_rn(e_pr, g);
+                // a node that fails is left through its skip link, and whatever comes next restores the sums
+                const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);           // :248
+                if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {                // :265-275
+                    e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
                 }
+                if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
+                e_t = alive ? (b.y >> 16) : (b.y & 0xffffu);
             }
-            const uint32_t dm = __ballot_sync(FULL_MASK, done);
+            const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
             if (dm == 0) continue;
-            const bool hit = done && e_leaf >= 0;
+            const bool hit = busy && e_t == XNODE_END && e_leaf >= 0;
             const uint32_t hm = __ballot_sync(FULL_MASK, hit);
             if (hm) {                                         // append records: one atomic per warp iteration
                 unsigned long long base = 0;
@@ -269,81 +266,78 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 base = __shfl_sync(FULL_MASK, base, __ffs(hm) - 1);
                 if (hit) {
                     const unsigned long long slot = base + __popc(hm & lt_mask);
+                    const int model = e_leaf >> 16;
                     if ((long long)slot < O.raw_cap) {
                         RawHit h;
                         h.window = win_local;
-                        h.p0 = (uint16_t)(e_c & 0xffff); h.p1 = (uint16_t)(e_c >> 16);
-                        h.model = (uint16_t)e_m; h.leaf = (uint16_t)e_leaf;
+                        h.p0 = (uint16_t)(e_c & 0xffffu); h.p1 = (uint16_t)(e_c >> 16);
+                        h.model = (uint16_t)model; h.leaf = (uint16_t)(e_leaf & 0xffff);
                         h.rank = 0;
                         h.pm = e_bpm; h.pr = e_bpr;
                         O.raw[slot] = h;
                     }
-                    atomicAdd(&O.group_hits[(long long)win_local * J.n_models + e_m], 1u);
+                    atomicAdd(&O.group_hits[(long long)win_local * n_models + model], 1u);
                 }
             }
-            if (done) e_c = LANE_NONE;
             bm &= ~dm;
-            __syncwarp();
         }
     };
 
+    // ---- gate on up to 32 queued candidates --------------------------------------------------------
+    const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
+    auto gate_batch = [&](const int nbatch, const int brute_model) {
+        const bool act = lane < nbatch;
+        const uint32_t c = act ? q1[qn1 - nbatch + lane] : 0;
+        qn1 -= nbatch;
+        __syncwarp();
+        const int p0 = c & 0xff, p1 = (c >> 8) & 0xff, m = c >> 16;
+        bool pass;
+        if (BRUTE) {
+            pass = gate_pass(c_models[brute_model], lookup, act, p0, p1, J.min_bpp);
+        } else {
+            // depth-first over the model's trie: a zero pair closes its subtree (the `break`)
+            int t = act ? sm.trie0[m] : 0;
+            const int tend = act ? sm.trie_end[m] : 0;
+            double sum = 0.0;
+            int cnt = 0;
+            while (__any_sync(FULL_MASK, t < tend)) {
+                if (t < tend) {
+                    const TrieNode tn = sm.trie[t];
+                    const double v = lookup(p0 + tn.ro, p1 + tn.co);
+                    if (v != 0.0) { sum = __dadd_rn(sum, __dmul_rn(v, (double)tn.mult)); cnt += tn.mult; t++; }
+                    else t = tn.skip;
+                }
+            }
+            const double mean = cnt ? __ddiv_rn(sum, (double)cnt) : 0.0;
+            pass = act && mean >= thr_hi;
+            const bool unsure = act && !pass && mean >= thr_lo;
+            uint32_t um = __ballot_sync(FULL_MASK, unsure);
+            while (um) {                                      // the reference's own sum, one model at a time
+                const int mm = __shfl_sync(FULL_MASK, m, __ffs(um) - 1);
+                const bool mine = unsure && m == mm;
+                if (gate_pass(c_models[mm], lookup, mine, p0, p1, J.min_bpp)) pass = true;
+                um &= ~__ballot_sync(FULL_MASK, mine);
+            }
+        }
+        const uint32_t pmask = __ballot_sync(FULL_MASK, pass);
+        if (pass) { q2[qn2 + __popc(pmask & lt_mask)] = c; atomicAdd(&sm.gate_pass[m], 1u); }
+        qn2 += __popc(pmask);
+        __syncwarp();
+    };
+    auto consume = [&](const bool drain, const int brute_model) {
+        if (drain) { while (qn1 > 0) gate_batch(min(qn1, 32), brute_model); }
+        else if (qn1 >= 32) gate_batch(32, brute_model);
+        if (no_score) qn2 = 0;
+        if (qn2 >= 32) engine(false);
+    };
+
     unsigned long long tests_all = 0;
-    for (int m = 0; m < J.n_models; m++) {
-        const CModel &M = c_models[m];
-        const int L0 = M.chain_len[0], L1 = M.chain_len[1];
-        const int n0 = rows_of(wlen, L0);
-        uint32_t *CB = sm.CB[m & 1];
-        uint32_t npass = 0, n_cand = 0;
-        // every warp has finished candidate generation of model m - 1: its bitmap can be cleared for
-        // model m + 1 (this model's bitmap was cleared one phase ago, or by the staging code)
-        __syncthreads();
-        for (int k = tid; k < FAST_W * FAST_WORDS; k += SCAN_THREADS) sm.CB[(m + 1) & 1][k] = 0;
-
-        auto gate_batch = [&](const int nbatch) {               // exact gate on up to 32 candidates
-            const bool act = lane < nbatch;
-            const uint32_t c = act ? q1[qn1 - nbatch + lane] : 0;
-            qn1 -= nbatch;
-            __syncwarp();
-            const bool pass = gate_pass(M, lookup, act, (int)(c & 0xffff), (int)(c >> 16), J.min_bpp) && !(J.debug & 2);
-            const uint32_t pmask = __ballot_sync(FULL_MASK, pass);
-            if (pass) { const int at = qn2 + __popc(pmask & lt_mask); q2[at] = c; q2m[at] = (uint8_t)m; }
-            qn2 += __popc(pmask);
-            npass += __popc(pmask);
-            __syncwarp();
-            if (J.debug & 1) qn2 = 0;
-            if (qn2 >= 32) eval_engine(false);
-        };
-        // a candidate whose generating value p satisfies p / (pairs in the program) >= min_bpp_mean passes
-        // for certain: the fp64 sum is >= p (positive terms, monotone rounding), the count <= that total,
-        // and division is monotone — so it skips the exact sum and is queued for scoring directly
-        const double n_slots = (double)M.cfg_begin[M.n_cfg];
-        auto push_survivors = [&](const bool has, const uint32_t cand) {
-            const uint32_t pmask = __ballot_sync(FULL_MASK, has && !(J.debug & 2));
-            if (pmask) {
-                if (pmask >> lane & 1) { const int at = qn2 + __popc(pmask & lt_mask); q2[at] = cand; q2m[at] = (uint8_t)m; }
-                qn2 += __popc(pmask);
-                npass += __popc(pmask);
-                n_cand += __popc(pmask);
-                __syncwarp();
-                if (J.debug & 1) qn2 = 0;
-                if (qn2 >= 32) eval_engine(false);
-            }
-        };
-        auto push_candidates = [&](const bool has, const uint32_t cand) {
-            const uint32_t pmask = __ballot_sync(FULL_MASK, has);
-            if (pmask) {
-                if (has) q1[qn1 + __popc(pmask & lt_mask)] = cand;
-                qn1 += __popc(pmask);
-                n_cand += __popc(pmask);
-                __syncwarp();
-                if (J.debug & 4) qn1 = 0;
-                if (qn1 >= 32) gate_batch(32);
-            }
-        };
-
-        if (all_candidates || M.brute) {
-            // every placement of the odometer is a candidate (non-positive threshold, or a model
-            // whose MUST pairs sit on one chain and so give no anchor): 32 placements per lane word
+    if (BRUTE) {
+        // every placement of the odometer is a candidate: 32 placements per lane word
+        for (int m = 0; m < n_models; m++) {
+            const CModel &M = c_models[m];
+            const int L1 = M.chain_len[1];
+            const int n0 = rows_of(wlen, M.chain_len[0]);
             const int p1_max = p1_last(wlen, L1, M.symmetric ? n0 - 1 : 0);
             const int nw = (p1_max >> 5) + 1;
             const int items = n0 * nw;
@@ -364,63 +358,87 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const bool has = cw != 0;
                     const int b = has ? __ffs(cw) - 1 : 0;
                     cw &= cw - 1;
-                    push_candidates(has, (uint32_t)p0 | ((uint32_t)((wd << 5) + b) << 16));
+                    const uint32_t pmask = __ballot_sync(FULL_MASK, has);
+                    if (has) q1[qn1 + __popc(pmask & lt_mask)] = (uint32_t)p0 | ((uint32_t)((wd << 5) + b) << 8) | ((uint32_t)m << 16);
+                    qn1 += __popc(pmask);
+                    __syncwarp();
+                    consume(false, m);
                 }
             }
-        } else {
-            // big entries x trie nodes -> placements (see the header of this file)
-            const int tb = sm.model[m].trie_base, T = M.n_trie;
-            for (int e0 = wid * 32; e0 < nnz; e0 += SCAN_THREADS) {
-                const int e = e0 + lane;
-                uint32_t ij = 0;
-                bool isbig = false;
-                if (e < nnz) {
-                    const int i = J.bpp_i[b0 + e], j = J.bpp_j[b0 + e];
+            consume(true, m);                                    // the exact gate reads one model's program
+        }
+    } else {
+        // big entries x trie nodes -> placements (see the header of this file)
+        const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
+        int round = 0;
+        for (int g0 = 0; g0 < n_models; g0 += CB_MODELS) {
+            const int g1 = min(g0 + CB_MODELS, n_models);
+            const int tg0 = c_models[g0].trie0, tg1 = c_models[g1 - 1].trie0 + c_models[g1 - 1].n_trie;
+            if (g0 > 0) {                                        // bitmaps of the next group of models
+                __syncthreads();
+                for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+            }
+            for (int eb = 0; eb < nnz; eb += BIG_CAP, round++) {
+                // ---- the round's big entries, compacted (order is irrelevant) -----------------------
+                uint32_t *nbig_p = &sm.nbig[round & 1];
+                for (int e = eb + tid; e < min(eb + BIG_CAP, nnz); e += SCAN_THREADS) {
                     const double p = __ldg(vals + e);
-                    isbig = p >= big_min && i < j && j < wlen;
-                    // i < 160 and j < 160: bit 15 of the i half flags "passes for certain"
-                    ij = (uint32_t)i | ((uint32_t)j << 16) | (__ddiv_rn(p, n_slots) >= J.min_bpp ? 0x8000u : 0u);
+                    if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
+                    if (p >= big_min) {
+                        uint32_t sure = 0;
+                        for (int m = g0; m < g1; m++) sure |= (p >= sm.sure_min[m] ? 1u : 0u) << m;
+                        const uint32_t i = J.bpp_i[b0 + e], j = J.bpp_j[b0 + e];
+                        sm.big[atomicAdd(nbig_p, 1u)] = i | (j << 8) | (sure << 16);
+                    }
                 }
-                const uint32_t bmask = __ballot_sync(FULL_MASK, isbig);
-                if (bmask == 0) continue;
-                if (isbig) bigl[__popc(bmask & lt_mask)] = ij;
-                __syncwarp();
-                const int combos = __popc(bmask) * 2 * T;         // entry x orientation x trie node
-                for (int c0 = 0; c0 < combos; c0 += 32) {
-                    const int cx = c0 + lane;
-                    bool ok = cx < combos, sure = false;
-                    uint32_t cand = 0;
-                    if (ok) {
-                        const int eo = (int)__umulhi((unsigned)cx, M.trie_magic), node = cx - eo * T;
-                        const uint32_t en = bigl[eo >> 1];
-                        sure = en & 0x8000u;
-                        const int row = (eo & 1) ? (int)(en >> 16) : (int)(en & 0x7fff);
-                        const int col = (eo & 1) ? (int)(en & 0x7fff) : (int)(en >> 16);
-                        TrieNode tn = sm.trie[tb + node];
-                        const int p0 = row - tn.ro, p1 = col - tn.co;
-                        const int lo = M.symmetric ? p0 : 0;
-                        ok = p0 >= 0 && p0 < n0 && p1 >= lo && p1 <= p1_last(wlen, L1, lo);
-                        while (ok && tn.parent >= 0) {            // every pair before it must be non-zero
-                            tn = sm.trie[tb + tn.parent];
-                            const int r = p0 + tn.ro, c = p1 + tn.co;
-                            ok = (sm.S[r * S_STRIDE + (c >> 5)] >> (c & 31)) & 1;
+                __syncthreads();
+                const int items = 2 * (int)*nbig_p;                // (entry, orientation)
+                if (tid == 0) sm.nbig[(round + 1) & 1] = 0;        // the other counter is idle until the next round's barrier
+                for (int row = wid * 32; row < items; row += SCAN_THREADS) {
+                    const int it = row + lane;
+                    const bool valid = it < items;
+                    const uint32_t en = sm.big[valid ? it >> 1 : 0];
+                    const int er = (it & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
+                    const int ec = (it & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
+                    for (int t = tg0; t < tg1; t++) {            // warp-uniform trie node
+                        const TrieNode tn = sm.trie[t];
+                        const uint32_t bd = sm.bounds[tn.model];
+                        const int p0 = er - tn.ro, p1 = ec - tn.co;
+                        const int lo = (bd >> 16) ? p0 : 0;
+                        bool ok = valid && (unsigned)p0 < (bd & 0xffu) && p1 >= lo && (p1 <= (int)((bd >> 8) & 0xffu) || p1 == lo);
+                        for (int a = tn.parent; a >= 0 && __any_sync(FULL_MASK, ok);) {   // every pair before it must be non-zero
+                            const TrieNode an = sm.trie[a];
+                            if (ok) ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
+                            a = an.parent;
                         }
                         if (ok) {
                             const uint32_t bit = 1u << (p1 & 31);
-                            ok = !(atomicOr(&CB[p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
-                            cand = (uint32_t)p0 | ((uint32_t)p1 << 16);
+                            ok = !(atomicOr(&sm.CB[tn.model - g0][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
                         }
+                        const uint32_t om = __ballot_sync(FULL_MASK, ok);
+                        if (om == 0) continue;
+                        const bool sure = ok && ((en >> (16 + tn.model)) & 1u);
+                        const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
+                        const uint32_t item = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)tn.model << 16);
+                        if (sure) q2[qn2 + __popc(smask & lt_mask)] = item;
+                        else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
+                        qn2 += __popc(smask);
+                        qn1 += __popc(cmask);
+                        if (lane == 0 && smask) atomicAdd(&sm.gate_pass[tn.model], (uint32_t)__popc(smask));
+                        __syncwarp();
+                        consume(false, 0);
                     }
-                    push_survivors(ok && sure, cand);
-                    push_candidates(ok && !sure, cand);
                 }
-                __syncwarp();
+                __syncthreads();                                  // the list is rewritten by the next round
             }
         }
-        if (qn1 > 0) gate_batch(qn1);
-        if (lane == 0 && npass) atomicAdd(&sm.gate_pass[m], npass);
-        if (lane == 0 && n_cand && J.debug) atomicAdd(&O.raw_count[3], (unsigned long long)n_cand);
-        if (tid == 0) {                                         // tests_all: closed form of the odometer
+        consume(true, 0);
+    }
+    if (tid == 0) {                                             // tests_all: closed form of the odometer
+        for (int m = 0; m < n_models; m++) {
+            const CModel &M = c_models[m];
+            const int L1 = M.chain_len[1];
+            const int n0 = rows_of(wlen, M.chain_len[0]);
             if (M.symmetric) {                                  // sum over p0 < n0 of max(1, A - p0), A = wlen - L1
                 const long long A = wlen - L1, k = A > 0 ? (A < n0 ? A : n0) : 0;
                 tests_all += (unsigned long long)(k * A - k * (k - 1) / 2 + (n0 - k));
@@ -429,11 +447,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             }
         }
     }
-    if (J.debug & 1) qn2 = 0;
-    eval_engine(true);
+    if (no_score) qn2 = 0;
+    engine(true);
     __syncthreads();
-    if (tid < J.n_models) {
-        O.gate_pass[(long long)win_local * J.n_models + tid] = sm.gate_pass[tid];
+    if (tid < n_models) {
+        O.gate_pass[(long long)win_local * n_models + tid] = sm.gate_pass[tid];
         if (sm.gate_pass[tid]) atomicAdd(&O.raw_count[2], (unsigned long long)sm.gate_pass[tid]);
     }
     if (tid == 0) atomicAdd(&O.raw_count[1], tests_all);
