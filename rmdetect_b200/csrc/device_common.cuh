@@ -41,12 +41,15 @@ __constant__ CModel c_models[RMD_MAX_MODELS];
 struct TrieNode {
     int8_t ro, co;            // pair as (row offset from p0, column offset from p1)
     uint8_t mult, model;
-    short parent;             // -1: first pair of a configuration
+    int8_t parent;            // -1: first pair of a configuration
+    uint8_t pbit;             // index into c_prel of (parent pair - this pair); 31: no parent
     unsigned short skip;      // first node after this subtree
 };
 static_assert(sizeof(TrieNode) == 8, "TrieNode layout");
 #define TRIE_CAP 128          // trie nodes of all resident models (checked by rmd_set_models)
 __constant__ TrieNode c_trie[TRIE_CAP];
+__constant__ uint16_t c_prel[32];   // distinct (parent - node) offsets over all tries: (dr & 0xff) | (dc & 0xff) << 8
+__constant__ int c_n_prel;
 
 // Search-tree node as the scoring engine reads it (32 bytes, built by rmd_set_models from
 // rmd_tree_node; all models concatenated, indices absolute).  A letter selector is

@@ -169,6 +169,9 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     TrieNode htrie[TRIE_CAP];
     memset(htrie, 0, sizeof htrie);
     std::vector<XNode> hx;
+    uint16_t hprel[32] = {0};
+    int n_prel = 0;
+    bool prel_overflow = false;
     std::vector<double> hcpt;
     for (int m = 0; m < n_models; m++) {
         const rmd_model_desc &d = models[m];
@@ -228,7 +231,19 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
                         TrieNode &tn = htrie[pos[nd]];
                         if (tmp[nd].mult > 255) return fail(ctx, RMD_E_LIMIT, "model %d: more than 255 configurations share a pair", m);
                         tn.ro = (int8_t)tmp[nd].ro; tn.co = (int8_t)tmp[nd].co; tn.mult = (uint8_t)tmp[nd].mult; tn.model = (uint8_t)m;
-                        tn.parent = (short)(tmp[nd].parent < 0 ? -1 : pos[tmp[nd].parent]);
+                        tn.parent = (int8_t)(tmp[nd].parent < 0 ? -1 : pos[tmp[nd].parent]);
+                        tn.pbit = 31;
+                        if (tmp[nd].parent >= 0) {             // parent pair relative to this one
+                            const int dr = tmp[tmp[nd].parent].ro - tmp[nd].ro, dc = tmp[tmp[nd].parent].co - tmp[nd].co;
+                            const uint16_t key = (uint16_t)((dr & 0xff) | ((dc & 0xff) << 8));
+                            int k = 0;
+                            while (k < n_prel && hprel[k] != key) k++;
+                            if (k == n_prel) {
+                                if (n_prel == 31) { prel_overflow = true; k = 0; }
+                                else hprel[n_prel++] = key;
+                            }
+                            tn.pbit = (uint8_t)k;
+                        }
                     }
                     if (top.second < (int)tmp[nd].kids.size()) { const int kid = tmp[nd].kids[top.second++]; stack.push_back({kid, 0}); }
                     else { htrie[pos[nd]].skip = (unsigned short)trie_total; stack.pop_back(); }
@@ -280,6 +295,9 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         c.ev_table = nullptr; c.ev_thr = nullptr; c.ev_nclass = 0; c.ev_nrows = 0;
     }
     for (const CModel &c : ctx->hmodels) if (c.brute) ctx->any_brute = true;
+    if (prel_overflow) ctx->any_brute = true;     // too many distinct pair geometries for the candidate filter: exact path
+    CK(cudaMemcpyToSymbol(c_prel, hprel, sizeof hprel));
+    CK(cudaMemcpyToSymbol(c_n_prel, &n_prel, sizeof n_prel));
     RESERVE(ctx->d_xnodes, sizeof(XNode) * std::max<size_t>(hx.size(), 1));
     RESERVE(ctx->d_xcpt, sizeof(double) * std::max<size_t>(hcpt.size(), 1));
     CK(cudaMemcpy(ctx->d_xnodes.p, hx.data(), sizeof(XNode) * hx.size(), cudaMemcpyHostToDevice));

@@ -46,9 +46,8 @@
 #define SCAN_WARPS (SCAN_THREADS / 32)
 #define Q1_CAP 64                       // gate candidates per warp: < 32 waiting + 32 pushed at once
 #define Q2_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
-#ifndef BIG_CAP
-#define BIG_CAP 512                     // entries looked at per round of candidate generation
-#endif
+#define WL_CAP 48                       // < 16 waiting + 32 from one chunk of entries
+#define S2_CAP 64                       // < 32 waiting + 32 pushed at once
 #ifndef CB_MODELS
 #define CB_MODELS 4                     // models whose duplicate bitmaps are resident together
 #endif
@@ -63,7 +62,8 @@ struct FastSmem {
     uint32_t Ub[UWORDS];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
     uint16_t Ur[UWORDS];                 // entries before this word in list order
     uint32_t CB[CB_MODELS][UWORDS];      // placements already queued, per model of the current group
-    uint32_t big[BIG_CAP];               // big entries of the round: i | j << 8 | sure-mask << 16
+    uint32_t wl[SCAN_WARPS][WL_CAP];     // per warp: big entries waiting for a full row, i | j << 8 | sure-mask << 16
+    uint32_t s2[SCAN_WARPS][S2_CAP];     // per warp: (placement, trie node) pairs that passed the parent test
     uint32_t q1[SCAN_WARPS][Q1_CAP];     // gate candidates  p0 | p1 << 8 | model << 16
     uint32_t q2[SCAN_WARPS][Q2_CAP];     // gate survivors, same format
     TrieNode trie[TRIE_CAP];
@@ -73,14 +73,14 @@ struct FastSmem {
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
     uint32_t scan_tmp[SCAN_WARPS + 1];
-    uint32_t nbig[2];
+    uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
     uint8_t letters[FAST_W + 16];        // slot LETTER_GAP_SLOT holds the gap code
 };
 
 // is pair (b1, b2) stored?  (lib/bpprobs.py:17-18; the diagonal is never stored)
 __device__ __forceinline__ bool bpp_present(const FastSmem &sm, int wlen, int b1, int b2) {
     const int lo = min(b1, b2), hi = max(b1, b2);
-    return hi < wlen && ((sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u);
+    return lo >= 0 && hi < wlen && ((sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u);
 }
 
 // bpp lookup by popcount rank: 0.0 unless the pair is stored
@@ -160,7 +160,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const double slots = (double)M.cfg_begin[M.n_cfg];
         sm.sure_min[tid] = J.min_bpp * slots * (1.0 + 1e-12);
     }
-    if (tid < 2) sm.nbig[tid] = 0;
+    if (tid < 32) sm.prel[tid] = c_prel[tid];
     {
         const int nt = c_models[n_models - 1].trie0 + c_models[n_models - 1].n_trie;
         for (int k = tid; k < nt; k += SCAN_THREADS) sm.trie[k] = c_trie[k];
@@ -368,69 +368,111 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             consume(true, m);                                    // the exact gate reads one model's program
         }
     } else {
-        // big entries x trie nodes -> placements (see the header of this file)
+        // big entries x trie nodes -> placements (see the header of this file).  Every warp works on its
+        // own share of the entries: no block-wide barrier in this loop.
         const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
-        int round = 0;
+        uint32_t *wl = sm.wl[wid], *s2 = sm.s2[wid];
+        const int n_prel = c_n_prel;
         for (int g0 = 0; g0 < n_models; g0 += CB_MODELS) {
             const int g1 = min(g0 + CB_MODELS, n_models);
-            const int tg0 = c_models[g0].trie0, tg1 = c_models[g1 - 1].trie0 + c_models[g1 - 1].n_trie;
             if (g0 > 0) {                                        // bitmaps of the next group of models
                 __syncthreads();
                 for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+                __syncthreads();
             }
-            for (int eb = 0; eb < nnz; eb += BIG_CAP, round++) {
-                // ---- the round's big entries, compacted (order is irrelevant) -----------------------
-                uint32_t *nbig_p = &sm.nbig[round & 1];
-                for (int e = eb + tid; e < min(eb + BIG_CAP, nnz); e += SCAN_THREADS) {
-                    const double p = __ldg(vals + e);
-                    if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
-                    if (p >= big_min) {
-                        uint32_t sure = 0;
-                        for (int m = g0; m < g1; m++) sure |= (p >= sm.sure_min[m] ? 1u : 0u) << m;
-                        const uint32_t i = J.bpp_i[b0 + e], j = J.bpp_j[b0 + e];
-                        sm.big[atomicAdd(nbig_p, 1u)] = i | (j << 8) | (sure << 16);
+            int nl = 0, ns = 0;                                  // warp-uniform fills of wl and s2
+
+            // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
+            auto stage2 = [&](const int n) {
+                const bool act = lane < n;
+                const uint32_t it = act ? s2[ns - n + lane] : 0;
+                ns -= n;
+                __syncwarp();
+                const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
+                const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
+                bool ok = act;
+                int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
+                while (__any_sync(FULL_MASK, ok && a >= 0)) {      // every pair before it must be non-zero
+                    if (ok && a >= 0) {
+                        const TrieNode an = sm.trie[a];
+                        ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
+                        a = an.parent;
                     }
                 }
-                __syncthreads();
-                const int items = 2 * (int)*nbig_p;                // (entry, orientation)
-                if (tid == 0) sm.nbig[(round + 1) & 1] = 0;        // the other counter is idle until the next round's barrier
-                for (int row = wid * 32; row < items; row += SCAN_THREADS) {
-                    const int it = row + lane;
-                    const bool valid = it < items;
-                    const uint32_t en = sm.big[valid ? it >> 1 : 0];
-                    const int er = (it & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
-                    const int ec = (it & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
-                    for (int t = tg0; t < tg1; t++) {            // warp-uniform trie node
+                if (ok) {
+                    const uint32_t bit = 1u << (p1 & 31);
+                    ok = !(atomicOr(&sm.CB[tn.model - g0][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
+                }
+                const bool sure = ok && (it >> 31);
+                const uint32_t om = __ballot_sync(FULL_MASK, ok);
+                const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
+                const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
+                if (sure) { q2[qn2 + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
+                else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
+                qn2 += __popc(smask);
+                qn1 += __popc(cmask);
+                __syncwarp();
+                consume(false, 0);
+            };
+
+            for (int chunk = wid * 32;;) {
+                while (nl < 16 && chunk < nnz) {                  // the warp's next 32 entries: keep the big ones
+                    const int e = chunk + lane;
+                    chunk += SCAN_THREADS;
+                    uint32_t en = 0;
+                    bool isbig = false;
+                    if (e < nnz) {
+                        const double p = __ldg(vals + e);
+                        if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
+                        if (p >= big_min) {
+                            isbig = true;
+                            uint32_t sure = 0;
+                            for (int m = g0; m < g1; m++) sure |= (p >= sm.sure_min[m] ? 1u : 0u) << m;
+                            en = (uint32_t)J.bpp_i[b0 + e] | ((uint32_t)J.bpp_j[b0 + e] << 8) | (sure << 16);
+                        }
+                    }
+                    const uint32_t bm = __ballot_sync(FULL_MASK, isbig);
+                    if (isbig) wl[nl + __popc(bm & lt_mask)] = en;
+                    nl += __popc(bm);
+                    __syncwarp();
+                }
+                if (nl == 0) break;
+                // a row of items: lane = (entry, orientation)
+                const int take = min(nl, 16);
+                const bool valid = (lane >> 1) < take;
+                const uint32_t en = wl[valid ? nl - take + (lane >> 1) : 0];
+                nl -= take;
+                __syncwarp();
+                const int er = (lane & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
+                const int ec = (lane & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
+                uint32_t PM = 0x80000000u;                        // which parent-relative pairs are present (bit 31: no parent)
+                for (int k = 0; k < n_prel; k++) {
+                    const uint32_t d = sm.prel[k];
+                    if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
+                }
+                for (int m = g0; m < g1; m++) {
+                    const uint32_t bd = sm.bounds[m];
+                    const uint32_t n0 = bd & 0xffu;
+                    const int hi = (int)((bd >> 8) & 0xffu);
+                    const bool sym = bd >> 16;
+                    const uint32_t sure_m = ((en >> (16 + m)) & 1u) << 31;
+                    const int t1 = sm.trie_end[m];
+                    for (int t = sm.trie0[m]; t < t1; t++) {      // warp-uniform trie node
                         const TrieNode tn = sm.trie[t];
-                        const uint32_t bd = sm.bounds[tn.model];
                         const int p0 = er - tn.ro, p1 = ec - tn.co;
-                        const int lo = (bd >> 16) ? p0 : 0;
-                        bool ok = valid && (unsigned)p0 < (bd & 0xffu) && p1 >= lo && (p1 <= (int)((bd >> 8) & 0xffu) || p1 == lo);
-                        for (int a = tn.parent; a >= 0 && __any_sync(FULL_MASK, ok);) {   // every pair before it must be non-zero
-                            const TrieNode an = sm.trie[a];
-                            if (ok) ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
-                            a = an.parent;
-                        }
-                        if (ok) {
-                            const uint32_t bit = 1u << (p1 & 31);
-                            ok = !(atomicOr(&sm.CB[tn.model - g0][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
-                        }
+                        bool ok = valid && ((PM >> tn.pbit) & 1u) && (uint32_t)p0 < n0;
+                        if (sym) ok = ok && p1 >= p0 && (p1 <= hi || p1 == p0);
+                        else ok = ok && (uint32_t)p1 <= (uint32_t)hi;
                         const uint32_t om = __ballot_sync(FULL_MASK, ok);
                         if (om == 0) continue;
-                        const bool sure = ok && ((en >> (16 + tn.model)) & 1u);
-                        const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
-                        const uint32_t item = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)tn.model << 16);
-                        if (sure) q2[qn2 + __popc(smask & lt_mask)] = item;
-                        else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
-                        qn2 += __popc(smask);
-                        qn1 += __popc(cmask);
-                        if (lane == 0 && smask) atomicAdd(&sm.gate_pass[tn.model], (uint32_t)__popc(smask));
+                        if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | sure_m;
+                        ns += __popc(om);
                         __syncwarp();
-                        consume(false, 0);
+                        if (ns >= 32) stage2(32);
                     }
                 }
-                __syncthreads();                                  // the list is rewritten by the next round
             }
+            if (ns > 0) stage2(ns);                              // the bitmaps belong to this group
         }
         consume(true, 0);
     }
