@@ -62,7 +62,8 @@ struct XNode {
     uint16_t skip, next;      // node after the subtree / next node in preorder; XNODE_END ends the walk
     uint16_t leaf;
     uint8_t model, fb;        // fb = flags | bdepth << 4
-    int16_t ddx, ddy;         // separation distances of a CHECK_DIST node (lib/node.py:184-192), else 0
+    int16_t dlo;              // CHECK_DIST node (lib/node.py:184-192): the walk dies when dlo <= p1 - p0 < dlo + dspan
+    uint16_t dspan;           // 0 elsewhere
 };
 static_assert(sizeof(XNode) == 32, "XNode layout");
 #define XNODE_END 0xffffu
@@ -84,6 +85,7 @@ struct DevJob {
     double min_bpp, cutoff;
     const XNode *xnodes;         // all models' search trees (scoring engine format)
     const double *xcpt;          // all models' CPTs, concatenated
+    int n_xnodes, n_xcpt;
     int debug;                   // profiling experiments only (RMD_DEBUG): 1 skip scoring, 2 skip the exact gate
 };
 

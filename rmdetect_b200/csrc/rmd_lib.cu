@@ -35,8 +35,12 @@ struct rmd_ctx {
     std::vector<void *> model_allocs;
     std::vector<void *> ev_allocs[RMD_MAX_MODELS];
     int max_chain = 0;
+    int n_xnodes = 0, n_xcpt = 0, sm_count = 0;
     bool any_brute = false;             // some model gives no anchor for candidates: scan_fast_kernel<true>
-    DBuf d_xnodes, d_xcpt;
+    DBuf d_xnodes, d_xcpt, d_next;
+    int teams = 8, ctas_per_sm = 1;      // shape of the persistent scan kernel (rmd_set_models)
+    size_t scan_smem = 0;
+    bool tables_in_smem = true;
     // resident job
     bool have_job = false;
     DevJob job{};
@@ -128,7 +132,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
                     &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt,
                     &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
                     &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact,
-                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
+                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
     for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
@@ -286,7 +290,9 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
                 if (n.flags & RMD_F_CHECK_DIST) {
                     const int dx = d.leaf_dist[2 * n.leaf], dy = d.leaf_dist[2 * n.leaf + 1];
                     if (dx > 32767 || dy > 32767 || dx < 0 || dy < 0) return fail(ctx, RMD_E_LIMIT, "model %d: separation out of range", m);
-                    x.ddx = (int16_t)dx; x.ddy = (int16_t)dy;
+                    // dead when 0 <= d < dx or -dy < d <= 0, d = p1 - p0: one interval [lo, hi)
+                    const int lo = dy > 0 ? -dy + 1 : (dx > 0 ? 0 : 1), hi = dx > 0 ? dx : (dy > 0 ? 1 : 0);
+                    x.dlo = (int16_t)lo; x.dspan = (uint16_t)(hi > lo ? hi - lo : 0);
                 }
                 hx.push_back(x);
             }
@@ -303,6 +309,26 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     CK(cudaMemcpy(ctx->d_xnodes.p, hx.data(), sizeof(XNode) * hx.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_xcpt.p, hcpt.data(), sizeof(double) * hcpt.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpyToSymbol(c_trie, htrie, sizeof htrie));
+    ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size();
+    {   // shape of the persistent scan kernel: tables + one FastSmem per team within the SM's shared memory
+        int smem_max = 0;
+        CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+        CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        const size_t tables = sizeof(XNode) * hx.size() + 16 * ((hcpt.size() + 1) / 2);
+        int teams = getenv("RMD_TEAMS") ? atoi(getenv("RMD_TEAMS")) : 8;
+        ctx->ctas_per_sm = getenv("RMD_CTAS_PER_SM") ? atoi(getenv("RMD_CTAS_PER_SM")) : 1;
+        teams = std::max(1, std::min(teams, SCAN_MAX_THREADS / SCAN_THREADS));
+        ctx->tables_in_smem = tables + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctx->ctas_per_sm;
+        const size_t fixed = ctx->tables_in_smem ? tables : 0;
+        while (teams > 1 && fixed + teams * sizeof(FastSmem) > (size_t)smem_max / ctx->ctas_per_sm) teams--;
+        ctx->teams = teams;
+        ctx->scan_smem = fixed + teams * sizeof(FastSmem);
+        if (ctx->scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", ctx->scan_smem, smem_max);
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    }
     ctx->n_models = n_models;
     CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * n_models));
     ctx->have_job = false;
@@ -365,6 +391,7 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
     J.debug = getenv("RMD_DEBUG") ? atoi(getenv("RMD_DEBUG")) : 0;
     J.seq_off = (const long long *)ctx->d_seq_off.p; J.win_base = (const long long *)ctx->d_win_base.p;
     J.xnodes = (const XNode *)ctx->d_xnodes.p; J.xcpt = (const double *)ctx->d_xcpt.p;
+    J.n_xnodes = ctx->n_xnodes; J.n_xcpt = ctx->n_xcpt;
     return RMD_OK;
 }
 
@@ -521,6 +548,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev[8], st));
     RESERVE(ctx->d_counters, 64);
+    RESERVE(ctx->d_next, sizeof(unsigned int) * (STREAM_CHUNKS + 1));
     RESERVE(ctx->d_gate_pass, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_hits, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(ngroups + 1));
@@ -535,6 +563,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         RESERVE(ctx->d_raw, sizeof(RawHit) * (size_t)ctx->raw_cap);
         launches = 0;
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(unsigned int) * (STREAM_CHUNKS + 1), st));
         CK(cudaMemsetAsync(ctx->d_gate_pass.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         CK(cudaMemsetAsync(ctx->d_group_hits.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         ScanOut O;
@@ -556,10 +585,17 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             }
             if (c1 <= c0) continue;
             if (use_fast) {
-                if (ctx->any_brute || !(J.min_bpp > 0.0))
-                    scan_fast_kernel<true><<<(unsigned)(c1 - c0), SCAN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
-                else
-                    scan_fast_kernel<false><<<(unsigned)(c1 - c0), SCAN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
+                unsigned int *next = (unsigned int *)ctx->d_next.p + ch;      // this launch's window counter
+                const bool brute = ctx->any_brute || !(J.min_bpp > 0.0);
+                const unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * ctx->ctas_per_sm, (c1 - c0 + ctx->teams - 1) / ctx->teams);
+                const unsigned block = (unsigned)ctx->teams * SCAN_THREADS;
+                if (ctx->tables_in_smem) {
+                    if (brute) scan_fast_kernel<true, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    else scan_fast_kernel<false, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                } else {
+                    if (brute) scan_fast_kernel<true, false><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    else scan_fast_kernel<false, false><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                }
                 launches++;
             }
             if (need_generic) {

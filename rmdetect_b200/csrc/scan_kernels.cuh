@@ -7,7 +7,8 @@
 //   lib/bpprobs.py:17-18    prob_pair       (sparse symmetric lookup, 0.0 when absent)
 //   lib/node.py:176-277     NodeSearch.eval (tree walk, see also eval_placement in device_common.cuh)
 //
-// Design (one CTA of 128 threads per window, windows up to 160 letters):
+// Design (a team of 128 threads per window, windows up to 160 letters; persistent CTAs of up to 8 teams
+// with the models' search trees and CPTs in shared memory):
 //   * the window's bpp coordinate list becomes, in shared memory, an upper-triangle bit matrix with
 //     per-word ranks: the value of pair (i, j) is entry rank + popc(bits below) of the window's list,
 //     read through L1;
@@ -51,8 +52,9 @@
 #ifndef CB_MODELS
 #define CB_MODELS 4                     // models whose duplicate bitmaps are resident together
 #endif
-#ifndef SCAN_MIN_CTAS
-#define SCAN_MIN_CTAS 9
+#define SCAN_MAX_THREADS 1024           // a CTA holds up to 8 teams of SCAN_THREADS
+#ifndef REFILL_MIN_IDLE
+#define REFILL_MIN_IDLE 8               // the scoring engine hands out queued work once this many lanes are idle
 #endif
 #define WORDS_PER_THREAD ((UWORDS + SCAN_THREADS - 1) / SCAN_THREADS)   // 7
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a sorted, unique upper triangle
@@ -72,7 +74,8 @@ struct FastSmem {
     uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
-    uint32_t scan_tmp[SCAN_WARPS + 1];
+    uint32_t scan_tmp[SCAN_WARPS];
+    uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
     uint8_t letters[FAST_W + 16];        // slot LETTER_GAP_SLOT holds the gap code
 };
@@ -120,41 +123,56 @@ __device__ __forceinline__ bool gate_pass(const CModel &M, Lookup lookup, bool a
 // With no pair summed the reference's mean is 0.0 and is still compared with min_bpp_mean, so a
 // non-positive threshold lets every placement through; every placement is then a candidate.
 
-template <bool BRUTE>
-__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS)
-scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
-                 const ScanOut O, const int min_wlen) {       // windows [w_begin, w_end); records are relative to w_base
-    __shared__ FastSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1;
-    const long long w = w_begin + blockIdx.x;
-    if (w >= w_end) return;
-    int seq, wlen;
-    long long start;
-    window_geom(J, w, seq, start, wlen);
-    if (wlen < min_wlen || wlen > FAST_W) return;           // long or degenerate windows: scan_generic_kernel
-    const long long gbase = J.seq_off[seq] + start;
-    const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
-    const int nnz = (int)(b1 - b0);
-    const double *vals = J.bpp_p + b0;                        // values stay in global memory (L1)
-    const uint32_t win_local = (uint32_t)(w - w_base);
-    const int n_models = J.n_models;
+// barrier of one team (4 warps); barrier 0 stays with __syncthreads()
+__device__ __forceinline__ void team_sync(const int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(SCAN_THREADS) : "memory");
+}
 
-    // ---- stage the window: letters, GC table, bit matrix with ranks, model tables ------------------
-    for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
-    for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
-    for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS)
-        sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : (k == LETTER_GAP_SLOT ? 4 : 0);
-    if (tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
+// exclusive scan of one value per thread over a team; `tmp` holds SCAN_WARPS words
+__device__ __forceinline__ uint32_t team_exclusive_scan(uint32_t v, uint32_t *tmp, uint32_t *total, const int team,
+                                                        const int lane, const int wid) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) tmp[wid] = inc;
+    team_sync(team);
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_WARPS; k++) { const uint32_t t = tmp[k]; all += t; if (k < wid) before += t; }
+    *total = all;
+    team_sync(team);
+    return before + inc - v;
+}
+
+// Persistent kernel: one CTA per SM slot, `blockDim.x / 128` teams of four warps; a team takes the next
+// window from a global counter, so a slow window delays nobody else.  The models' search trees and CPTs
+// sit in shared memory once per CTA (TABLES: they fit), next to the teams' window state.
+template <bool BRUTE, bool TABLES>
+__global__ void __launch_bounds__(SCAN_MAX_THREADS, 1)
+scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
+                 const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
+    extern __shared__ uint4 dyn_smem[];
+    const int tid = threadIdx.x & (SCAN_THREADS - 1), lane = tid & 31, wid = tid >> 5, team = threadIdx.x / SCAN_THREADS;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const int n_models = J.n_models;
+    // ---- CTA-wide tables ------------------------------------------------------------------------
+    const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;      // in uint4
+    uint4 *sx = dyn_smem;
+    double *scpt = reinterpret_cast<double *>(dyn_smem + x_words);
+    FastSmem &sm = reinterpret_cast<FastSmem *>(dyn_smem + x_words + c_words)[team];
+    if (TABLES) {
+        const uint4 *gx = reinterpret_cast<const uint4 *>(J.xnodes);
+        for (int k = threadIdx.x; k < x_words; k += blockDim.x) sx[k] = __ldg(gx + k);
+        for (int k = threadIdx.x; k < J.n_xcpt; k += blockDim.x) scpt[k] = __ldg(J.xcpt + k);
+    }
     if (tid < n_models) {
         const CModel &M = c_models[tid];
-        sm.gate_pass[tid] = 0;
         sm.xnode0[tid] = (uint16_t)M.xnode0;
         sm.trie0[tid] = (uint16_t)M.trie0;
         sm.trie_end[tid] = (uint16_t)(M.trie0 + M.n_trie);
-        // odometer ranges (lib/scanner.py:161-193): p0 < n0; p1 from lo (p0 when SYMMETRIC) to max(hi, lo)
-        sm.bounds[tid] = (uint32_t)rows_of(wlen, M.chain_len[0]) | ((uint32_t)max(wlen - M.chain_len[1] - 1, 0) << 8) |
-                         (M.symmetric ? 1u << 16 : 0u);
         // mean = sum / count >= p / slots: sum >= p (positive terms, monotone rounding), count <= slots,
         // division monotone; the factor covers the rounding of the product and of that division
         const double slots = (double)M.cfg_begin[M.n_cfg];
@@ -166,338 +184,376 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         for (int k = tid; k < nt; k += SCAN_THREADS) sm.trie[k] = c_trie[k];
     }
     __syncthreads();
-    for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) {     // four entries per thread in flight
-        int ei[4], ej[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int e = e0 + k * SCAN_THREADS + tid;
-            ei[k] = ej[k] = 0;
-            if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int e = e0 + k * SCAN_THREADS + tid, i = ei[k], j = ej[k];
-            if (e < nnz && i < j && j < wlen) atomicOr(&sm.Ub[i * FAST_WORDS + (j >> 5)], 1u << (j & 31));
-        }
-    }
-    __syncthreads();
-    {   // rank of the first bit of every word = its position in the (i, j)-sorted list
-        uint32_t mine = 0;
-        const int k0 = tid * WORDS_PER_THREAD;
-#pragma unroll
-        for (int k = 0; k < WORDS_PER_THREAD; k++)
-            if (k0 + k < UWORDS) mine += __popc(sm.Ub[k0 + k]);
-        uint32_t total, run = block_exclusive_scan<SCAN_THREADS>(mine, sm.scan_tmp, &total);
-#pragma unroll
-        for (int k = 0; k < WORDS_PER_THREAD; k++)
-            if (k0 + k < UWORDS) { sm.Ur[k0 + k] = (uint16_t)run; run += __popc(sm.Ub[k0 + k]); }
-        // the ranks are list positions only if every entry set its own bit
-        if (tid == 0 && total != (uint32_t)nnz) atomicOr(&O.raw_count[7], ERR_BAD_LIST);
-    }
-    __syncthreads();
-
-    auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
-    uint32_t *q1 = sm.q1[wid], *q2 = sm.q2[wid];
-    int qn1 = 0, qn2 = 0;                                   // warp-uniform queue fills
+    const uint4 *xn = TABLES ? sx : reinterpret_cast<const uint4 *>(J.xnodes);
+    const double *xcpt = TABLES ? scpt : J.xcpt;
     const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (lib/node.py:248)
     const bool no_score = !root_ok || (J.debug & 1);
-
-    // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ----------
-    const uint4 *xn = reinterpret_cast<const uint4 *>(J.xnodes);
-    uint32_t e_c = 0, e_t = XNODE_END;                      // placement p0 | p1 << 16; node (XNODE_END: lane idle)
-    int e_leaf = -1;                                        // best leaf | model << 16
-    double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
-    double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
-    unsigned long long dbg_iter = 0, dbg_visits = 0;        // RMD_DEBUG & 8: engine statistics
-
-    auto engine = [&](const bool drain) {
-        uint32_t bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);     // busy lanes, kept current below
-        for (;;) {
-            if (qn2 > 0 && bm != FULL_MASK) {                // hand queued survivors to idle lanes
-                const uint32_t im = ~bm;
-                const int r = __popc(im & lt_mask);
-                if ((im >> lane & 1) && r < qn2) {
-                    const uint32_t c = q2[qn2 - 1 - r];
-                    e_c = (c & 0xffu) | ((c & 0xff00u) << 8);
-                    e_t = sm.xnode0[c >> 16];
-                    e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
-                    e_stk[0] = make_double2(0.0, 0.0);
-                }
-                qn2 -= min(qn2, __popc(im));
-                bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
-            }
-            if (bm == 0) break;
-            if (!drain && qn2 == 0 && bm != FULL_MASK) break;   // pause: nothing left to keep every lane fed
-            if (J.debug & 8) { dbg_iter++; dbg_visits += __popc(bm); }
-            const bool busy = e_t != XNODE_END;
-            if (busy) {
-                const uint4 a = __ldg(xn + 2 * e_t), b = __ldg(xn + 2 * e_t + 1);
-                auto letter = [&](const uint32_t sel) {
-                    return (int)sm.letters[(__funnelshift_rc(e_c, 0u, sel & 0xffu) & 0xffffu) + ((int)sel >> 8)];
-                };
-                const int nt = letter(a.x), c0 = letter(a.y), c1 = letter(a.z);         // :199-213
-                const uint32_t idx = a.w + min(nt, 5) + min(c0, 5) * (b.x & 0xffffu) + min(c1, 5) * (b.x >> 16);
-                double v = __ldg(J.xcpt + idx);
-                const double g = sm.gc[nt];                           // :223 (slot 4 holds log 0.25)
-                if (v == CUDART_INF) v = g;                           // GC-sentinel row (:217-218)
-                const uint32_t fl = b.z;                              // leaf | model << 16 | flags << 24 | bdepth << 28
-                const int bdepth = fl >> 28;
-                if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
-                const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);                   // :184-192 (0, 0 unless CHECK_DIST)
-                const int ddx = (int)(short)(b.w & 0xffffu), ddy = (int)(short)(b.w >> 16);
-                const bool apart = !((d >= 0 && d < ddx) || (d <= 0 && -d < ddy));
-                e_pm = __dadd_rn(e_pm, v);                            // :227-228
-                e_pr = __dadd_rn(e_pr, g);
-                // a node that fails is left through its skip link, and whatever comes next restores the sums
-                const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);           // :248
-                if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {                // :265-275
-                    e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
-                }
-                if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
-                e_t = alive ? (b.y >> 16) : (b.y & 0xffffu);
-            }
-            const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
-            if (dm == 0) continue;
-            const bool hit = busy && e_t == XNODE_END && e_leaf >= 0;
-            const uint32_t hm = __ballot_sync(FULL_MASK, hit);
-            if (hm) {                                         // append records: one atomic per warp iteration
-                unsigned long long base = 0;
-                if (lane == __ffs(hm) - 1) base = atomicAdd(&O.raw_count[0], (unsigned long long)__popc(hm));
-                base = __shfl_sync(FULL_MASK, base, __ffs(hm) - 1);
-                if (hit) {
-                    const unsigned long long slot = base + __popc(hm & lt_mask);
-                    const int model = e_leaf >> 16;
-                    if ((long long)slot < O.raw_cap) {
-                        RawHit h;
-                        h.window = win_local;
-                        h.p0 = (uint16_t)(e_c & 0xffffu); h.p1 = (uint16_t)(e_c >> 16);
-                        h.model = (uint16_t)model; h.leaf = (uint16_t)(e_leaf & 0xffff);
-                        h.rank = 0;
-                        h.pm = e_bpm; h.pr = e_bpr;
-                        O.raw[slot] = h;
-                    }
-                    atomicAdd(&O.group_hits[(long long)win_local * n_models + model], 1u);
-                }
-            }
-            bm &= ~dm;
-        }
-    };
-
-    // ---- gate on up to 32 queued candidates --------------------------------------------------------
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
-    auto gate_batch = [&](const int nbatch, const int brute_model) {
-        const bool act = lane < nbatch;
-        const uint32_t c = act ? q1[qn1 - nbatch + lane] : 0;
-        qn1 -= nbatch;
-        __syncwarp();
-        const int p0 = c & 0xff, p1 = (c >> 8) & 0xff, m = c >> 16;
-        bool pass;
-        if (BRUTE) {
-            pass = gate_pass(c_models[brute_model], lookup, act, p0, p1, J.min_bpp);
-        } else {
-            // depth-first over the model's trie: a zero pair closes its subtree (the `break`)
-            int t = act ? sm.trie0[m] : 0;
-            const int tend = act ? sm.trie_end[m] : 0;
-            double sum = 0.0;
-            int cnt = 0;
-            while (__any_sync(FULL_MASK, t < tend)) {
-                if (t < tend) {
-                    const TrieNode tn = sm.trie[t];
-                    const double v = lookup(p0 + tn.ro, p1 + tn.co);
-                    if (v != 0.0) { sum = __dadd_rn(sum, __dmul_rn(v, (double)tn.mult)); cnt += tn.mult; t++; }
-                    else t = tn.skip;
-                }
+    uint32_t *q1 = sm.q1[wid], *q2 = sm.q2[wid];
+
+    for (int turn = 0;; turn ^= 1) {
+        if (tid == 0) sm.next[turn] = atomicAdd(next_window, 1u);
+        team_sync(team);
+        const long long w = w_begin + sm.next[turn];
+        if (w >= w_end) break;
+        int seq, wlen;
+        long long start;
+        window_geom(J, w, seq, start, wlen);
+        if (wlen < min_wlen || wlen > FAST_W) continue;       // long or degenerate windows: scan_generic_kernel
+        const long long gbase = J.seq_off[seq] + start;
+        const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
+        const int nnz = (int)(b1 - b0);
+        const double *vals = J.bpp_p + b0;                    // values stay in global memory (L1)
+        const uint32_t win_local = (uint32_t)(w - w_base);
+
+        // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
+        for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
+        for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+        for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS)
+            sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : (k == LETTER_GAP_SLOT ? 4 : 0);
+        if (tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
+        if (tid < n_models) {
+            const CModel &M = c_models[tid];
+            sm.gate_pass[tid] = 0;
+            // odometer ranges (lib/scanner.py:161-193): p0 < n0; p1 from lo (p0 when SYMMETRIC) to max(hi, lo)
+            sm.bounds[tid] = (uint32_t)rows_of(wlen, M.chain_len[0]) | ((uint32_t)max(wlen - M.chain_len[1] - 1, 0) << 8) |
+                             (M.symmetric ? 1u << 16 : 0u);
+        }
+        team_sync(team);
+        for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) { // four entries per thread in flight
+            int ei[4], ej[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int e = e0 + k * SCAN_THREADS + tid;
+                ei[k] = ej[k] = 0;
+                if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
             }
-            const double mean = cnt ? __ddiv_rn(sum, (double)cnt) : 0.0;
-            pass = act && mean >= thr_hi;
-            const bool unsure = act && !pass && mean >= thr_lo;
-            uint32_t um = __ballot_sync(FULL_MASK, unsure);
-            while (um) {                                      // the reference's own sum, one model at a time
-                const int mm = __shfl_sync(FULL_MASK, m, __ffs(um) - 1);
-                const bool mine = unsure && m == mm;
-                if (gate_pass(c_models[mm], lookup, mine, p0, p1, J.min_bpp)) pass = true;
-                um &= ~__ballot_sync(FULL_MASK, mine);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int e = e0 + k * SCAN_THREADS + tid, i = ei[k], j = ej[k];
+                if (e < nnz && i < j && j < wlen) atomicOr(&sm.Ub[i * FAST_WORDS + (j >> 5)], 1u << (j & 31));
             }
         }
-        const uint32_t pmask = __ballot_sync(FULL_MASK, pass);
-        if (pass) { q2[qn2 + __popc(pmask & lt_mask)] = c; atomicAdd(&sm.gate_pass[m], 1u); }
-        qn2 += __popc(pmask);
-        __syncwarp();
-    };
-    auto consume = [&](const bool drain, const int brute_model) {
-        if (drain) { while (qn1 > 0) gate_batch(min(qn1, 32), brute_model); }
-        else if (qn1 >= 32) gate_batch(32, brute_model);
-        if (no_score) qn2 = 0;
-        if (qn2 >= 32) engine(false);
-    };
-
-    unsigned long long tests_all = 0;
-    if (BRUTE) {
-        // every placement of the odometer is a candidate: 32 placements per lane word
-        for (int m = 0; m < n_models; m++) {
-            const CModel &M = c_models[m];
-            const int L1 = M.chain_len[1];
-            const int n0 = rows_of(wlen, M.chain_len[0]);
-            const int p1_max = p1_last(wlen, L1, M.symmetric ? n0 - 1 : 0);
-            const int nw = (p1_max >> 5) + 1;
-            const int items = n0 * nw;
-            for (int base = wid * 32; base < items; base += SCAN_THREADS) {
-                const int t = base + lane;
-                uint32_t cw = 0;
-                int p0 = 0, wd = 0;
-                if (t < items) {
-                    p0 = t / nw; wd = t - p0 * nw;
-                    const int lo = M.symmetric ? p0 : 0;         // odometer range of p1 for this p0
-                    const int hi = p1_last(wlen, L1, lo);
-                    const int blo = lo - (wd << 5), bhi = hi - (wd << 5);
-                    cw = bhi < 0 || blo > 31 ? 0u : 0xffffffffu;
-                    if (blo > 0 && blo <= 31) cw &= 0xffffffffu << blo;
-                    if (bhi >= 0 && bhi < 31) cw &= 0xffffffffu >> (31 - bhi);
-                }
-                while (__any_sync(FULL_MASK, cw != 0)) {          // one candidate per lane per round
-                    const bool has = cw != 0;
-                    const int b = has ? __ffs(cw) - 1 : 0;
-                    cw &= cw - 1;
-                    const uint32_t pmask = __ballot_sync(FULL_MASK, has);
-                    if (has) q1[qn1 + __popc(pmask & lt_mask)] = (uint32_t)p0 | ((uint32_t)((wd << 5) + b) << 8) | ((uint32_t)m << 16);
-                    qn1 += __popc(pmask);
-                    __syncwarp();
-                    consume(false, m);
-                }
-            }
-            consume(true, m);                                    // the exact gate reads one model's program
+        team_sync(team);
+        {   // rank of the first bit of every word = its position in the (i, j)-sorted list
+            uint32_t mine = 0;
+            const int k0 = tid * WORDS_PER_THREAD;
+#pragma unroll
+            for (int k = 0; k < WORDS_PER_THREAD; k++)
+                if (k0 + k < UWORDS) mine += __popc(sm.Ub[k0 + k]);
+            uint32_t total, run = team_exclusive_scan(mine, sm.scan_tmp, &total, team, lane, wid);
+#pragma unroll
+            for (int k = 0; k < WORDS_PER_THREAD; k++)
+                if (k0 + k < UWORDS) { sm.Ur[k0 + k] = (uint16_t)run; run += __popc(sm.Ub[k0 + k]); }
+            // the ranks are list positions only if every entry set its own bit
+            if (tid == 0 && total != (uint32_t)nnz) atomicOr(&O.raw_count[7], ERR_BAD_LIST);
         }
-    } else {
-        // big entries x trie nodes -> placements (see the header of this file).  Every warp works on its
-        // own share of the entries: no block-wide barrier in this loop.
-        const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
-        uint32_t *wl = sm.wl[wid], *s2 = sm.s2[wid];
-        const int n_prel = c_n_prel;
-        for (int g0 = 0; g0 < n_models; g0 += CB_MODELS) {
-            const int g1 = min(g0 + CB_MODELS, n_models);
-            if (g0 > 0) {                                        // bitmaps of the next group of models
-                __syncthreads();
-                for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
-                __syncthreads();
-            }
-            int nl = 0, ns = 0;                                  // warp-uniform fills of wl and s2
+        team_sync(team);
 
-            // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
-            auto stage2 = [&](const int n) {
-                const bool act = lane < n;
-                const uint32_t it = act ? s2[ns - n + lane] : 0;
-                ns -= n;
-                __syncwarp();
-                const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
-                const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
-                bool ok = act;
-                int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
-                while (__any_sync(FULL_MASK, ok && a >= 0)) {      // every pair before it must be non-zero
-                    if (ok && a >= 0) {
-                        const TrieNode an = sm.trie[a];
-                        ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
-                        a = an.parent;
+        auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
+        int qn1 = 0, qn2 = 0;                               // warp-uniform queue fills
+
+        // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ------
+        uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
+        int e_leaf = -1;                                    // best leaf | model << 16
+        double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
+        double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
+#ifdef RMD_STATS
+        unsigned long long dbg_iter = 0, dbg_visits = 0;    // engine statistics
+#endif
+
+        auto engine = [&](const bool drain) {
+            uint32_t bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);     // busy lanes, kept current below
+            for (;;) {
+                if (qn2 > 0 && __popc(~bm) >= (drain ? 1 : REFILL_MIN_IDLE)) {   // hand queued survivors to idle lanes
+                    const uint32_t im = ~bm;
+                    const int r = __popc(im & lt_mask);
+                    if ((im >> lane & 1) && r < qn2) {
+                        const uint32_t c = q2[qn2 - 1 - r];
+                        e_c = (c & 0xffu) | ((c & 0xff00u) << 8);
+                        e_t = sm.xnode0[c >> 16];
+                        e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
+                        e_stk[0] = make_double2(0.0, 0.0);
+                    }
+                    qn2 -= min(qn2, __popc(im));
+                    bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
+                }
+                if (bm == 0) break;
+                if (!drain && qn2 == 0 && bm != FULL_MASK) break;   // pause: nothing left to keep every lane fed
+#ifdef RMD_STATS
+                dbg_iter++; dbg_visits += __popc(bm);
+#endif
+                const bool busy = e_t != XNODE_END;
+                if (busy) {
+                    const uint4 a = xn[2 * e_t], b = xn[2 * e_t + 1];
+                    auto letter = [&](const uint32_t sel) {
+                        return (int)sm.letters[(__funnelshift_rc(e_c, 0u, sel & 0xffu) & 0xffffu) + ((int)sel >> 8)];
+                    };
+                    const int nt = letter(a.x), c0 = letter(a.y), c1 = letter(a.z);         // :199-213
+                    const uint32_t idx = a.w + min(nt, 5) + min(c0, 5) * (b.x & 0xffffu) + min(c1, 5) * (b.x >> 16);
+                    double v = xcpt[idx];
+                    const double g = sm.gc[nt];                       // :223 (slot 4 holds log 0.25)
+                    if (v == CUDART_INF) v = g;                       // GC-sentinel row (:217-218)
+                    const uint32_t fl = b.z;                          // leaf | model << 16 | flags << 24 | bdepth << 28
+                    const int bdepth = fl >> 28;
+                    if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
+                    // :184-192 as one interval test: chains closer than the configuration allows (empty unless CHECK_DIST)
+                    const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);
+                    const bool apart = (uint32_t)(d - (int)(short)(b.w & 0xffffu)) >= (b.w >> 16);
+                    e_pm = __dadd_rn(e_pm, v);                        // :227-228
+                    e_pr = __dadd_rn(e_pr, g);
+                    // a node that fails is left through its skip link, and whatever comes next restores the sums
+                    const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);       // :248
+                    if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {            // :265-275
+                        e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
+                    }
+                    if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
+                    e_t = alive ? (b.y >> 16) : (b.y & 0xffffu);
+                }
+                const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
+                if (dm == 0) continue;
+                const bool hit = busy && e_t == XNODE_END && e_leaf >= 0;
+                const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+                if (hm) {                                     // append records: one atomic per warp iteration
+                    unsigned long long base = 0;
+                    if (lane == __ffs(hm) - 1) base = atomicAdd(&O.raw_count[0], (unsigned long long)__popc(hm));
+                    base = __shfl_sync(FULL_MASK, base, __ffs(hm) - 1);
+                    if (hit) {
+                        const unsigned long long slot = base + __popc(hm & lt_mask);
+                        const int model = e_leaf >> 16;
+                        if ((long long)slot < O.raw_cap) {
+                            RawHit h;
+                            h.window = win_local;
+                            h.p0 = (uint16_t)(e_c & 0xffffu); h.p1 = (uint16_t)(e_c >> 16);
+                            h.model = (uint16_t)model; h.leaf = (uint16_t)(e_leaf & 0xffff);
+                            h.rank = 0;
+                            h.pm = e_bpm; h.pr = e_bpr;
+                            O.raw[slot] = h;
+                        }
+                        atomicAdd(&O.group_hits[(long long)win_local * n_models + model], 1u);
                     }
                 }
-                if (ok) {
-                    const uint32_t bit = 1u << (p1 & 31);
-                    ok = !(atomicOr(&sm.CB[tn.model - g0][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
-                }
-                const bool sure = ok && (it >> 31);
-                const uint32_t om = __ballot_sync(FULL_MASK, ok);
-                const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
-                const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
-                if (sure) { q2[qn2 + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
-                else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
-                qn2 += __popc(smask);
-                qn1 += __popc(cmask);
-                __syncwarp();
-                consume(false, 0);
-            };
+                bm &= ~dm;
+            }
+        };
 
-            for (int chunk = wid * 32;;) {
-                while (nl < 16 && chunk < nnz) {                  // the warp's next 32 entries: keep the big ones
-                    const int e = chunk + lane;
-                    chunk += SCAN_THREADS;
-                    uint32_t en = 0;
-                    bool isbig = false;
-                    if (e < nnz) {
-                        const double p = __ldg(vals + e);
-                        if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
-                        if (p >= big_min) {
-                            isbig = true;
-                            uint32_t sure = 0;
-                            for (int m = g0; m < g1; m++) sure |= (p >= sm.sure_min[m] ? 1u : 0u) << m;
-                            en = (uint32_t)J.bpp_i[b0 + e] | ((uint32_t)J.bpp_j[b0 + e] << 8) | (sure << 16);
+        // ---- gate on up to 32 queued candidates ----------------------------------------------------
+        auto gate_batch = [&](const int nbatch, const int brute_model) {
+            const bool act = lane < nbatch;
+            const uint32_t c = act ? q1[qn1 - nbatch + lane] : 0;
+            qn1 -= nbatch;
+            __syncwarp();
+            const int p0 = c & 0xff, p1 = (c >> 8) & 0xff, m = c >> 16;
+            bool pass;
+            if (BRUTE) {
+                pass = gate_pass(c_models[brute_model], lookup, act, p0, p1, J.min_bpp);
+            } else {
+                // depth-first over the model's trie: a zero pair closes its subtree (the `break`)
+                int t = act ? sm.trie0[m] : 0;
+                const int tend = act ? sm.trie_end[m] : 0;
+                double sum = 0.0;
+                int cnt = 0;
+                while (__any_sync(FULL_MASK, t < tend)) {
+                    if (t < tend) {
+                        const TrieNode tn = sm.trie[t];
+                        const double v = lookup(p0 + tn.ro, p1 + tn.co);
+                        if (v != 0.0) { sum = __dadd_rn(sum, __dmul_rn(v, (double)tn.mult)); cnt += tn.mult; t++; }
+                        else t = tn.skip;
+                    }
+                }
+                const double mean = cnt ? __ddiv_rn(sum, (double)cnt) : 0.0;
+                pass = act && mean >= thr_hi;
+                const bool unsure = act && !pass && mean >= thr_lo;
+                uint32_t um = __ballot_sync(FULL_MASK, unsure);
+                while (um) {                                  // the reference's own sum, one model at a time
+                    const int mm = __shfl_sync(FULL_MASK, m, __ffs(um) - 1);
+                    const bool mine = unsure && m == mm;
+                    if (gate_pass(c_models[mm], lookup, mine, p0, p1, J.min_bpp)) pass = true;
+                    um &= ~__ballot_sync(FULL_MASK, mine);
+                }
+            }
+            const uint32_t pmask = __ballot_sync(FULL_MASK, pass);
+            if (pass) { q2[qn2 + __popc(pmask & lt_mask)] = c; atomicAdd(&sm.gate_pass[m], 1u); }
+            qn2 += __popc(pmask);
+            __syncwarp();
+        };
+        auto consume = [&](const bool drain, const int brute_model) {
+            if (drain) { while (qn1 > 0) gate_batch(min(qn1, 32), brute_model); }
+            else if (qn1 >= 32) gate_batch(32, brute_model);
+            if (no_score) qn2 = 0;
+            if (qn2 >= 32) engine(false);
+        };
+
+        if (BRUTE) {
+            // every placement of the odometer is a candidate: 32 placements per lane word
+            for (int m = 0; m < n_models; m++) {
+                const CModel &M = c_models[m];
+                const int L1 = M.chain_len[1];
+                const int n0 = rows_of(wlen, M.chain_len[0]);
+                const int p1_max = p1_last(wlen, L1, M.symmetric ? n0 - 1 : 0);
+                const int nw = (p1_max >> 5) + 1;
+                const int items = n0 * nw;
+                for (int base = wid * 32; base < items; base += SCAN_THREADS) {
+                    const int t = base + lane;
+                    uint32_t cw = 0;
+                    int p0 = 0, wd = 0;
+                    if (t < items) {
+                        p0 = t / nw; wd = t - p0 * nw;
+                        const int lo = M.symmetric ? p0 : 0;     // odometer range of p1 for this p0
+                        const int hi = p1_last(wlen, L1, lo);
+                        const int blo = lo - (wd << 5), bhi = hi - (wd << 5);
+                        cw = bhi < 0 || blo > 31 ? 0u : 0xffffffffu;
+                        if (blo > 0 && blo <= 31) cw &= 0xffffffffu << blo;
+                        if (bhi >= 0 && bhi < 31) cw &= 0xffffffffu >> (31 - bhi);
+                    }
+                    while (__any_sync(FULL_MASK, cw != 0)) {      // one candidate per lane per round
+                        const bool has = cw != 0;
+                        const int b = has ? __ffs(cw) - 1 : 0;
+                        cw &= cw - 1;
+                        const uint32_t pmask = __ballot_sync(FULL_MASK, has);
+                        if (has) q1[qn1 + __popc(pmask & lt_mask)] = (uint32_t)p0 | ((uint32_t)((wd << 5) + b) << 8) | ((uint32_t)m << 16);
+                        qn1 += __popc(pmask);
+                        __syncwarp();
+                        consume(false, m);
+                    }
+                }
+                consume(true, m);                                // the exact gate reads one model's program
+            }
+        } else {
+            // big entries x trie nodes -> placements (see the header of this file).  Every warp works on its
+            // own share of the entries: no team-wide barrier in this loop.
+            const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
+            uint32_t *wl = sm.wl[wid], *s2 = sm.s2[wid];
+            const int n_prel = c_n_prel;
+            for (int g0 = 0; g0 < n_models; g0 += CB_MODELS) {
+                const int g1 = min(g0 + CB_MODELS, n_models);
+                if (g0 > 0) {                                    // bitmaps of the next group of models
+                    team_sync(team);
+                    for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+                    team_sync(team);
+                }
+                int nl = 0, ns = 0;                              // warp-uniform fills of wl and s2
+
+                // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
+                auto stage2 = [&](const int n) {
+                    const bool act = lane < n;
+                    const uint32_t it = act ? s2[ns - n + lane] : 0;
+                    ns -= n;
+                    __syncwarp();
+                    const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
+                    const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
+                    bool ok = act;
+                    int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
+                    while (__any_sync(FULL_MASK, ok && a >= 0)) {  // every pair before it must be non-zero
+                        if (ok && a >= 0) {
+                            const TrieNode an = sm.trie[a];
+                            ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
+                            a = an.parent;
                         }
                     }
-                    const uint32_t bm = __ballot_sync(FULL_MASK, isbig);
-                    if (isbig) wl[nl + __popc(bm & lt_mask)] = en;
-                    nl += __popc(bm);
+                    if (ok) {
+                        const uint32_t bit = 1u << (p1 & 31);
+                        ok = !(atomicOr(&sm.CB[tn.model - g0][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
+                    }
+                    const bool sure = ok && (it >> 31);
+                    const uint32_t om = __ballot_sync(FULL_MASK, ok);
+                    const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
+                    const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
+                    if (sure) { q2[qn2 + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
+                    else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
+                    qn2 += __popc(smask);
+                    qn1 += __popc(cmask);
                     __syncwarp();
-                }
-                if (nl == 0) break;
-                // a row of items: lane = (entry, orientation)
-                const int take = min(nl, 16);
-                const bool valid = (lane >> 1) < take;
-                const uint32_t en = wl[valid ? nl - take + (lane >> 1) : 0];
-                nl -= take;
-                __syncwarp();
-                const int er = (lane & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
-                const int ec = (lane & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
-                uint32_t PM = 0x80000000u;                        // which parent-relative pairs are present (bit 31: no parent)
-                for (int k = 0; k < n_prel; k++) {
-                    const uint32_t d = sm.prel[k];
-                    if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
-                }
-                for (int m = g0; m < g1; m++) {
-                    const uint32_t bd = sm.bounds[m];
-                    const uint32_t n0 = bd & 0xffu;
-                    const int hi = (int)((bd >> 8) & 0xffu);
-                    const bool sym = bd >> 16;
-                    const uint32_t sure_m = ((en >> (16 + m)) & 1u) << 31;
-                    const int t1 = sm.trie_end[m];
-                    for (int t = sm.trie0[m]; t < t1; t++) {      // warp-uniform trie node
-                        const TrieNode tn = sm.trie[t];
-                        const int p0 = er - tn.ro, p1 = ec - tn.co;
-                        bool ok = valid && ((PM >> tn.pbit) & 1u) && (uint32_t)p0 < n0;
-                        if (sym) ok = ok && p1 >= p0 && (p1 <= hi || p1 == p0);
-                        else ok = ok && (uint32_t)p1 <= (uint32_t)hi;
-                        const uint32_t om = __ballot_sync(FULL_MASK, ok);
-                        if (om == 0) continue;
-                        if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | sure_m;
-                        ns += __popc(om);
+                    consume(false, 0);
+                };
+
+                for (int chunk = wid * 32;;) {
+                    while (nl < 16 && chunk < nnz) {              // the warp's next 32 entries: keep the big ones
+                        const int e = chunk + lane;
+                        chunk += SCAN_THREADS;
+                        uint32_t en = 0;
+                        bool isbig = false;
+                        if (e < nnz) {
+                            const double p = __ldg(vals + e);
+                            if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
+                            if (p >= big_min) {
+                                isbig = true;
+                                uint32_t sure = 0;
+                                for (int m = g0; m < g1; m++) sure |= (p >= sm.sure_min[m] ? 1u : 0u) << m;
+                                en = (uint32_t)J.bpp_i[b0 + e] | ((uint32_t)J.bpp_j[b0 + e] << 8) | (sure << 16);
+                            }
+                        }
+                        const uint32_t bm = __ballot_sync(FULL_MASK, isbig);
+                        if (isbig) wl[nl + __popc(bm & lt_mask)] = en;
+                        nl += __popc(bm);
                         __syncwarp();
-                        if (ns >= 32) stage2(32);
+                    }
+                    if (nl == 0) break;
+                    // a row of items: lane = (entry, orientation)
+                    const int take = min(nl, 16);
+                    const bool valid = (lane >> 1) < take;
+                    const uint32_t en = wl[valid ? nl - take + (lane >> 1) : 0];
+                    nl -= take;
+                    __syncwarp();
+                    const int er = (lane & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
+                    const int ec = (lane & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
+                    uint32_t PM = 0x80000000u;                    // which parent-relative pairs are present (bit 31: no parent)
+                    for (int k = 0; k < n_prel; k++) {
+                        const uint32_t d = sm.prel[k];
+                        if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
+                    }
+                    for (int m = g0; m < g1; m++) {
+                        const uint32_t bd = sm.bounds[m];
+                        const uint32_t n0 = bd & 0xffu;
+                        const int hi = (int)((bd >> 8) & 0xffu);
+                        const bool sym = bd >> 16;
+                        const uint32_t sure_m = ((en >> (16 + m)) & 1u) << 31;
+                        const int t1 = sm.trie_end[m];
+                        for (int t = sm.trie0[m]; t < t1; t++) {  // warp-uniform trie node
+                            const TrieNode tn = sm.trie[t];
+                            const int p0 = er - tn.ro, p1 = ec - tn.co;
+                            bool ok = valid && ((PM >> tn.pbit) & 1u) && (uint32_t)p0 < n0;
+                            if (sym) ok = ok && p1 >= p0 && (p1 <= hi || p1 == p0);
+                            else ok = ok && (uint32_t)p1 <= (uint32_t)hi;
+                            const uint32_t om = __ballot_sync(FULL_MASK, ok);
+                            if (om == 0) continue;
+                            if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | sure_m;
+                            ns += __popc(om);
+                            __syncwarp();
+                            if (ns >= 32) stage2(32);
+                        }
                     }
                 }
+                if (ns > 0) stage2(ns);                          // the bitmaps belong to this group
             }
-            if (ns > 0) stage2(ns);                              // the bitmaps belong to this group
+            consume(true, 0);
         }
-        consume(true, 0);
-    }
-    if (tid == 0) {                                             // tests_all: closed form of the odometer
-        for (int m = 0; m < n_models; m++) {
-            const CModel &M = c_models[m];
-            const int L1 = M.chain_len[1];
-            const int n0 = rows_of(wlen, M.chain_len[0]);
-            if (M.symmetric) {                                  // sum over p0 < n0 of max(1, A - p0), A = wlen - L1
-                const long long A = wlen - L1, k = A > 0 ? (A < n0 ? A : n0) : 0;
-                tests_all += (unsigned long long)(k * A - k * (k - 1) / 2 + (n0 - k));
-            } else {
-                tests_all += (unsigned long long)n0 * (unsigned long long)(p1_last(wlen, L1, 0) + 1);
+        if (no_score) qn2 = 0;
+        engine(true);
+        team_sync(team);
+        if (tid < n_models) {
+            O.gate_pass[(long long)win_local * n_models + tid] = sm.gate_pass[tid];
+            if (sm.gate_pass[tid]) atomicAdd(&O.raw_count[2], (unsigned long long)sm.gate_pass[tid]);
+        }
+        if (tid == 0) {                                         // tests_all: closed form of the odometer
+            unsigned long long tests_all = 0;
+            for (int m = 0; m < n_models; m++) {
+                const CModel &M = c_models[m];
+                const int L1 = M.chain_len[1];
+                const int n0 = rows_of(wlen, M.chain_len[0]);
+                if (M.symmetric) {                              // sum over p0 < n0 of max(1, A - p0), A = wlen - L1
+                    const long long A = wlen - L1, k = A > 0 ? (A < n0 ? A : n0) : 0;
+                    tests_all += (unsigned long long)(k * A - k * (k - 1) / 2 + (n0 - k));
+                } else {
+                    tests_all += (unsigned long long)n0 * (unsigned long long)(p1_last(wlen, L1, 0) + 1);
+                }
             }
+            atomicAdd(&O.raw_count[1], tests_all);
         }
+#ifdef RMD_STATS
+        if (lane == 0) { atomicAdd(&O.raw_count[4], dbg_visits); atomicAdd(&O.raw_count[5], dbg_iter); }
+#endif
     }
-    if (no_score) qn2 = 0;
-    engine(true);
-    __syncthreads();
-    if (tid < n_models) {
-        O.gate_pass[(long long)win_local * n_models + tid] = sm.gate_pass[tid];
-        if (sm.gate_pass[tid]) atomicAdd(&O.raw_count[2], (unsigned long long)sm.gate_pass[tid]);
-    }
-    if (tid == 0) atomicAdd(&O.raw_count[1], tests_all);
-    if ((J.debug & 8) && lane == 0) { atomicAdd(&O.raw_count[4], dbg_visits); atomicAdd(&O.raw_count[5], dbg_iter); }
 }
 
 // ------------------------------------------------------------------------------------------------
