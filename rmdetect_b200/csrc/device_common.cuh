@@ -50,22 +50,27 @@ static_assert(sizeof(TrieNode) == 8, "TrieNode layout");
 __constant__ TrieNode c_trie[TRIE_CAP];
 __constant__ uint16_t c_prel[32];   // distinct (parent - node) offsets over all tries: (dr & 0xff) | (dc & 0xff) << 8
 __constant__ int c_n_prel;
+__constant__ unsigned long long c_nodemask[32][2];   // trie nodes with pbit == k, as a 128-bit mask
 
 // Search-tree node as the scoring engine reads it (32 bytes, built by rmd_set_models from
-// rmd_tree_node; all models concatenated, indices absolute).  A letter selector is
-// sh | oft << 8: position = ((p0 | p1 << 16) >> sh & 0xffff) + oft with sh = 0 / 16 for chain 0 / 1;
-// a gap (and an absent parent) has sh = 32 and oft = the sentinel slot that holds the gap code.
+// rmd_tree_node; all models concatenated, indices absolute).  The engine keeps the 16 letters from
+// p0 on and the 16 letters from p1 on as one 64-bit word, two bits per letter; a letter selector is the
+// bit position k = 2 * offset + 32 * chain.  A gap parent is folded into `cpt`, an absent one has stride 0.
 struct XNode {
-    int32_t own, par0, par1;
+    uint32_t sel;             // k_own | k_parent0 << 8 | k_parent1 << 16 | XSEL_OWN_GAP
     uint32_t cpt;             // index of the node's first CPT entry in the concatenated table
-    uint16_t m0, m1;          // CPT strides of the parents' letters (0: no such parent)
+    uint16_t m0, m1;          // CPT strides of the parents' letters
     uint16_t skip, next;      // node after the subtree / next node in preorder; XNODE_END ends the walk
     uint16_t leaf;
     uint8_t model, fb;        // fb = flags | bdepth << 4
     int16_t dlo;              // CHECK_DIST node (lib/node.py:184-192): the walk dies when dlo <= p1 - p0 < dlo + dspan
     uint16_t dspan;           // 0 elsewhere
+    uint32_t pad_[2];
 };
 static_assert(sizeof(XNode) == 32, "XNode layout");
+#define XSEL_OWN_GAP (1u << 24)
+#define XNODE_MAX_OFFSET 15                  // letters per chain held in the engine's word
+#define RMD_SURV_MAX_SEQ 4096                // GC-table rows a survivor record can name
 #define XNODE_END 0xffffu
 #define LETTER_GAP_SLOT RMD_FAST_WINDOW      // letters[LETTER_GAP_SLOT] holds the gap code (4)
 
@@ -86,6 +91,7 @@ struct DevJob {
     const XNode *xnodes;         // all models' search trees (scoring engine format)
     const double *xcpt;          // all models' CPTs, concatenated
     int n_xnodes, n_xcpt;
+    int motif_ok;                // every chain of every model fits the scoring engine's letter word
     int debug;                   // profiling experiments only (RMD_DEBUG): 1 skip scoring, 2 skip the exact gate
 };
 
@@ -100,8 +106,15 @@ struct RawHit {
 };
 static_assert(sizeof(RawHit) == 32, "RawHit layout");
 
+// per launch pair: window counter of the persistent scan kernel, survivors appended, survivors taken by score_kernel
+struct LaunchCtl { unsigned int next_window, pad0; unsigned long long surv_count, head, pad1; };
+
 struct ScanOut {
     RawHit *raw;
+    unsigned long long *stats;       // RMD_STATS builds: cycles per phase, summed over warps
+    uint4 *surv;                     // gate survivors for score_kernel: window, p0 | p1 << 8 | model << 16 | seq << 20, letters of chain 0, of chain 1
+    long long surv_cap;
+    struct LaunchCtl *ctl;           // counters of this launch pair (scan_fast_kernel + score_kernel)
     unsigned long long *raw_count;   // [0] records appended, [1] tests_all, [2] tests_pairs
     long long raw_cap;
     uint32_t *gate_pass;             // [n_win_range][n_models]
@@ -141,6 +154,17 @@ __device__ __forceinline__ int rows_of(int wlen, int L0) { return wlen - L0 > 1 
 __device__ __forceinline__ int p1_last(int wlen, int L1, int p1_first) {
     int hi = wlen - L1 - 1;
     return hi > p1_first ? hi : p1_first;
+}
+
+// placements the odometer visits in a window of wlen letters, all p0 and p1 (closed form of the loop)
+__device__ __forceinline__ unsigned long long odometer_count(const CModel &M, int wlen) {
+    const int L1 = M.chain_len[1];
+    const int n0 = rows_of(wlen, M.chain_len[0]);
+    if (M.symmetric) {                                      // sum over p0 < n0 of max(1, A - p0), A = wlen - L1
+        const long long A = wlen - L1, k = A > 0 ? (A < n0 ? A : n0) : 0;
+        return (unsigned long long)(k * A - k * (k - 1) / 2 + (n0 - k));
+    }
+    return (unsigned long long)n0 * (unsigned long long)(p1_last(wlen, L1, 0) + 1);
 }
 
 struct EvalOut { int leaf; double pm, pr; };

@@ -36,6 +36,7 @@ struct rmd_ctx {
     std::vector<void *> ev_allocs[RMD_MAX_MODELS];
     int max_chain = 0;
     int n_xnodes = 0, n_xcpt = 0, sm_count = 0;
+    bool motif_ok = true;
     bool any_brute = false;             // some model gives no anchor for candidates: scan_fast_kernel<true>
     DBuf d_xnodes, d_xcpt, d_next;
     int teams = 8, ctas_per_sm = 1;      // shape of the persistent scan kernel (rmd_set_models)
@@ -173,6 +174,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     TrieNode htrie[TRIE_CAP];
     memset(htrie, 0, sizeof htrie);
     std::vector<XNode> hx;
+    bool motif_ok = true;
     uint16_t hprel[32] = {0};
     int n_prel = 0;
     bool prel_overflow = false;
@@ -269,20 +271,26 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
             if (d.n_leaves > 65535) return fail(ctx, RMD_E_LIMIT, "model %d: too many gap configurations", m);
             c.xnode0 = (int)x0;
             hcpt.insert(hcpt.end(), d.cpt, d.cpt + (size_t)d.n_cpt_rows * RMD_NSYM);
-            auto selector = [](int chain, int oft) -> int32_t {
-                if (oft < 0) return (int32_t)(32 | (LETTER_GAP_SLOT << 8));            // a gap reads the sentinel slot
-                return (int32_t)((chain ? 16 : 0) | (oft << 8));
-            };
             for (int t = 0; t < d.n_tree; t++) {
                 const rmd_tree_node &n = d.tree[t];
                 XNode x;
                 memset(&x, 0, sizeof x);
-                x.own = selector(n.chain, n.oft);
-                x.par0 = n.npar > 0 ? selector(n.par_chain[0], n.par_oft[0]) : selector(0, -1);
-                x.par1 = n.npar > 1 ? selector(n.par_chain[1], n.par_oft[1]) : selector(0, -1);
-                x.cpt = (uint32_t)(cpt0 + (size_t)n.cpt_row * RMD_NSYM);
-                x.m0 = n.npar == 1 ? RMD_NSYM : n.npar == 2 ? RMD_NSYM * RMD_NSYM : 0;     // row = c0, or c0 * 6 + c1
-                x.m1 = n.npar == 2 ? RMD_NSYM : 0;
+                const int stride[2] = {n.npar == 1 ? RMD_NSYM : n.npar == 2 ? RMD_NSYM * RMD_NSYM : 0,      // row = c0, or c0 * 6 + c1
+                                       n.npar == 2 ? RMD_NSYM : 0};
+                size_t base = cpt0 + (size_t)n.cpt_row * RMD_NSYM;
+                uint32_t sel = 0;
+                if (n.oft < 0) sel |= XSEL_OWN_GAP;
+                else { if (n.oft > XNODE_MAX_OFFSET) motif_ok = false; sel |= (uint32_t)((2 * n.oft + 32 * (n.chain ? 1 : 0)) & 63); }
+                uint16_t mm[2] = {0, 0};
+                for (int k = 0; k < n.npar; k++) {
+                    if (n.par_oft[k] < 0) base += (size_t)4 * stride[k];                 // a gap parent: its letter is the gap code
+                    else {
+                        if (n.par_oft[k] > XNODE_MAX_OFFSET) motif_ok = false;
+                        sel |= (uint32_t)((2 * n.par_oft[k] + 32 * (n.par_chain[k] ? 1 : 0)) & 63) << (8 + 8 * k);
+                        mm[k] = (uint16_t)stride[k];
+                    }
+                }
+                x.sel = sel; x.cpt = (uint32_t)base; x.m0 = mm[0]; x.m1 = mm[1];
                 x.skip = n.skip >= d.n_tree ? (uint16_t)XNODE_END : (uint16_t)(x0 + n.skip);
                 x.next = t + 1 >= d.n_tree ? (uint16_t)XNODE_END : (uint16_t)(x0 + t + 1);
                 x.leaf = n.leaf; x.model = (uint8_t)m;
@@ -309,7 +317,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     CK(cudaMemcpy(ctx->d_xnodes.p, hx.data(), sizeof(XNode) * hx.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_xcpt.p, hcpt.data(), sizeof(double) * hcpt.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpyToSymbol(c_trie, htrie, sizeof htrie));
-    ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size();
+    ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size(); ctx->motif_ok = motif_ok;
     {   // shape of the persistent scan kernel: tables + one FastSmem per team within the SM's shared memory
         int smem_max = 0;
         CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -391,7 +399,7 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
     J.debug = getenv("RMD_DEBUG") ? atoi(getenv("RMD_DEBUG")) : 0;
     J.seq_off = (const long long *)ctx->d_seq_off.p; J.win_base = (const long long *)ctx->d_win_base.p;
     J.xnodes = (const XNode *)ctx->d_xnodes.p; J.xcpt = (const double *)ctx->d_xcpt.p;
-    J.n_xnodes = ctx->n_xnodes; J.n_xcpt = ctx->n_xcpt;
+    J.n_xnodes = ctx->n_xnodes; J.n_xcpt = ctx->n_xcpt; J.motif_ok = ctx->motif_ok ? 1 : 0;
     return RMD_OK;
 }
 
@@ -554,9 +562,9 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(ngroups + 1));
     if (ctx->raw_cap == 0) ctx->raw_cap = std::max<long long>(1 << 16, 24 * nwin);
     // the shared-memory kernel takes windows longer than every chain and up to 160 letters
-    const bool use_fast = ctx->max_chain <= 32;
+    const bool use_fast = ctx->max_chain <= 32 && ctx->motif_ok;
     const int min_fast_wlen = use_fast ? ctx->max_chain + 1 : 0x7fffffff;
-    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen;
+    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen || ctx->any_other;
     unsigned long long counters[8];
     int launches = 0;
     for (int attempt = 0; attempt < 2; attempt++) {

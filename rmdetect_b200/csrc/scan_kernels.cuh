@@ -77,7 +77,9 @@ struct FastSmem {
     uint32_t scan_tmp[SCAN_WARPS];
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
-    uint8_t letters[FAST_W + 16];        // slot LETTER_GAP_SLOT holds the gap code
+    uint8_t letters[FAST_W + 16];
+    uint32_t l2[FAST_W / 16 + 2];        // the letters again, two bits each (meaningful when plain)
+    uint32_t plain;                      // every letter of the window is one of ACGU
 };
 
 // is pair (b1, b2) stored?  (lib/bpprobs.py:17-18; the diagonal is never stored)
@@ -209,8 +211,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
         for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
         for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
-        for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS)
-            sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : (k == LETTER_GAP_SLOT ? 4 : 0);
+        for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
+        if (tid == 0) sm.plain = 1;
         if (tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
         if (tid < n_models) {
             const CModel &M = c_models[tid];
@@ -220,6 +222,17 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                              (M.symmetric ? 1u << 16 : 0u);
         }
         team_sync(team);
+        if (tid < FAST_W / 16 + 2) {                          // two-bit letters for the scoring engine
+            uint32_t word = 0, other = 0;
+            for (int k = 0; k < 16; k++) {
+                const int pos = tid * 16 + k;
+                const uint32_t c = pos < FAST_W + 16 ? sm.letters[pos] : 0;
+                word |= (c & 3u) << (2 * k);
+                other |= c >> 2;
+            }
+            sm.l2[tid] = word;
+            if (other) atomicAnd(&sm.plain, 0u);
+        }
         for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) { // four entries per thread in flight
             int ei[4], ej[4];
 #pragma unroll
@@ -246,15 +259,17 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             for (int k = 0; k < WORDS_PER_THREAD; k++)
                 if (k0 + k < UWORDS) { sm.Ur[k0 + k] = (uint16_t)run; run += __popc(sm.Ub[k0 + k]); }
             // the ranks are list positions only if every entry set its own bit
-            if (tid == 0 && total != (uint32_t)nnz) atomicOr(&O.raw_count[7], ERR_BAD_LIST);
+            if (tid == 0 && total != (uint32_t)nnz && sm.plain) atomicOr(&O.raw_count[7], ERR_BAD_LIST);
         }
         team_sync(team);
+        if (!sm.plain) continue;                              // a letter other than ACGU: the window is scan_generic_kernel's
 
         auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
         int qn1 = 0, qn2 = 0;                               // warp-uniform queue fills
 
         // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ------
         uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
+        unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
         int e_leaf = -1;                                    // best leaf | model << 16
         double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
         double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
@@ -270,8 +285,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const int r = __popc(im & lt_mask);
                     if ((im >> lane & 1) && r < qn2) {
                         const uint32_t c = q2[qn2 - 1 - r];
-                        e_c = (c & 0xffu) | ((c & 0xff00u) << 8);
+                        const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu;
+                        e_c = p0 | (p1 << 16);
                         e_t = sm.xnode0[c >> 16];
+                        e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
+                              ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
                         e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
                         e_stk[0] = make_double2(0.0, 0.0);
                     }
@@ -285,21 +303,19 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 #endif
                 const bool busy = e_t != XNODE_END;
                 if (busy) {
-                    const uint4 a = xn[2 * e_t], b = xn[2 * e_t + 1];
-                    auto letter = [&](const uint32_t sel) {
-                        return (int)sm.letters[(__funnelshift_rc(e_c, 0u, sel & 0xffu) & 0xffffu) + ((int)sel >> 8)];
-                    };
-                    const int nt = letter(a.x), c0 = letter(a.y), c1 = letter(a.z);         // :199-213
-                    const uint32_t idx = a.w + min(nt, 5) + min(c0, 5) * (b.x & 0xffffu) + min(c1, 5) * (b.x >> 16);
-                    double v = xcpt[idx];
+                    const uint4 a = xn[2 * e_t];                      // sel, cpt, m0 | m1 << 16, skip | next << 16
+                    const uint2 b = *reinterpret_cast<const uint2 *>(xn + 2 * e_t + 1);   // leaf | model << 16 | flags << 24 | bdepth << 28, dlo | dspan << 16
+                    const int nt = (a.x & XSEL_OWN_GAP) ? 4 : (int)((uint32_t)(e_m >> (a.x & 63u)) & 3u);          // :199-213
+                    const uint32_t c0 = (uint32_t)(e_m >> ((a.x >> 8) & 63u)) & 3u, c1 = (uint32_t)(e_m >> ((a.x >> 16) & 63u)) & 3u;
+                    double v = xcpt[a.y + nt + c0 * (a.z & 0xffffu) + c1 * (a.z >> 16)];
                     const double g = sm.gc[nt];                       // :223 (slot 4 holds log 0.25)
                     if (v == CUDART_INF) v = g;                       // GC-sentinel row (:217-218)
-                    const uint32_t fl = b.z;                          // leaf | model << 16 | flags << 24 | bdepth << 28
+                    const uint32_t fl = b.x;
                     const int bdepth = fl >> 28;
                     if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
                     // :184-192 as one interval test: chains closer than the configuration allows (empty unless CHECK_DIST)
                     const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);
-                    const bool apart = (uint32_t)(d - (int)(short)(b.w & 0xffffu)) >= (b.w >> 16);
+                    const bool apart = (uint32_t)(d - (int)(short)(b.y & 0xffffu)) >= (b.y >> 16);
                     e_pm = __dadd_rn(e_pm, v);                        // :227-228
                     e_pr = __dadd_rn(e_pr, g);
                     // a node that fails is left through its skip link, and whatever comes next restores the sums
@@ -308,7 +324,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                         e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
                     }
                     if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
-                    e_t = alive ? (b.y >> 16) : (b.y & 0xffffu);
+                    e_t = alive ? (a.w >> 16) : (a.w & 0xffffu);
                 }
                 const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
                 if (dm == 0) continue;
@@ -537,17 +553,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         }
         if (tid == 0) {                                         // tests_all: closed form of the odometer
             unsigned long long tests_all = 0;
-            for (int m = 0; m < n_models; m++) {
-                const CModel &M = c_models[m];
-                const int L1 = M.chain_len[1];
-                const int n0 = rows_of(wlen, M.chain_len[0]);
-                if (M.symmetric) {                              // sum over p0 < n0 of max(1, A - p0), A = wlen - L1
-                    const long long A = wlen - L1, k = A > 0 ? (A < n0 ? A : n0) : 0;
-                    tests_all += (unsigned long long)(k * A - k * (k - 1) / 2 + (n0 - k));
-                } else {
-                    tests_all += (unsigned long long)n0 * (unsigned long long)(p1_last(wlen, L1, 0) + 1);
-                }
-            }
+            for (int m = 0; m < n_models; m++) tests_all += odometer_count(c_models[m], wlen);
             atomicAdd(&O.raw_count[1], tests_all);
         }
 #ifdef RMD_STATS
@@ -592,11 +598,25 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     int seq, wlen;
     long long start;
     window_geom(J, w, seq, start, wlen);
-    if (wlen <= 0 || (wlen >= min_fast_wlen && wlen <= FAST_W)) return;    // those windows: scan_fast_kernel
+    if (wlen <= 0) return;
+    if (wlen >= min_fast_wlen && wlen <= FAST_W) {                         // scan_fast_kernel's, unless a letter is not ACGU
+        int other = 0;
+        if (J.codes8) for (int k = tid; k < wlen; k += GEN_THREADS) other |= J.codes8[J.seq_off[seq] + start + k] > 3;
+        if (!__syncthreads_or(other)) return;
+    }
     const CModel &M = c_models[m];
     const long long gbase = J.seq_off[seq] + start;
     const long long b0 = J.bpp_off[w];
     const int nnz = (int)(J.bpp_off[w + 1] - b0);
+    if (nnz == 0 && J.min_bpp > 0.0) {             // no pair, positive threshold: every placement fails the gate (mean 0.0)
+        if (tid == 0) {
+            const long long grp = (w - w_base) * J.n_models + m;
+            O.gate_pass[grp] = 0;
+            O.group_hits[grp] = 0;
+            atomicAdd(&O.raw_count[1], odometer_count(M, wlen));
+        }
+        return;
+    }
     if (tid < RMD_N_CODES) gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
     if (tid == 0) s_pass = 0;
     __syncthreads();

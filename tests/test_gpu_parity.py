@@ -238,3 +238,100 @@ def test_one_megabase_counts_match_oracle():
     assert res["n_raw"] == nh
     assert tries[0] == n_win * 70939
     eng.close()
+
+
+class _TableFold:
+    """bpp provider for tests: window string -> (i, j, p) arrays."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def coo(self, win):
+        return self.fn(win)
+
+
+def _scan_vs_oracle(names, seq, fold, min_bpp, win_len=150, win_step=75):
+    from oracle import pyoracle
+    from rmdetect_b200.scanner import ScanEngine
+    eng = ScanEngine([load_model(n) for n in names], [load_evalues(n) for n in names], LN_UNKNOWN)
+    res = eng.scan_job(eng.build_job([("s", seq, None)], win_len, win_step, fold, "", min_bpp, LN_CUTOFF))
+    eng.close()
+    oms = [pyoracle.OracleModel(load_model(n)) for n in names]
+    oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+    starts = pyoracle.windows(len(seq), win_len, win_step)
+    hits, tries, _ = pyoracle.scan_sequence(oms, oes, 0, seq, win_len, win_step, [fold.coo(seq[s:s + win_len]) for s in starts],
+                                            min_bpp, LN_UNKNOWN, LN_CUTOFF)
+    assert res["tries"] == tries
+    assert len(res["hits"]) == len(hits)
+    for g, w in zip(res["hits"], hits):
+        assert (g["model"], g["start"], g["p0"], g["p1"], g["leaf"]) == (w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"])
+        assert (g["prob_model"], g["prob_rand"], g["score"], g["evalue"]) == (w["prob_model"], w["prob_rand"], w["score"], w["evalue"])
+    return res
+
+
+@pytest.mark.parametrize("min_bpp", [0.0, -1.0])
+def test_non_positive_threshold_takes_every_placement(min_bpp):
+    """min_bpp_mean <= 0: the mean of no pairs (0.0) passes, every placement is scored (lib/scanner.py:143,211-214)."""
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    seq = synth_sequence(190, 31)
+    res = _scan_vs_oracle(["KT_1.0", "TGA_1.0"], seq, SynthFold(4), min_bpp)
+    assert res["tries"][0] == res["tries"][1]
+
+
+def test_gate_mean_on_the_threshold():
+    """Means that sit exactly on, one ulp under and one ulp over min_bpp_mean: the kernel's fast sum
+    (value x multiplicity) must hand these to the reference-order sum."""
+    from rmdetect_b200.synth import synth_bpp_coo, synth_sequence
+    t = 0.001
+    near = [t, np.nextafter(t, 0.0), np.nextafter(t, 1.0), 3 * t - 2 * np.nextafter(t, 1.0), 2 * t, t / 2, t / 3, 1e-5, 0.0015, 0.0005]
+
+    def fold(win):
+        i, j, p = synth_bpp_coo(win, 12)
+        p = p.copy()
+        rng = random.Random(len(win) * 7919 + sum(map(ord, win[:20])))
+        for k in range(len(p)):
+            p[k] = near[rng.randrange(len(near))]
+        return i, j, p
+
+    seq = synth_sequence(450, 8)
+    _scan_vs_oracle(MODEL_ORDER, seq, _TableFold(fold), t)
+
+
+def test_dense_matrix_window():
+    """Every pair of the window stored (11 175 entries): list ranks beyond 8 bits, every trie node alive."""
+    from rmdetect_b200.synth import synth_sequence
+
+    def fold(win):
+        n = len(win)
+        i, j = np.triu_indices(n, 1)
+        rng = np.random.default_rng(n)
+        return i.astype(np.uint16), j.astype(np.uint16), rng.choice([2e-4, 8e-4, 1.2e-3, 5e-3], size=len(i))
+
+    seq = synth_sequence(150, 3)
+    res = _scan_vs_oracle(["CL_1.0", "GB_1.0"], seq, _TableFold(fold), 0.001)
+    assert res["tries"][1] > 1000
+
+
+def test_malformed_bpp_list_is_rejected():
+    """The kernel's own checks (the host layer sorts and validates; a C caller may not)."""
+    from rmdetect_b200._native import NativeError
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    seq = synth_sequence(150, 3)
+
+    def duplicate(job):
+        job["bpp_i"][7], job["bpp_j"][7] = job["bpp_i"][6], job["bpp_j"][6]
+
+    def negative(job):
+        job["bpp_p"][5] = -job["bpp_p"][5]
+
+    def lower_triangle(job):
+        job["bpp_i"][9], job["bpp_j"][9] = job["bpp_j"][9], job["bpp_i"][9]
+
+    for spoil in (duplicate, negative, lower_triangle):
+        eng = ScanEngine([load_model(n) for n in MODEL_ORDER], [None] * 4, LN_UNKNOWN)
+        job = eng.build_job([("s", seq, None)], 150, 75, SynthFold(1), "", 0.001, LN_CUTOFF)
+        spoil(job)
+        with pytest.raises(NativeError):
+            eng.scan_job(job)
+        eng.close()
