@@ -34,7 +34,8 @@ WIN_LEN, WIN_STEP = 150, 75
 MODEL_FILES = ["cl_1", "tga_1", "gb_1", "kt_1"]         # the order os.listdir gave the reference in the build container
 DATA = os.path.join(ROOT, "tests", "golden", "ref_data", "models")
 LN_UNKNOWN, LN_CUTOFF, MIN_BPP = math.log(1e-4), math.log(0.1), 0.001
-NCU_DRAM_BYTES_PER_LAUNCH = 1049848000 + 30227968        # one scan_fast_kernel launch over the 10 Mb workload
+CAL_SAMPLES = 1 << 20                                    # calibration samples per model and GPU
+NCU_DRAM_BYTES_PER_LAUNCH = 1047918000 + 27238912        # one scan_fast_kernel launch over the 10 Mb workload (ncu --set full)
 
 
 def load_models():
@@ -201,15 +202,33 @@ def run_ours(args):
     assert e["tries"] == tries and len(e["hits"]) == n_hits
     d2h = len(e["hits"]) * _native.HIT_DTYPE.itemsize + 2 * n_win * len(models) * 4 + 64
 
+    # ---- second metric: calibration samples per second (BASELINE.json configs[3], throughput mode) ----
+    # every rank scores its own CAL_SAMPLES device-drawn samples per model against the 165 GC classes
+    from rmdetect_b200.calibrate import class_logs
+    from rmdetect_b200.gcx import GC
+    cl = class_logs(GC.get_classes(5, 15, 85))
+    hists = [np.zeros((len(cl), 512)) for _ in models]
+    for mi, m in enumerate(models):                             # warm-up
+        ctx.calibrate(mi, None, cl, LN_CUTOFF, hists[mi], seed=SEED, first=0, n=1 << 14, L=len(m.nodes))
+    barrier()
+    t2 = time.perf_counter()
+    cal_kernel_ms = 0.0
+    for mi, m in enumerate(models):
+        _, ms_k = ctx.calibrate(mi, None, cl, LN_CUTOFF, hists[mi], seed=SEED, first=rank * CAL_SAMPLES, n=CAL_SAMPLES,
+                                L=len(m.nodes))
+        cal_kernel_ms += ms_k
+    barrier()
+    cal_wall = time.perf_counter() - t2
+
     # ---- reduce over ranks: time = max, work = sum ---------------------------------------------------
-    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_hits, n_raw, tries[0], tries[1]], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(gathered, cnt)                      # the only collective: small per-rank hit counts
         cnt = torch.stack(gathered).sum(0)
-    wall, e2e_wall, dev_ms, e2e_dev_ms = t.tolist()
+    wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms = t.tolist()
     total_units = units * world
     value = total_units * args.steps / wall
     e2e_value = total_units * args.steps / e2e_wall
@@ -245,11 +264,16 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "nt·model/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_wall / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
                     "api": "rmd_scan (C ABI) on pinned host buffers"},
+            "calibration": {"metric": "calibration samples scored/sec", "value": CAL_SAMPLES * len(models) * world / cal_wall,
+                            "unit": "samples/s", "samples_per_model_per_gpu": CAL_SAMPLES, "classes": int(len(cl)),
+                            "ms_total": 1e3 * cal_wall, "kernel_ms": cal_kernel_ms,
+                            "note": "rmd_calibrate_synth: device-drawn samples, 165 weighted scores each, histograms "
+                                    "downloaded per model; reference loop: ~3.5 k samples/s/core (SURVEY.md §6)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if args.mb == 10 else None,
-                         "traffic_source": "profiles/r01_scan_fast_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, "
+                         "traffic_source": "profiles/r01b_scan_fast_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, "
                                            "ncu --set full of this command)",
                          "kernel": "scan_fast_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo),
