@@ -23,6 +23,8 @@
  *   rmd_scan            the same with host buffers: upload + scan + result download
  *   rmd_eval            lib/node.py:176-277 called directly (rmcalibrate.py:279-281 style)
  *   rmd_calibrate       rmcalibrate.py:35-62,265-295 (sample scoring into weighted histograms)
+ *   rmd_parse_dot_ps    lib/rnatools.py:176-205 (parse_bpprobs: dot.ps text -> base-pair probabilities)
+ *   rmd_compact_bpp     no reference counterpart: lossless 6-byte transport form of a bpp entry
  *   rmd_synth_*         no reference counterpart: synthetic genome / stand-in bpp generators,
  *                       bit-identical twins of rmdetect_b200/synth.py, for benchmarks
  */
@@ -101,6 +103,10 @@ typedef struct rmd_scan_input {
     const double *bpp_p;
     double min_bpp_mean;
     double cutoff;              /* natural log, e.g. log(0.1) */
+    /* compact transport of the same lists (optional; when bpp_q is given, bpp_i / bpp_j / bpp_p are not read):
+       6 bytes per entry instead of 12, see rmd_compact_bpp() */
+    const uint16_t *bpp_ij;     /* i | j << 8 (windows up to 256 letters) */
+    const uint32_t *bpp_q;      /* round(sqrt(p) * 1e9) | (ulp correction + 1) << 30 */
 } rmd_scan_input;
 
 /* one hit, final order = window, model (as given to rmd_set_models), p0, p1 */
@@ -183,6 +189,22 @@ int rmd_download_codes(rmd_ctx *ctx, uint8_t *codes, int64_t n);
 int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint16_t *j, double *p, int64_t cap, int64_t *n);
 /* the whole resident bpp store: bpp_off[n_win + 1] and, when the pointers are not NULL, the n_bpp entries */
 int rmd_download_job(rmd_ctx *ctx, int64_t *bpp_off, uint16_t *i, uint16_t *j, double *p);
+
+/* Compact form of a coordinate list (host only, no device work).  RNAfold prints sqrt(p) with 9 decimals
+   (lib/rnatools.py:176-205 squares it with `** 2.0`), so p = (q / 1e9)^2 up to the last bit of libm's pow:
+   q = round(sqrt(p) * 1e9) < 2^30 and c in {-1, 0, +1} ulps are stored, and the device rebuilds exactly the
+   caller's double.  Returns RMD_E_INVALID (and the index in *first_bad) for an entry that has no such
+   form (i or j > 255, p further than one ulp from a squared 9-decimal number); use the fp64 arrays then. */
+int rmd_compact_bpp(const uint16_t *i, const uint16_t *j, const double *p, int64_t n,
+                    uint16_t *ij, uint32_t *q, int64_t *first_bad);
+
+/* Parse the text of a ViennaRNA dot.ps (replaces lib/rnatools.py:176-205 parse_bpprobs, reading the file
+   RNAfold -p really writes): every `i j sqrt(p) ubox` line becomes an entry (0-based, i < j, p = sqrt_p ** 2.0
+   as the reference computes it, zeros dropped, a later line for the same pair replaces the earlier one), the
+   result sorted by (i, j).  seq receives the /sequence block (NUL-terminated, at most seq_cap - 1 letters),
+   q may be NULL.  Returns RMD_E_LIMIT when cap is too small (*n = entries needed). */
+int rmd_parse_dot_ps(const char *text, int64_t len, uint16_t *i, uint16_t *j, double *p, uint32_t *q,
+                     int64_t cap, int64_t *n, char *seq, int64_t seq_cap);
 
 /* pinned host staging for callers that want full PCIe rate */
 void *rmd_host_alloc(int64_t bytes);

@@ -38,7 +38,8 @@ class ScanInput(C.Structure):
                 ("gc_log", C.c_void_p), ("gc_class", C.c_void_p),
                 ("win_len", C.c_int32), ("win_step", C.c_int32), ("n_win", C.c_int64),
                 ("bpp_off", C.c_void_p), ("bpp_i", C.c_void_p), ("bpp_j", C.c_void_p), ("bpp_p", C.c_void_p),
-                ("min_bpp_mean", C.c_double), ("cutoff", C.c_double)]
+                ("min_bpp_mean", C.c_double), ("cutoff", C.c_double),
+                ("bpp_ij", C.c_void_p), ("bpp_q", C.c_void_p)]
 
 
 class ScanResult(C.Structure):
@@ -56,7 +57,7 @@ assert HIT_DTYPE.itemsize == 72
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
            "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_scan_resident", "rmd_scan", "rmd_eval",
            "rmd_calibrate", "rmd_calibrate_synth", "rmd_synth_job", "rmd_download_codes", "rmd_download_bpp",
-           "rmd_download_job", "rmd_host_alloc", "rmd_host_free"]
+           "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
 
 _lib = None
 
@@ -95,6 +96,8 @@ def load_library():
     L.rmd_download_codes.argtypes = [vp, vp, i64]
     L.rmd_download_bpp.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(i64)]
     L.rmd_download_job.argtypes = [vp, vp, vp, vp, vp]
+    L.rmd_compact_bpp.argtypes = [vp, vp, vp, i64, vp, vp, C.POINTER(i64)]
+    L.rmd_parse_dot_ps.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, i64, C.POINTER(i64), C.c_char_p, i64]
     L.rmd_host_alloc.argtypes = [i64]
     L.rmd_host_alloc.restype = vp
     L.rmd_host_free.argtypes = [vp]
@@ -187,6 +190,7 @@ class Context:
         si.bpp_off, si.bpp_i, si.bpp_j, si.bpp_p = (_ptr(job["bpp_off"]), _ptr(job["bpp_i"]), _ptr(job["bpp_j"]),
                                                     _ptr(job["bpp_p"]))
         si.min_bpp_mean, si.cutoff = job["min_bpp_mean"], job["cutoff"]
+        si.bpp_ij, si.bpp_q = _ptr(job.get("bpp_ij")), _ptr(job.get("bpp_q"))       # compact transport (optional)
         return si
 
     def upload(self, job):
@@ -302,6 +306,43 @@ class Context:
         self._check(self.lib.rmd_download_job(self.h, off.ctypes.data, i.ctypes.data, j.ctypes.data, p.ctypes.data),
                     "rmd_download_job")
         return off, i, j, p
+
+
+def compact_bpp(i, j, p, pinned=False):
+    """(ij uint16[], q uint32[]) — the 6-byte transport form of a coordinate list (include/rmdetect_b200.h:
+    rmd_compact_bpp), or None when some entry has no such form."""
+    lib = load_library()
+    i = np.ascontiguousarray(i, dtype=np.uint16)
+    j = np.ascontiguousarray(j, dtype=np.uint16)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    n = len(p)
+    ij = pinned_array(n, np.uint16) if pinned else np.zeros(max(n, 1), dtype=np.uint16)
+    q = pinned_array(n, np.uint32) if pinned else np.zeros(max(n, 1), dtype=np.uint32)
+    bad = C.c_int64(-1)
+    rc = lib.rmd_compact_bpp(i.ctypes.data, j.ctypes.data, p.ctypes.data, n, ij.ctypes.data, q.ctypes.data, C.byref(bad))
+    if rc != 0:
+        return None
+    return ij[:n] if not pinned else ij, q[:n] if not pinned else q
+
+
+def parse_dot_ps(text):
+    """(sequence, i uint16[], j uint16[], p float64[], q uint32[]) from the text of a ViennaRNA dot.ps, by the
+    library's native parser (rmd_parse_dot_ps; replaces lib/rnatools.py:176-205 of the reference)."""
+    lib = load_library()
+    raw = text if isinstance(text, bytes) else text.encode("ascii", "replace")
+    cap = raw.count(b"ubox") + 1
+    i = np.zeros(cap, dtype=np.uint16)
+    j = np.zeros(cap, dtype=np.uint16)
+    p = np.zeros(cap, dtype=np.float64)
+    q = np.zeros(cap, dtype=np.uint32)
+    n = C.c_int64(0)
+    seq = C.create_string_buffer(len(raw) + 1)
+    rc = lib.rmd_parse_dot_ps(raw, len(raw), i.ctypes.data, j.ctypes.data, p.ctypes.data, q.ctypes.data, cap,
+                              C.byref(n), seq, len(raw) + 1)
+    if rc != 0:
+        raise NativeError("rmd_parse_dot_ps failed (%d)" % rc)
+    k = n.value
+    return seq.value.decode("ascii") or None, i[:k], j[:k], p[:k], q[:k]
 
 
 class _Pinned:

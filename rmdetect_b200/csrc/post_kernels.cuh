@@ -151,6 +151,19 @@ __global__ void compact_hits_kernel(const rmd_hit *hits, long long n, const uint
     if (i < n && keep[i]) out[keep_off[i]] = hits[i];
 }
 
+// ---- compact bpp transport -> the coordinate lists the scan reads (see rmd_compact_bpp) --------------
+// p = (q / 1e9)^2 moved by c - 1 ulps (c = top two bits): exactly the double the caller held.
+__global__ void expand_bpp_kernel(const uint16_t *ij, const uint32_t *q, long long n, uint16_t *oi, uint16_t *oj, double *op) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t w = ij[k], v = q[k];
+    const double x = __ddiv_rn((double)(v & 0x3fffffffu), 1e9);
+    const long long bits = __double_as_longlong(__dmul_rn(x, x)) + (long long)(v >> 30) - 1;
+    oi[k] = (uint16_t)(w & 0xffu);
+    oj[k] = (uint16_t)(w >> 8);
+    op[k] = __longlong_as_double(bits);
+}
+
 // ---- K2: pack letter codes to 2 bits, flag non-ACGU letters, count letters per sequence ---------
 __global__ void pack_codes_kernel(const uint8_t *codes8, long long n, uint32_t *codes2, int *any_other) {
     const long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one output word = 16 letters

@@ -50,7 +50,7 @@ struct rmd_ctx {
     bool any_other = false;
     std::vector<long long> h_seq_off, h_win_base;
     DBuf d_seq_off, d_win_base, d_codes8, d_codes2, d_gc_log, d_gc_class, d_bpp_off, d_bpp_i, d_bpp_j, d_bpp_p;
-    DBuf d_flag, d_counts, d_bpp_cnt;
+    DBuf d_flag, d_counts, d_bpp_cnt, d_bpp_ij, d_bpp_q;      // d_bpp_ij / d_bpp_q: compact transport staging
     // scan outputs
     DBuf d_raw, d_counters, d_gate_pass, d_group_hits, d_group_off, d_scan_sums, d_final, d_keep, d_keep_off, d_compact;
     rmd_hit *h_hits = nullptr;
@@ -130,7 +130,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
     cudaDeviceSynchronize();
     free_models(ctx);
     DBuf *bufs[] = {&ctx->d_seq_off, &ctx->d_win_base, &ctx->d_codes8, &ctx->d_codes2, &ctx->d_gc_log, &ctx->d_gc_class,
-                    &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt,
+                    &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt, &ctx->d_bpp_ij, &ctx->d_bpp_q,
                     &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
                     &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact,
                     &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
@@ -414,6 +414,28 @@ static int stage_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class)
     return RMD_OK;
 }
 
+// Copy bpp entries [e0, e1) of a job to the device on `copy_st`; with the compact transport the lists the scan
+// reads are rebuilt by expand_bpp_kernel, issued on the compute stream after the copy.
+static int stage_entries(rmd_ctx *ctx, const rmd_scan_input *in, long long e0, long long e1, cudaStream_t copy_st) {
+    if (e1 <= e0) return RMD_OK;
+    const size_t n = (size_t)(e1 - e0);
+    if (in->bpp_q) {
+        CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_ij.p + e0, in->bpp_ij + e0, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, copy_st));
+        CK(cudaMemcpyAsync((uint32_t *)ctx->d_bpp_q.p + e0, in->bpp_q + e0, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, copy_st));
+        if (copy_st != ctx->stream) {
+            CK(cudaEventRecord(ctx->ev[11], copy_st));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[11], 0));
+        }
+        expand_bpp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint16_t *)ctx->d_bpp_ij.p + e0, (const uint32_t *)ctx->d_bpp_q.p + e0, (long long)n,
+                                                                                 (uint16_t *)ctx->d_bpp_i.p + e0, (uint16_t *)ctx->d_bpp_j.p + e0, (double *)ctx->d_bpp_p.p + e0);
+    } else {
+        CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_i.p + e0, in->bpp_i + e0, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, copy_st));
+        CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_j.p + e0, in->bpp_j + e0, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, copy_st));
+        CK(cudaMemcpyAsync((double *)ctx->d_bpp_p.p + e0, in->bpp_p + e0, sizeof(double) * n, cudaMemcpyHostToDevice, copy_st));
+    }
+    return RMD_OK;
+}
+
 // Stage a job.  with_entries == false leaves the bpp entry arrays (i, j, p) to the caller, which
 // streams them in window chunks while earlier chunks are being scanned (rmd_scan).
 static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries) {
@@ -446,10 +468,17 @@ static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries)
     }
     if (in->bpp_off) CK(cudaMemcpyAsync(ctx->d_bpp_off.p, in->bpp_off, sizeof(long long) * (in->n_win + 1), cudaMemcpyHostToDevice, st));
     else CK(cudaMemsetAsync(ctx->d_bpp_off.p, 0, sizeof(long long) * (in->n_win + 1), st));
+    const bool compact = in->bpp_q != nullptr;
+    if (compact && !in->bpp_ij) return fail(ctx, RMD_E_INVALID, "rmd_upload: bpp_q needs bpp_ij");
+    if (compact && ctx->max_wlen > 256) return fail(ctx, RMD_E_LIMIT, "compact bpp transport holds windows up to 256 letters (this job: %d)", ctx->max_wlen);
+    if (nb && !compact && (!in->bpp_i || !in->bpp_j || !in->bpp_p)) return fail(ctx, RMD_E_INVALID, "rmd_upload: bpp_i / bpp_j / bpp_p are NULL");
+    if (compact) {
+        RESERVE(ctx->d_bpp_ij, sizeof(uint16_t) * (size_t)std::max<long long>(nb, 1));
+        RESERVE(ctx->d_bpp_q, sizeof(uint32_t) * (size_t)std::max<long long>(nb, 1));
+    }
     if (nb && with_entries) {
-        CK(cudaMemcpyAsync(ctx->d_bpp_i.p, in->bpp_i, sizeof(uint16_t) * nb, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_bpp_j.p, in->bpp_j, sizeof(uint16_t) * nb, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_bpp_p.p, in->bpp_p, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+        int r2 = stage_entries(ctx, in, 0, nb, st);
+        if (r2) return r2;
     }
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -578,16 +607,32 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.raw_cap = ctx->raw_cap;
         O.gate_pass = (uint32_t *)ctx->d_gate_pass.p; O.group_hits = (uint32_t *)ctx->d_group_hits.p;
         CK(cudaEventRecord(ctx->ev[0], st));
-        const int n_chunks = (stream_in && attempt == 0 && ctx->n_bpp > 0) ? (int)std::min<long long>(STREAM_CHUNKS, std::max<long long>(nwin / 2048, 1)) : 1;
+        // Chunks of windows whose lists are copied while earlier chunks are scanned.  Every chunk is one launch of
+        // the persistent kernel and pays its tail, so there should be few; the first must be small so that the scan
+        // starts early.  When the copy is clearly faster than the scan (compact transport) the chunks double in
+        // size; otherwise equal chunks keep the last scan short.
+        const bool streaming = stream_in && attempt == 0 && ctx->n_bpp > 0;
+        long long bounds[STREAM_CHUNKS + 1];
+        int n_chunks = 1;
+        bounds[0] = w_begin; bounds[1] = w_end;
+        if (streaming && nwin >= 4096) {
+            if (stream_in->bpp_q) {
+                n_chunks = 0;
+                long long at = w_begin, size = std::max<long long>(nwin / 32, 2048);
+                while (w_end - at > 2 * size && n_chunks < STREAM_CHUNKS - 1) { at += size; bounds[++n_chunks] = at; size *= 2; }
+                bounds[++n_chunks] = w_end;
+            } else {
+                n_chunks = (int)std::min<long long>(STREAM_CHUNKS, nwin / 2048);
+                for (int k = 0; k <= n_chunks; k++) bounds[k] = w_begin + nwin * k / n_chunks;
+            }
+        }
         for (int ch = 0; ch < n_chunks && nwin > 0; ch++) {
-            const long long c0 = w_begin + nwin * ch / n_chunks, c1 = w_begin + nwin * (ch + 1) / n_chunks;
-            if (stream_in && attempt == 0 && ctx->n_bpp > 0) {        // entries of windows [c0, c1): copy stream, then let the scan wait for them
+            const long long c0 = bounds[ch], c1 = bounds[ch + 1];
+            if (streaming) {                                        // entries of windows [c0, c1): copy stream, then let the scan wait for them
                 const long long e0 = stream_in->bpp_off[c0], e1 = stream_in->bpp_off[c1];
-                if (e1 > e0) {
-                    CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_i.p + e0, stream_in->bpp_i + e0, sizeof(uint16_t) * (e1 - e0), cudaMemcpyHostToDevice, ctx->copy_stream));
-                    CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_j.p + e0, stream_in->bpp_j + e0, sizeof(uint16_t) * (e1 - e0), cudaMemcpyHostToDevice, ctx->copy_stream));
-                    CK(cudaMemcpyAsync((double *)ctx->d_bpp_p.p + e0, stream_in->bpp_p + e0, sizeof(double) * (e1 - e0), cudaMemcpyHostToDevice, ctx->copy_stream));
-                }
+                int r3 = stage_entries(ctx, stream_in, e0, e1, ctx->copy_stream);
+                if (r3) return r3;
+                if (stream_in->bpp_q && e1 > e0) launches++;
                 CK(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
                 CK(cudaStreamWaitEvent(st, ctx->ev[10], 0));
             }

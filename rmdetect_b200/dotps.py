@@ -48,3 +48,11 @@ def read_dot_ps(path):
         last[:-1] = (lo[1:] != lo[:-1]) | (hi[1:] != hi[:-1])
         lo, hi, p = lo[last], hi[last], p[last]
     return seq, lo.astype(np.uint16), hi.astype(np.uint16), p
+
+
+def read_dot_ps_native(path):
+    """Same result as read_dot_ps through the library's parser (rmd_parse_dot_ps), plus the compact
+    transport words q (0 where an entry has no compact form): (sequence, i, j, p, q)."""
+    from ._native import parse_dot_ps
+    with open(path, "rb") as fh:
+        return parse_dot_ps(fh.read())

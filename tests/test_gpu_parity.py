@@ -335,3 +335,30 @@ def test_malformed_bpp_list_is_rejected():
         with pytest.raises(NativeError):
             eng.scan_job(job)
         eng.close()
+
+
+def test_compact_transport_gives_identical_results():
+    """rmd_scan with the 6-byte transport (ij + q words, expanded on the device) == rmd_scan with fp64 lists."""
+    from rmdetect_b200._native import compact_bpp
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    seqs = [("a", synth_sequence(3000, 41), None), ("b", synth_sequence(777, 42), None)]
+    job = eng.build_job(seqs, 150, 75, SynthFold(7), "", 0.001, LN_CUTOFF)
+    # make some values need the one-ulp correction (libm pow vs x * x)
+    for k in range(0, len(job["bpp_p"]), 97):
+        job["bpp_p"][k] = np.nextafter(job["bpp_p"][k], 1.0 if k % 2 else 0.0)
+    want = eng.scan_job(job)
+    ij, q = compact_bpp(job["bpp_i"], job["bpp_j"], job["bpp_p"])
+    assert (q >> 30 != 1).sum() >= len(q) // 97
+    cjob = dict(job, bpp_ij=ij, bpp_q=q)
+    cjob["bpp_i"] = cjob["bpp_j"] = cjob["bpp_p"] = None
+    got = eng.ctx.scan(cjob)
+    assert got["tries"] == want["tries"] and len(want["hits"]) > 10
+    assert got["hits"].tobytes() == want["hits"].tobytes()
+    assert np.array_equal(got["gate_pass"], want["gate_pass"])
+    # the resident path too (rmd_upload + rmd_scan_resident)
+    eng.ctx.upload(cjob)
+    res = eng.ctx.scan_resident(0, job["n_win"])
+    assert res["hits"].tobytes() == want["hits"].tobytes()
+    eng.close()
