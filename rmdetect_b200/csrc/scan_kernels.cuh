@@ -193,27 +193,129 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
     uint32_t *q1 = sm.q1[wid], *q2 = sm.q2[wid];
 
+    uint32_t win_local = 0;                                 // window being generated (records are relative to w_base)
+    int qn1 = 0, qn2 = 0;                                   // warp-uniform queue fills
+    int cur_seq = -1;                                       // sequence whose GC table is in sm.gc
+
+    // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ------
+    // A walk needs nothing of its window but the chains' letters (a register pair) and the sequence's GC table,
+    // so walks in flight carry over into the team's next window: the engine drains only when the sequence
+    // changes and at the end of the kernel.
+    uint32_t e_c = 0, e_t = XNODE_END, e_win = 0;       // placement p0 | p1 << 16; node (XNODE_END: lane idle); its window
+    unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
+    int e_leaf = -1;                                    // best leaf | model << 16
+    double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
+    double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
+#ifdef RMD_STATS
+    unsigned long long dbg_iter = 0, dbg_visits = 0;    // engine statistics
+#endif
+
+    auto engine = [&](const bool drain) {
+        uint32_t bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);     // busy lanes, kept current below
+        for (;;) {
+            if (qn2 > 0 && __popc(~bm) >= (drain ? 1 : REFILL_MIN_IDLE)) {   // hand queued survivors to idle lanes
+                const uint32_t im = ~bm;
+                const int r = __popc(im & lt_mask);
+                if ((im >> lane & 1) && r < qn2) {
+                    const uint32_t c = q2[qn2 - 1 - r];
+                    const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu;
+                    e_c = p0 | (p1 << 16);
+                    e_win = win_local;
+                    e_t = sm.xnode0[c >> 16];
+                    e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
+                          ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
+                    e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
+                    e_stk[0] = make_double2(0.0, 0.0);
+                }
+                qn2 -= min(qn2, __popc(im));
+                bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
+            }
+            if (bm == 0) break;
+            if (!drain && qn2 == 0) break;                   // pause: the walks in flight wait for company
+#ifdef RMD_STATS
+            dbg_iter++; dbg_visits += __popc(bm);
+#endif
+            const bool busy = e_t != XNODE_END;
+            if (busy) {
+                const uint4 a = xn[2 * e_t];                      // sel, cpt, m0 | m1 << 16, skip | next << 16
+                const uint2 b = *reinterpret_cast<const uint2 *>(xn + 2 * e_t + 1);   // leaf | model << 16 | flags << 24 | bdepth << 28, dlo | dspan << 16
+                const int nt = (a.x & XSEL_OWN_GAP) ? 4 : (int)((uint32_t)(e_m >> (a.x & 63u)) & 3u);          // :199-213
+                const uint32_t c0 = (uint32_t)(e_m >> ((a.x >> 8) & 63u)) & 3u, c1 = (uint32_t)(e_m >> ((a.x >> 16) & 63u)) & 3u;
+                double v = xcpt[a.y + nt + c0 * (a.z & 0xffffu) + c1 * (a.z >> 16)];
+                const double g = sm.gc[nt];                       // :223 (slot 4 holds log 0.25)
+                if (v == CUDART_INF) v = g;                       // GC-sentinel row (:217-218)
+                const uint32_t fl = b.x;
+                const int bdepth = fl >> 28;
+                if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
+                // :184-192 as one interval test: chains closer than the configuration allows (empty unless CHECK_DIST)
+                const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);
+                const bool apart = (uint32_t)(d - (int)(short)(b.y & 0xffffu)) >= (b.y >> 16);
+                e_pm = __dadd_rn(e_pm, v);                        // :227-228
+                e_pr = __dadd_rn(e_pr, g);
+                // a node that fails is left through its skip link, and whatever comes next restores the sums
+                const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);       // :248
+                if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {            // :265-275
+                    e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
+                }
+                if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
+                e_t = alive ? (a.w >> 16) : (a.w & 0xffffu);
+            }
+            const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
+            if (dm == 0) continue;
+            const bool hit = busy && e_t == XNODE_END && e_leaf >= 0;
+            const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+            if (hm) {                                     // append records: one atomic per warp iteration
+                unsigned long long base = 0;
+                if (lane == __ffs(hm) - 1) base = atomicAdd(&O.raw_count[0], (unsigned long long)__popc(hm));
+                base = __shfl_sync(FULL_MASK, base, __ffs(hm) - 1);
+                if (hit) {
+                    const unsigned long long slot = base + __popc(hm & lt_mask);
+                    const int model = e_leaf >> 16;
+                    if ((long long)slot < O.raw_cap) {
+                        RawHit h;
+                        h.window = e_win;
+                        h.p0 = (uint16_t)(e_c & 0xffffu); h.p1 = (uint16_t)(e_c >> 16);
+                        h.model = (uint16_t)model; h.leaf = (uint16_t)(e_leaf & 0xffff);
+                        h.rank = 0;
+                        h.pm = e_bpm; h.pr = e_bpr;
+                        O.raw[slot] = h;
+                    }
+                    atomicAdd(&O.group_hits[(long long)e_win * n_models + model], 1u);
+                }
+            }
+            bm &= ~dm;
+        }
+    };
+
     for (int turn = 0;; turn ^= 1) {
         if (tid == 0) sm.next[turn] = atomicAdd(next_window, 1u);
         team_sync(team);
         const long long w = w_begin + sm.next[turn];
-        if (w >= w_end) break;
-        int seq, wlen;
-        long long start;
-        window_geom(J, w, seq, start, wlen);
+        const bool last = w >= w_end;
+        int seq = cur_seq, wlen = 0;
+        long long start = 0;
+        if (!last) window_geom(J, w, seq, start, wlen);
+        const bool new_seq = seq != cur_seq;
+        if (last || new_seq) {                                // walks in flight read the old sequence's GC table: finish them
+            qn2 = 0;
+            engine(true);
+            if (last) break;
+            team_sync(team);
+            cur_seq = seq;
+        }
         if (wlen < min_wlen || wlen > FAST_W) continue;       // long or degenerate windows: scan_generic_kernel
         const long long gbase = J.seq_off[seq] + start;
         const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
         const int nnz = (int)(b1 - b0);
         const double *vals = J.bpp_p + b0;                    // values stay in global memory (L1)
-        const uint32_t win_local = (uint32_t)(w - w_base);
+        win_local = (uint32_t)(w - w_base);
 
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
         for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
         for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
         for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
         if (tid == 0) sm.plain = 1;
-        if (tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
+        if (new_seq && tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
         if (tid < n_models) {
             const CModel &M = c_models[tid];
             sm.gate_pass[tid] = 0;
@@ -265,93 +367,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         if (!sm.plain) continue;                              // a letter other than ACGU: the window is scan_generic_kernel's
 
         auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
-        int qn1 = 0, qn2 = 0;                               // warp-uniform queue fills
-
-        // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ------
-        uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
-        unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
-        int e_leaf = -1;                                    // best leaf | model << 16
-        double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
-        double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
-#ifdef RMD_STATS
-        unsigned long long dbg_iter = 0, dbg_visits = 0;    // engine statistics
-#endif
-
-        auto engine = [&](const bool drain) {
-            uint32_t bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);     // busy lanes, kept current below
-            for (;;) {
-                if (qn2 > 0 && __popc(~bm) >= (drain ? 1 : REFILL_MIN_IDLE)) {   // hand queued survivors to idle lanes
-                    const uint32_t im = ~bm;
-                    const int r = __popc(im & lt_mask);
-                    if ((im >> lane & 1) && r < qn2) {
-                        const uint32_t c = q2[qn2 - 1 - r];
-                        const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu;
-                        e_c = p0 | (p1 << 16);
-                        e_t = sm.xnode0[c >> 16];
-                        e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
-                              ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
-                        e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
-                        e_stk[0] = make_double2(0.0, 0.0);
-                    }
-                    qn2 -= min(qn2, __popc(im));
-                    bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
-                }
-                if (bm == 0) break;
-                if (!drain && qn2 == 0 && bm != FULL_MASK) break;   // pause: nothing left to keep every lane fed
-#ifdef RMD_STATS
-                dbg_iter++; dbg_visits += __popc(bm);
-#endif
-                const bool busy = e_t != XNODE_END;
-                if (busy) {
-                    const uint4 a = xn[2 * e_t];                      // sel, cpt, m0 | m1 << 16, skip | next << 16
-                    const uint2 b = *reinterpret_cast<const uint2 *>(xn + 2 * e_t + 1);   // leaf | model << 16 | flags << 24 | bdepth << 28, dlo | dspan << 16
-                    const int nt = (a.x & XSEL_OWN_GAP) ? 4 : (int)((uint32_t)(e_m >> (a.x & 63u)) & 3u);          // :199-213
-                    const uint32_t c0 = (uint32_t)(e_m >> ((a.x >> 8) & 63u)) & 3u, c1 = (uint32_t)(e_m >> ((a.x >> 16) & 63u)) & 3u;
-                    double v = xcpt[a.y + nt + c0 * (a.z & 0xffffu) + c1 * (a.z >> 16)];
-                    const double g = sm.gc[nt];                       // :223 (slot 4 holds log 0.25)
-                    if (v == CUDART_INF) v = g;                       // GC-sentinel row (:217-218)
-                    const uint32_t fl = b.x;
-                    const int bdepth = fl >> 28;
-                    if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
-                    // :184-192 as one interval test: chains closer than the configuration allows (empty unless CHECK_DIST)
-                    const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);
-                    const bool apart = (uint32_t)(d - (int)(short)(b.y & 0xffffu)) >= (b.y >> 16);
-                    e_pm = __dadd_rn(e_pm, v);                        // :227-228
-                    e_pr = __dadd_rn(e_pr, g);
-                    // a node that fails is left through its skip link, and whatever comes next restores the sums
-                    const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);       // :248
-                    if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {            // :265-275
-                        e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
-                    }
-                    if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
-                    e_t = alive ? (a.w >> 16) : (a.w & 0xffffu);
-                }
-                const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
-                if (dm == 0) continue;
-                const bool hit = busy && e_t == XNODE_END && e_leaf >= 0;
-                const uint32_t hm = __ballot_sync(FULL_MASK, hit);
-                if (hm) {                                     // append records: one atomic per warp iteration
-                    unsigned long long base = 0;
-                    if (lane == __ffs(hm) - 1) base = atomicAdd(&O.raw_count[0], (unsigned long long)__popc(hm));
-                    base = __shfl_sync(FULL_MASK, base, __ffs(hm) - 1);
-                    if (hit) {
-                        const unsigned long long slot = base + __popc(hm & lt_mask);
-                        const int model = e_leaf >> 16;
-                        if ((long long)slot < O.raw_cap) {
-                            RawHit h;
-                            h.window = win_local;
-                            h.p0 = (uint16_t)(e_c & 0xffffu); h.p1 = (uint16_t)(e_c >> 16);
-                            h.model = (uint16_t)model; h.leaf = (uint16_t)(e_leaf & 0xffff);
-                            h.rank = 0;
-                            h.pm = e_bpm; h.pr = e_bpr;
-                            O.raw[slot] = h;
-                        }
-                        atomicAdd(&O.group_hits[(long long)win_local * n_models + model], 1u);
-                    }
-                }
-                bm &= ~dm;
-            }
-        };
+        qn1 = 0; qn2 = 0;
 
         // ---- gate on up to 32 queued candidates ----------------------------------------------------
         auto gate_batch = [&](const int nbatch, const int brute_model) {
@@ -545,7 +561,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             consume(true, 0);
         }
         if (no_score) qn2 = 0;
-        engine(true);
+        engine(false);                                        // until the queue is empty; walks in flight carry over
         team_sync(team);
         if (tid < n_models) {
             O.gate_pass[(long long)win_local * n_models + tid] = sm.gate_pass[tid];
