@@ -75,6 +75,7 @@ struct FastSmem {
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
     uint32_t scan_tmp[SCAN_WARPS];
+    uint32_t chunk_ctr[2];               // next entry chunk of the window, per model group (alternating)
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
     uint8_t letters[FAST_W + 16];
@@ -315,6 +316,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
         for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
         if (tid == 0) sm.plain = 1;
+        if (tid < 2) sm.chunk_ctr[tid] = 0;
         if (new_seq && tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
         if (tid < n_models) {
             const CModel &M = c_models[tid];
@@ -462,6 +464,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 if (g0 > 0) {                                    // bitmaps of the next group of models
                     team_sync(team);
                     for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+                    if (tid == 0) sm.chunk_ctr[(g0 / CB_MODELS + 1) & 1] = 0;
                     team_sync(team);
                 }
                 int nl = 0, ns = 0;                              // warp-uniform fills of wl and s2
@@ -499,10 +502,13 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     consume(false, 0);
                 };
 
-                for (int chunk = wid * 32;;) {
-                    while (nl < 16 && chunk < nnz) {              // the warp's next 32 entries: keep the big ones
+                for (bool more = true;;) {
+                    while (nl < 16 && more) {                     // the team's next 32 entries: keep the big ones
+                        int chunk = 0;                            // taken from a team counter: the four warps stay balanced
+                        if (lane == 0) chunk = (int)atomicAdd(&sm.chunk_ctr[(g0 / CB_MODELS) & 1], 32u);
+                        chunk = __shfl_sync(FULL_MASK, chunk, 0);
+                        if (chunk >= nnz) { more = false; break; }
                         const int e = chunk + lane;
-                        chunk += SCAN_THREADS;
                         uint32_t en = 0;
                         bool isbig = false;
                         if (e < nnz) {
