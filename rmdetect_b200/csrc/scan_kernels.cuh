@@ -60,14 +60,18 @@
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a sorted, unique upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
+struct WarpQueues {                      // one warp's work lists (one base address per warp)
+    uint32_t wl[WL_CAP];                 // big entries waiting for a full row, i | j << 8 | sure-mask << 16
+    uint32_t s2[S2_CAP];                 // (placement, trie node) pairs that passed the parent test
+    uint32_t q1[Q1_CAP];                 // gate candidates  p0 | p1 << 8 | model << 16
+    uint32_t q2[Q2_CAP];                 // gate survivors, same format
+};
+
 struct FastSmem {
     uint32_t Ub[UWORDS];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
     uint16_t Ur[UWORDS];                 // entries before this word in list order
     uint32_t CB[CB_MODELS][UWORDS];      // placements already queued, per model of the current group
-    uint32_t wl[SCAN_WARPS][WL_CAP];     // per warp: big entries waiting for a full row, i | j << 8 | sure-mask << 16
-    uint32_t s2[SCAN_WARPS][S2_CAP];     // per warp: (placement, trie node) pairs that passed the parent test
-    uint32_t q1[SCAN_WARPS][Q1_CAP];     // gate candidates  p0 | p1 << 8 | model << 16
-    uint32_t q2[SCAN_WARPS][Q2_CAP];     // gate survivors, same format
+    WarpQueues wq[SCAN_WARPS];
     TrieNode trie[TRIE_CAP];
     double gc[RMD_N_CODES];
     double sure_min[RMD_MAX_MODELS];     // a generating value >= this passes the gate for certain
@@ -159,7 +163,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
     extern __shared__ uint4 dyn_smem[];
     const int tid = threadIdx.x & (SCAN_THREADS - 1), lane = tid & 31, wid = tid >> 5, team = threadIdx.x / SCAN_THREADS;
-    const uint32_t lt_mask = (1u << lane) - 1;
+    uint32_t lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     const int n_models = J.n_models;
     // ---- CTA-wide tables ------------------------------------------------------------------------
     const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;      // in uint4
@@ -192,7 +197,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (lib/node.py:248)
     const bool no_score = !root_ok || (J.debug & 1);
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
-    uint32_t *q1 = sm.q1[wid], *q2 = sm.q2[wid];
+    WarpQueues &wq = sm.wq[wid];
+    uint32_t *const q1 = wq.q1, *const q2 = wq.q2;
 
     uint32_t win_local = 0;                                 // window being generated (records are relative to w_base)
     int qn1 = 0, qn2 = 0;                                   // warp-uniform queue fills
@@ -457,7 +463,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             // big entries x trie nodes -> placements (see the header of this file).  Every warp works on its
             // own share of the entries: no team-wide barrier in this loop.
             const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
-            uint32_t *wl = sm.wl[wid], *s2 = sm.s2[wid];
+            uint32_t *const wl = wq.wl, *const s2 = wq.s2;
             const int n_prel = c_n_prel;
             for (int g0 = 0; g0 < n_models; g0 += CB_MODELS) {
                 const int g1 = min(g0 + CB_MODELS, n_models);
