@@ -10,8 +10,8 @@
 // Design (a team of 128 threads per window, windows up to 160 letters; persistent CTAs of up to 8 teams
 // with the models' search trees and CPTs in shared memory):
 //   * the window's bpp coordinate list becomes, in shared memory, an upper-triangle bit matrix with
-//     per-word ranks: the value of pair (i, j) is entry rank + popc(bits below) of the window's list,
-//     read through L1;
+//     per-word ranks (the list position of the entry that opens the word): the value of pair (i, j) is
+//     entry rank + popc(bits below) of the window's list, read through L1;
 //   * candidates come from the matrix, not from the 70 000 placements.  The gate mean can reach
 //     min_bpp_mean only if one of the summed values is (within 1e-12) at least min_bpp_mean, and a
 //     pair is summed only if the pairs before it in its configuration are non-zero (the
@@ -56,8 +56,7 @@
 #ifndef REFILL_MIN_IDLE
 #define REFILL_MIN_IDLE 8               // the scoring engine hands out queued work once this many lanes are idle
 #endif
-#define WORDS_PER_THREAD ((UWORDS + SCAN_THREADS - 1) / SCAN_THREADS)   // 7
-#define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a sorted, unique upper triangle
+#define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
 struct WarpQueues {                      // one warp's work lists (one base address per warp)
@@ -78,7 +77,6 @@ struct FastSmem {
     uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
-    uint32_t scan_tmp[SCAN_WARPS];
     uint32_t chunk_ctr[2];               // next entry chunk of the window, per model group (alternating)
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
@@ -133,25 +131,6 @@ __device__ __forceinline__ bool gate_pass(const CModel &M, Lookup lookup, bool a
 // barrier of one team (4 warps); barrier 0 stays with __syncthreads()
 __device__ __forceinline__ void team_sync(const int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(SCAN_THREADS) : "memory");
-}
-
-// exclusive scan of one value per thread over a team; `tmp` holds SCAN_WARPS words
-__device__ __forceinline__ uint32_t team_exclusive_scan(uint32_t v, uint32_t *tmp, uint32_t *total, const int team,
-                                                        const int lane, const int wid) {
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(FULL_MASK, inc, o);
-        if (lane >= o) inc += n;
-    }
-    if (lane == 31) tmp[wid] = inc;
-    team_sync(team);
-    uint32_t before = 0, all = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_WARPS; k++) { const uint32_t t = tmp[k]; all += t; if (k < wid) before += t; }
-    *total = all;
-    team_sync(team);
-    return before + inc - v;
 }
 
 // Persistent kernel: one CTA per SM slot, `blockDim.x / 128` teams of four warps; a team takes the next
@@ -343,33 +322,28 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             sm.l2[tid] = word;
             if (other) atomicAnd(&sm.plain, 0u);
         }
+        // bits and ranks in one pass over the list: the entry that opens a word (its predecessor lies in another
+        // word) is that word's rank; a list that is not strictly increasing in (i, j), or leaves the window's upper
+        // triangle, is refused
         for (int e0 = 0; e0 < nnz; e0 += SCAN_THREADS * 4) { // four entries per thread in flight
-            int ei[4], ej[4];
+            int ei[4], ej[4], pi[4], pj[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int e = e0 + k * SCAN_THREADS + tid;
-                ei[k] = ej[k] = 0;
+                ei[k] = ej[k] = 0; pi[k] = pj[k] = -1;
                 if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
+                if (e < nnz && e > 0) { pi[k] = J.bpp_i[b0 + e - 1]; pj[k] = J.bpp_j[b0 + e - 1]; }
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int e = e0 + k * SCAN_THREADS + tid, i = ei[k], j = ej[k];
-                if (e < nnz && i < j && j < wlen) atomicOr(&sm.Ub[i * FAST_WORDS + (j >> 5)], 1u << (j & 31));
+                if (e >= nnz) continue;
+                const bool inside = i < j && j < wlen, rising = (pi[k] << 16 | pj[k]) < (i << 16 | j) || e == 0;
+                if (!inside || !rising) { atomicOr(&O.raw_count[7], ERR_BAD_LIST); continue; }
+                const int word = i * FAST_WORDS + (j >> 5);
+                atomicOr(&sm.Ub[word], 1u << (j & 31));
+                if (e == 0 || pi[k] * FAST_WORDS + (pj[k] >> 5) != word) sm.Ur[word] = (uint16_t)e;
             }
-        }
-        team_sync(team);
-        {   // rank of the first bit of every word = its position in the (i, j)-sorted list
-            uint32_t mine = 0;
-            const int k0 = tid * WORDS_PER_THREAD;
-#pragma unroll
-            for (int k = 0; k < WORDS_PER_THREAD; k++)
-                if (k0 + k < UWORDS) mine += __popc(sm.Ub[k0 + k]);
-            uint32_t total, run = team_exclusive_scan(mine, sm.scan_tmp, &total, team, lane, wid);
-#pragma unroll
-            for (int k = 0; k < WORDS_PER_THREAD; k++)
-                if (k0 + k < UWORDS) { sm.Ur[k0 + k] = (uint16_t)run; run += __popc(sm.Ub[k0 + k]); }
-            // the ranks are list positions only if every entry set its own bit
-            if (tid == 0 && total != (uint32_t)nnz && sm.plain) atomicOr(&O.raw_count[7], ERR_BAD_LIST);
         }
         team_sync(team);
         if (!sm.plain) continue;                              // a letter other than ACGU: the window is scan_generic_kernel's
