@@ -584,7 +584,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     if (ngroups >= (1LL << 31)) return fail(ctx, RMD_E_LIMIT, "window range too large for one call (%lld windows x %d models)", nwin, J.n_models);
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev[8], st));
-    RESERVE(ctx->d_counters, 64);
+    RESERVE(ctx->d_counters, 128);
     RESERVE(ctx->d_next, sizeof(unsigned int) * (STREAM_CHUNKS + 1));
     RESERVE(ctx->d_gate_pass, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_hits, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
@@ -594,17 +594,17 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     const bool use_fast = ctx->max_chain <= 32 && ctx->motif_ok;
     const int min_fast_wlen = use_fast ? ctx->max_chain + 1 : 0x7fffffff;
     const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen || ctx->any_other;
-    unsigned long long counters[8];
+    unsigned long long counters[16];
     int launches = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         RESERVE(ctx->d_raw, sizeof(RawHit) * (size_t)ctx->raw_cap);
         launches = 0;
-        CK(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+        CK(cudaMemsetAsync(ctx->d_counters.p, 0, 128, st));
         CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(unsigned int) * (STREAM_CHUNKS + 1), st));
         CK(cudaMemsetAsync(ctx->d_gate_pass.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         CK(cudaMemsetAsync(ctx->d_group_hits.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         ScanOut O;
-        O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.raw_cap = ctx->raw_cap;
+        O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.stats = O.raw_count + 8; O.raw_cap = ctx->raw_cap;
         O.gate_pass = (uint32_t *)ctx->d_gate_pass.p; O.group_hits = (uint32_t *)ctx->d_group_hits.p;
         CK(cudaEventRecord(ctx->ev[0], st));
         // Chunks of windows whose lists are copied while earlier chunks are scanned.  Every chunk is one launch of
@@ -657,7 +657,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             }
         }
         CK(cudaEventRecord(ctx->ev[1], st));
-        CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 128, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (counters[7] & ERR_BAD_LIST) return fail(ctx, RMD_E_INVALID, "a window's bpp list is not a sorted, duplicate-free upper triangle (i < j < window length)");
@@ -670,7 +670,10 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     out->n_raw = n_raw;
     out->tries[0] = (int64_t)counters[1];
     out->tries[1] = (int64_t)counters[2];
-    if (getenv("RMD_DEBUG")) fprintf(stderr, "[rmd debug] gate candidates %llu, tree visits %llu in %llu warp iterations\n", counters[3], counters[4], counters[5]);
+#ifdef RMD_STATS
+    fprintf(stderr, "[rmd stats] tree visits %llu in %llu warp iterations; warp cycles: staging %llu, generate+gate+score %llu, "
+            "window-end engine %llu, barrier+tail %llu\n", counters[4], counters[5], counters[8], counters[9], counters[10], counters[11]);
+#endif
     // ---- ordering, scoring, duplicate removal, compaction ---------------------------------------
     RESERVE(ctx->d_final, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));
     RESERVE(ctx->d_compact, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));

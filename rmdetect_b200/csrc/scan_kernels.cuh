@@ -56,6 +56,10 @@
 #ifndef REFILL_MIN_IDLE
 #define REFILL_MIN_IDLE 8               // the scoring engine hands out queued work once this many lanes are idle
 #endif
+#ifndef TAIL_ENTRIES
+#define TAIL_ENTRIES 192                // the last entries of a window are handed out in smaller rows
+#define TAIL_ROW 8
+#endif
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
@@ -290,6 +294,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             cur_seq = seq;
         }
         if (wlen < min_wlen || wlen > FAST_W) continue;       // long or degenerate windows: scan_generic_kernel
+#ifdef RMD_STATS
+        const long long ck0 = clock64();
+#endif
         const long long gbase = J.seq_off[seq] + start;
         const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
         const int nnz = (int)(b1 - b0);
@@ -348,6 +355,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         team_sync(team);
         if (!sm.plain) continue;                              // a letter other than ACGU: the window is scan_generic_kernel's
 
+#ifdef RMD_STATS
+        const long long ck1 = clock64();
+#endif
         auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
         qn1 = 0; qn2 = 0;
 
@@ -483,7 +493,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 };
 
                 for (bool more = true;;) {
-                    while (nl < 16 && more) {                     // the team's next 32 entries: keep the big ones
+                    // rows shrink towards the end of the list so that the four warps finish together
+                    const int want = (int)sm.chunk_ctr[(g0 / CB_MODELS) & 1] + TAIL_ENTRIES < nnz ? 16 : TAIL_ROW;
+                    while (nl < want && more) {                   // the team's next 32 entries: keep the big ones
                         int chunk = 0;                            // taken from a team counter: the four warps stay balanced
                         if (lane == 0) chunk = (int)atomicAdd(&sm.chunk_ctr[(g0 / CB_MODELS) & 1], 32u);
                         chunk = __shfl_sync(FULL_MASK, chunk, 0);
@@ -546,8 +558,14 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             }
             consume(true, 0);
         }
+#ifdef RMD_STATS
+        const long long ck2 = clock64();
+#endif
         if (no_score) qn2 = 0;
         engine(false);                                        // until the queue is empty; walks in flight carry over
+#ifdef RMD_STATS
+        const long long ck3 = clock64();
+#endif
         team_sync(team);
         if (tid < n_models) {
             O.gate_pass[(long long)win_local * n_models + tid] = sm.gate_pass[tid];
@@ -559,7 +577,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             atomicAdd(&O.raw_count[1], tests_all);
         }
 #ifdef RMD_STATS
-        if (lane == 0) { atomicAdd(&O.raw_count[4], dbg_visits); atomicAdd(&O.raw_count[5], dbg_iter); }
+        if (lane == 0) {
+            atomicAdd(&O.raw_count[4], dbg_visits); atomicAdd(&O.raw_count[5], dbg_iter); dbg_visits = 0; dbg_iter = 0;
+            const long long ck4 = clock64();
+            atomicAdd(&O.stats[0], (unsigned long long)(ck1 - ck0)); atomicAdd(&O.stats[1], (unsigned long long)(ck2 - ck1));
+            atomicAdd(&O.stats[2], (unsigned long long)(ck3 - ck2)); atomicAdd(&O.stats[3], (unsigned long long)(ck4 - ck3));
+        }
 #endif
     }
 }
