@@ -29,6 +29,7 @@ struct CModel {
     int ev_nclass, ev_nrows;
     int trie0, n_trie;          // this model's nodes in c_trie
     int xnode0;                 // this model's first node in the concatenated XNode array
+    int cb_slot;                // duplicate bitmap of this model in its group; -1: a trie of at most two nodes needs none
     unsigned short cfg_begin[RMD_MAX_GATE_CFGS + 1];
     rmd_gate_pair pairs[RMD_MAX_GATE_PAIRS];
 };
@@ -50,6 +51,8 @@ static_assert(sizeof(TrieNode) == 8, "TrieNode layout");
 __constant__ TrieNode c_trie[TRIE_CAP];
 __constant__ uint16_t c_prel[32];   // distinct (parent - node) offsets over all tries: (dr & 0xff) | (dc & 0xff) << 8
 __constant__ int c_n_prel;
+__constant__ unsigned char c_groups[RMD_MAX_MODELS + 1];   // candidate generation handles models [c_groups[g], c_groups[g + 1]) together
+__constant__ int c_n_groups;
 __constant__ unsigned long long c_nodemask[32][2];   // trie nodes with pbit == k, as a 128-bit mask
 
 // Search-tree node as the scoring engine reads it (32 bytes, built by rmd_set_models from

@@ -42,6 +42,7 @@ struct rmd_ctx {
     int teams = 8, ctas_per_sm = 1;      // shape of the persistent scan kernel (rmd_set_models)
     size_t scan_smem = 0;
     bool tables_in_smem = true;
+    bool local_stack = false;           // gap trees branch deeper than STK_SLOTS: the engine's save slots live in local memory
     // resident job
     bool have_job = false;
     DevJob job{};
@@ -178,6 +179,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     uint16_t hprel[32] = {0};
     int n_prel = 0;
     bool prel_overflow = false;
+    int stack_slots = 1;
     std::vector<double> hcpt;
     for (int m = 0; m < n_models; m++) {
         const rmd_model_desc &d = models[m];
@@ -270,6 +272,17 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
             if (x0 + (size_t)d.n_tree >= XNODE_END) return fail(ctx, RMD_E_LIMIT, "search trees of the model set exceed %u nodes", XNODE_END - 1);
             if (d.n_leaves > 65535) return fail(ctx, RMD_E_LIMIT, "model %d: too many gap configurations", m);
             c.xnode0 = (int)x0;
+            // save slots of the scoring engine: depths are renumbered from the model's first saving node, so the shipped
+            // models need three slots.  A node that restores at renumbered depth 0 restarts from zero: it is a child of
+            // the implicit root (the flattener gives those depth 1 and no saving node above them).
+            int dmin = RMD_MAX_BRANCH_DEPTH + 1, dmax = -1;
+            for (int t = 0; t < d.n_tree; t++)
+                if (d.tree[t].flags & RMD_F_SAVE) { dmin = std::min<int>(dmin, d.tree[t].bdepth); dmax = std::max<int>(dmax, d.tree[t].bdepth); }
+            if (dmax < 0) dmin = 1;                                // no saving node: only root children may restore
+            for (int t = 0; t < d.n_tree; t++)
+                if ((d.tree[t].flags & RMD_F_RESTORE) && d.tree[t].bdepth <= dmin && d.tree[t].bdepth != 1)
+                    return fail(ctx, RMD_E_INVALID, "model %d: tree node %d restores a sum that was never saved", m, t);
+            stack_slots = std::max(stack_slots, dmax - dmin + 1);
             hcpt.insert(hcpt.end(), d.cpt, d.cpt + (size_t)d.n_cpt_rows * RMD_NSYM);
             for (int t = 0; t < d.n_tree; t++) {
                 const rmd_tree_node &n = d.tree[t];
@@ -294,7 +307,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
                 x.skip = n.skip >= d.n_tree ? (uint16_t)XNODE_END : (uint16_t)(x0 + n.skip);
                 x.next = t + 1 >= d.n_tree ? (uint16_t)XNODE_END : (uint16_t)(x0 + t + 1);
                 x.leaf = n.leaf; x.model = (uint8_t)m;
-                x.fb = (uint8_t)((n.flags & 0xf) | (n.bdepth << 4));
+                x.fb = (uint8_t)((n.flags & 0xf) | (std::max(n.bdepth - dmin, 0) << 4));
                 if (n.flags & RMD_F_CHECK_DIST) {
                     const int dx = d.leaf_dist[2 * n.leaf], dy = d.leaf_dist[2 * n.leaf + 1];
                     if (dx > 32767 || dy > 32767 || dx < 0 || dy < 0) return fail(ctx, RMD_E_LIMIT, "model %d: separation out of range", m);
@@ -308,6 +321,20 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         c.tree = tree; c.leaf_dist = (const int2 *)ld; c.cpt = cpt; c.leaf_offsets = lo;
         c.ev_table = nullptr; c.ev_thr = nullptr; c.ev_nclass = 0; c.ev_nrows = 0;
     }
+    {   // groups of models whose candidates are generated together: a gate trie of more than two nodes needs a
+        // duplicate bitmap, and CB_SLOTS bitmaps are resident at a time
+        unsigned char groups[RMD_MAX_MODELS + 1] = {0};
+        int n_groups = 0, used = 0;
+        for (int m = 0; m < n_models; m++) {
+            CModel &c = ctx->hmodels[m];
+            const bool bitmap = c.n_trie > 2;
+            if (bitmap && used == CB_SLOTS) { groups[++n_groups] = (unsigned char)m; used = 0; }
+            c.cb_slot = bitmap ? used++ : -1;
+        }
+        groups[++n_groups] = (unsigned char)n_models;
+        CK(cudaMemcpyToSymbol(c_groups, groups, sizeof groups));
+        CK(cudaMemcpyToSymbol(c_n_groups, &n_groups, sizeof n_groups));
+    }
     for (const CModel &c : ctx->hmodels) if (c.brute) ctx->any_brute = true;
     if (prel_overflow) ctx->any_brute = true;     // too many distinct pair geometries for the candidate filter: exact path
     CK(cudaMemcpyToSymbol(c_prel, hprel, sizeof hprel));
@@ -318,6 +345,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     CK(cudaMemcpy(ctx->d_xcpt.p, hcpt.data(), sizeof(double) * hcpt.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpyToSymbol(c_trie, htrie, sizeof htrie));
     ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size(); ctx->motif_ok = motif_ok;
+    ctx->local_stack = stack_slots > STK_SLOTS || getenv("RMD_LOCAL_STACK");
     {   // shape of the persistent scan kernel: tables + one FastSmem per team within the SM's shared memory
         int smem_max = 0;
         CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -332,10 +360,11 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         ctx->teams = teams;
         ctx->scan_smem = fixed + teams * sizeof(FastSmem);
         if (ctx->scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", ctx->scan_smem, smem_max);
-        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CK(cudaFuncSetAttribute(scan_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CK(cudaFuncSetAttribute(scan_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        CK(cudaFuncSetAttribute(scan_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     }
     ctx->n_models = n_models;
     CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * n_models));
@@ -643,11 +672,13 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                 const unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * ctx->ctas_per_sm, (c1 - c0 + ctx->teams - 1) / ctx->teams);
                 const unsigned block = (unsigned)ctx->teams * SCAN_THREADS;
                 if (ctx->tables_in_smem) {
-                    if (brute) scan_fast_kernel<true, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
-                    else scan_fast_kernel<false, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    // the exact-gate and global-table variants are the rare ones: they keep the local-memory stack
+                    if (brute) scan_fast_kernel<true, true, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    else if (ctx->local_stack) scan_fast_kernel<false, true, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    else scan_fast_kernel<false, true, false><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
                 } else {
-                    if (brute) scan_fast_kernel<true, false><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
-                    else scan_fast_kernel<false, false><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    if (brute) scan_fast_kernel<true, false, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    else scan_fast_kernel<false, false, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
                 }
                 launches++;
             }

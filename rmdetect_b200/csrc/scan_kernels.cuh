@@ -49,8 +49,8 @@
 #define Q2_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
 #define WL_CAP 48                       // < 16 waiting + 32 from one chunk of entries
 #define S2_CAP 64                       // < 32 waiting + 32 pushed at once
-#ifndef CB_MODELS
-#define CB_MODELS 4                     // models whose duplicate bitmaps are resident together
+#ifndef CB_SLOTS
+#define CB_SLOTS 1                      // duplicate bitmaps resident together (models whose gate trie has more than two nodes)
 #endif
 #define SCAN_MAX_THREADS 1024           // a CTA holds up to 8 teams of SCAN_THREADS
 #ifndef REFILL_MIN_IDLE
@@ -60,6 +60,7 @@
 #define TAIL_ENTRIES 192                // the last entries of a window are handed out in smaller rows
 #define TAIL_ROW 8
 #endif
+#define STK_SLOTS 3                     // save slots of the scoring engine kept in shared memory (per lane)
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
@@ -73,14 +74,17 @@ struct WarpQueues {                      // one warp's work lists (one base addr
 struct FastSmem {
     uint32_t Ub[UWORDS];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
     uint16_t Ur[UWORDS];                 // entries before this word in list order
-    uint32_t CB[CB_MODELS][UWORDS];      // placements already queued, per model of the current group
+    uint32_t CB[CB_SLOTS][UWORDS];       // placements already queued, per bitmap-using model of the current group
     WarpQueues wq[SCAN_WARPS];
+    double2 stk[STK_SLOTS][SCAN_THREADS]; // running sums saved at gap branches, [slot][thread]: conflict-free 16-byte accesses
+    double2 zero2;                       // (0, 0)
     TrieNode trie[TRIE_CAP];
     double gc[RMD_N_CODES];
     double sure_min[RMD_MAX_MODELS];     // a generating value >= this passes the gate for certain
     uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
+    int8_t cb_slot[RMD_MAX_MODELS];
     uint32_t chunk_ctr[2];               // next entry chunk of the window, per model group (alternating)
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
@@ -140,7 +144,8 @@ __device__ __forceinline__ void team_sync(const int team) {
 // Persistent kernel: one CTA per SM slot, `blockDim.x / 128` teams of four warps; a team takes the next
 // window from a global counter, so a slow window delays nobody else.  The models' search trees and CPTs
 // sit in shared memory once per CTA (TABLES: they fit), next to the teams' window state.
-template <bool BRUTE, bool TABLES>
+// LSTK: the model set branches deeper than STK_SLOTS, the engine's save slots go to local memory.
+template <bool BRUTE, bool TABLES, bool LSTK>
 __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
@@ -164,12 +169,14 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         sm.xnode0[tid] = (uint16_t)M.xnode0;
         sm.trie0[tid] = (uint16_t)M.trie0;
         sm.trie_end[tid] = (uint16_t)(M.trie0 + M.n_trie);
+        sm.cb_slot[tid] = (int8_t)M.cb_slot;
         // mean = sum / count >= p / slots: sum >= p (positive terms, monotone rounding), count <= slots,
         // division monotone; the factor covers the rounding of the product and of that division
         const double slots = (double)M.cfg_begin[M.n_cfg];
         sm.sure_min[tid] = J.min_bpp * slots * (1.0 + 1e-12);
     }
     if (tid < 32) sm.prel[tid] = c_prel[tid];
+    if (tid == 0) sm.zero2 = make_double2(0.0, 0.0);
     {
         const int nt = c_models[n_models - 1].trie0 + c_models[n_models - 1].n_trie;
         for (int k = tid; k < nt; k += SCAN_THREADS) sm.trie[k] = c_trie[k];
@@ -195,7 +202,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
     int e_leaf = -1;                                    // best leaf | model << 16
     double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
-    double2 e_stk[RMD_MAX_BRANCH_DEPTH + 1];
+    // sums saved at gap branches: slot k - 1 holds the sums of the branch node at (renumbered) depth k; a node that
+    // restores at depth 0 is a child of the implicit root and restarts from zero
+    double2 e_stk[LSTK ? RMD_MAX_BRANCH_DEPTH + 2 : 1];
+    e_stk[0] = make_double2(0.0, 0.0);
+    double2 *const s_stk = &sm.stk[0][tid];
 #ifdef RMD_STATS
     unsigned long long dbg_iter = 0, dbg_visits = 0;    // engine statistics
 #endif
@@ -215,7 +226,6 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
                           ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
                     e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
-                    e_stk[0] = make_double2(0.0, 0.0);
                 }
                 qn2 -= min(qn2, __popc(im));
                 bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
@@ -236,7 +246,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 if (v == CUDART_INF) v = g;                       // GC-sentinel row (:217-218)
                 const uint32_t fl = b.x;
                 const int bdepth = fl >> 28;
-                if (fl & (RMD_F_RESTORE << 24)) { const double2 s = e_stk[bdepth - 1]; e_pm = s.x; e_pr = s.y; }
+                if (fl & (RMD_F_RESTORE << 24)) {
+                    const double2 s = LSTK ? e_stk[bdepth] : *(bdepth ? s_stk + (bdepth - 1) * SCAN_THREADS : &sm.zero2);
+                    e_pm = s.x; e_pr = s.y;
+                }
                 // :184-192 as one interval test: chains closer than the configuration allows (empty unless CHECK_DIST)
                 const int d = (int)(e_c >> 16) - (int)(e_c & 0xffffu);
                 const bool apart = (uint32_t)(d - (int)(short)(b.y & 0xffffu)) >= (b.y >> 16);
@@ -247,7 +260,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {            // :265-275
                     e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
                 }
-                if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth] = make_double2(e_pm, e_pr);
+                if (alive && (fl & (RMD_F_SAVE << 24))) {
+                    if (LSTK) e_stk[bdepth + 1] = make_double2(e_pm, e_pr);
+                    else s_stk[bdepth * SCAN_THREADS] = make_double2(e_pm, e_pr);
+                }
                 e_t = alive ? (a.w >> 16) : (a.w & 0xffffu);
             }
             const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
@@ -305,7 +321,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
         for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
-        for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+        for (int k = tid; k < CB_SLOTS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
         for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
         if (tid == 0) sm.plain = 1;
         if (tid < 2) sm.chunk_ctr[tid] = 0;
@@ -449,12 +465,13 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
             uint32_t *const wl = wq.wl, *const s2 = wq.s2;
             const int n_prel = c_n_prel;
-            for (int g0 = 0; g0 < n_models; g0 += CB_MODELS) {
-                const int g1 = min(g0 + CB_MODELS, n_models);
-                if (g0 > 0) {                                    // bitmaps of the next group of models
+            const int n_groups = c_n_groups;
+            for (int grp = 0; grp < n_groups; grp++) {
+                const int g0 = c_groups[grp], g1 = c_groups[grp + 1];
+                if (grp > 0) {                                   // bitmaps of the next group of models
                     team_sync(team);
-                    for (int k = tid; k < CB_MODELS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
-                    if (tid == 0) sm.chunk_ctr[(g0 / CB_MODELS + 1) & 1] = 0;
+                    for (int k = tid; k < CB_SLOTS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+                    if (tid == 0) sm.chunk_ctr[(grp + 1) & 1] = 0;
                     team_sync(team);
                 }
                 int nl = 0, ns = 0;                              // warp-uniform fills of wl and s2
@@ -476,9 +493,20 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             a = an.parent;
                         }
                     }
-                    if (ok) {
-                        const uint32_t bit = 1u << (p1 & 31);
-                        ok = !(atomicOr(&sm.CB[tn.model - g0][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);   // first time only
+                    if (ok) {                                    // a placement is queued once
+                        const int slot = sm.cb_slot[tn.model];
+                        if (slot >= 0) {
+                            const uint32_t bit = 1u << (p1 & 31);
+                            ok = !(atomicOr(&sm.CB[slot][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);
+                        } else {
+                            // a trie of two nodes: the first node produces the placement whenever its own pair is big,
+                            // the second one only otherwise (one entry and one node give one placement)
+                            const int t0 = sm.trie0[tn.model];
+                            if ((int)((it >> 16) & 0x7f) != t0) {
+                                const TrieNode fn = sm.trie[t0];
+                                ok = !(lookup(p0 + fn.ro, p1 + fn.co) >= big_min);
+                            }
+                        }
                     }
                     const bool sure = ok && (it >> 31);
                     const uint32_t om = __ballot_sync(FULL_MASK, ok);
@@ -494,10 +522,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 
                 for (bool more = true;;) {
                     // rows shrink towards the end of the list so that the four warps finish together
-                    const int want = (int)sm.chunk_ctr[(g0 / CB_MODELS) & 1] + TAIL_ENTRIES < nnz ? 16 : TAIL_ROW;
+                    const int want = (int)sm.chunk_ctr[grp & 1] + TAIL_ENTRIES < nnz ? 16 : TAIL_ROW;
                     while (nl < want && more) {                   // the team's next 32 entries: keep the big ones
                         int chunk = 0;                            // taken from a team counter: the four warps stay balanced
-                        if (lane == 0) chunk = (int)atomicAdd(&sm.chunk_ctr[(g0 / CB_MODELS) & 1], 32u);
+                        if (lane == 0) chunk = (int)atomicAdd(&sm.chunk_ctr[grp & 1], 32u);
                         chunk = __shfl_sync(FULL_MASK, chunk, 0);
                         if (chunk >= nnz) { more = false; break; }
                         const int e = chunk + lane;

@@ -312,6 +312,27 @@ def test_dense_matrix_window():
     assert res["tries"][1] > 1000
 
 
+def test_model_groups_and_two_node_tries():
+    """Candidate generation by groups: gate tries of more than two nodes (CL, ARICH) take turns with the one resident
+    duplicate bitmap, tries of two nodes (KT, GB, TGA) drop duplicates by the first-big-pair rule; dense matrices
+    make every placement reachable from several entries."""
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+
+    def fold(win):
+        n = len(win)
+        i, j = np.triu_indices(n, 1)
+        rng = np.random.default_rng(n + 1)
+        keep = rng.random(len(i)) < 0.35
+        return i[keep].astype(np.uint16), j[keep].astype(np.uint16), rng.choice([3e-4, 9.99e-4, 1e-3, 2.5e-3, 0.3], size=int(keep.sum()))
+
+    seq = synth_sequence(260, 12)
+    names = ["CL_1.0", "KT_1.0", "ARICH_1.0", "GB_1.0", "CL_1.0", "TGA_1.0"]
+    res = _scan_vs_oracle(names, seq, _TableFold(fold), 0.001)
+    assert res["tries"][1] > 5000
+    _scan_vs_oracle(["TGA_1.0", "GB_1.0", "KT_1.0"], seq, _TableFold(fold), 0.001)
+    _scan_vs_oracle(names, synth_sequence(700, 13), SynthFold(5), 0.001)
+
+
 def test_malformed_bpp_list_is_rejected():
     """The kernel's own checks (the host layer sorts and validates; a C caller may not)."""
     from rmdetect_b200._native import NativeError

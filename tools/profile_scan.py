@@ -13,9 +13,12 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import LN_CUTOFF, LN_UNKNOWN, MIN_BPP, SEED, WIN_LEN, WIN_STEP, load_models   # noqa: E402
+from rmdetect_b200 import _native                                                          # noqa: E402
 from rmdetect_b200.gcx import gc_table                                                    # noqa: E402
 from rmdetect_b200.scanner import ScanEngine                                              # noqa: E402
 
+if os.environ.get("RMD_LIB"):                       # A/B runs of differently built libraries (development only)
+    _native.LIB_PATH = os.path.abspath(os.environ["RMD_LIB"])
 ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=3)
