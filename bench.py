@@ -301,6 +301,72 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_genome(args):
+    """BASELINE.json configs[4]: a synthetic genome of --gnt G letters, both strands, all four models, sharded by
+    piece + halo over the ranks (rmdetect_b200/genome.py).  One step = the whole genome; sequence and stand-in bpp
+    matrices are generated on the device piece by piece, their time is reported apart."""
+    import torch
+    from rmdetect_b200.genome import scan_synthetic_genome
+    from rmdetect_b200.scanner import ScanEngine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    models, evs = load_models()
+    eng = ScanEngine(models, evs, LN_UNKNOWN, device=local)
+    total = int(args.gnt * 1e9)
+    piece = int(args.piece_mb * 1e6) // WIN_STEP
+    scan_synthetic_genome(eng, min(total, piece * WIN_STEP * world), True, SEED, WIN_LEN, WIN_STEP, MIN_BPP, LN_CUTOFF,
+                          rank=rank, world=world, dist=dist, piece_windows=piece, min_score=args.min_score)   # warm-up: one piece per strand
+    sampler = ClockSampler(local)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = scan_synthetic_genome(eng, total, True, SEED, WIN_LEN, WIN_STEP, MIN_BPP, LN_CUTOFF, rank=rank, world=world,
+                              dist=dist, piece_windows=piece, min_score=args.min_score)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall, r["rank_ms_generate"], r["rank_ms_scan_kernel"], r["rank_ms_device"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, ms_gen, ms_kernel, ms_dev = t.tolist()
+    clocks = sampler.summary()
+    if rank == 0:
+        units = 2 * total * len(models)
+        line = {
+            "metric": "nt·models scanned/sec", "unit": "nt·model/s", "n_gpus": world, "steps": 1, "warmup": 1,
+            "value": units / (ms_dev * 1e-3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5: synthetic genome of %.3f G letters, both strands, win 150/75, models CL,TGA,GB,KT, "
+                                   "synthetic bpp (gate on), pieces of %d windows + halo per GPU" % (args.gnt, piece),
+                       "windows": r["windows"], "bpp_entries": r["bpp_entries"], "placements": r["tests_all"],
+                       "gate_passes": r["tests_pairs"], "hits_before_dedupe": r["hits_before_dedupe"], "hits": r["hits"],
+                       "min_score": args.min_score,
+                       "hit_checksum": "%016x" % r["checksum"], "letter_counts_forward": r["counts"],
+                       "timing": "value = letters x models / device time of the scan calls (CUDA events, max over ranks); "
+                                 "wall_s also holds the on-device generation of sequence and bpp matrices (ViennaRNA's "
+                                 "place), which is not part of the metric",
+                       "wall_s": wall, "scan_device_s": ms_dev * 1e-3, "scan_kernel_s": ms_kernel * 1e-3,
+                       "generation_s": ms_gen * 1e-3,
+                       "value_incl_generation": units / wall},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,9 +374,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mb", type=int, default=10, help="chromosome length per GPU in Mb")
+    ap.add_argument("--workload", default="chromosome", choices=["chromosome", "genome"],
+                    help="chromosome: BASELINE configs[2] (the default, the metric's configuration); genome: configs[4]")
+    ap.add_argument("--gnt", type=float, default=3.0, help="genome workload: letters per strand, in units of 1e9")
+    ap.add_argument("--min-score", type=float, default=5.0,
+                    help="genome workload: the command line's score filter (rmdetect.py --min-score), applied on the device")
+    ap.add_argument("--piece-mb", type=float, default=20.0, help="genome workload: letters per resident piece, in Mb")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "genome":
+        run_genome(args)
     else:
         run_ours(args)
 

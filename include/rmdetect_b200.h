@@ -21,10 +21,12 @@
  *                       (__filter_duplicates), lib/node.py:153-277 (eval / get_solution),
  *                       lib/candidates.py:360-366 (score, E-value), :508-514 (absolute positions)
  *   rmd_scan            the same with host buffers: upload + scan + result download
+ *   rmd_set_min_score   rmdetect.py:44 + lib/candidates.py:78-97 (score filter of the CLI, before the download)
  *   rmd_eval            lib/node.py:176-277 called directly (rmcalibrate.py:279-281 style)
  *   rmd_calibrate       rmcalibrate.py:35-62,265-295 (sample scoring into weighted histograms)
  *   rmd_parse_dot_ps    lib/rnatools.py:176-205 (parse_bpprobs: dot.ps text -> base-pair probabilities)
  *   rmd_compact_bpp     no reference counterpart: lossless 6-byte transport form of a bpp entry
+ *   rmd_synth_strand    lib/sequences.py:138-143 (reverse complement), applied to the synthetic stream
  *   rmd_synth_*         no reference counterpart: synthetic genome / stand-in bpp generators,
  *                       bit-identical twins of rmdetect_b200/synth.py, for benchmarks
  */
@@ -156,6 +158,11 @@ int rmd_set_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class);
 /* 1: rmd_scan* also return the hits removed by the duplicate rule (keep = 0, n_hits = n_raw), which the
    reference shows to its per-window callbacks before lib/scanner.py:53 filters them; default 0 */
 int rmd_set_return_dropped(rmd_ctx *ctx, int enable);
+/* enable != 0: hits with score <= min_score are dropped on the device, after the duplicate rule, before the download
+   (keep = 0 when rmd_set_return_dropped is on; tries and the per-window counters are not affected).  This is the
+   command line's own filter (rmdetect.py:44 -> lib/candidates.py:78-97, --min-score, default 5.0) moved in front of
+   the copy; the Scanner drop-in leaves it off because the reference's callbacks see unfiltered candidates. */
+int rmd_set_min_score(rmd_ctx *ctx, int enable, double min_score);
 /* scan windows [w_begin, w_end) of the resident job */
 int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out);
 /* upload + scan of all windows + download, host buffers in, host buffers out */
@@ -184,6 +191,13 @@ int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, uin
                   int32_t win_len, int32_t win_step, double min_bpp_mean, double cutoff,
                   const double *gc_log, const int32_t *gc_class, int64_t *n_win, int64_t *n_bpp,
                   float *ms_generate);
+/* Strand read by the following rmd_synth_job / rmd_synth_counts calls.  total: letters of the whole stream
+   (0: unbounded, forward only).  reverse != 0: position k of the strand is the complement of stream position
+   total - 1 - k, i.e. the reverse-complement sequence lib/sequences.py:103-111,138-143 appends for --both-strands. */
+int rmd_synth_strand(rmd_ctx *ctx, int64_t total, int32_t reverse);
+/* letter counts (A, C, G, U) of strand positions [first, first + n); nothing is stored.  Lets a strand that is
+   scanned in pieces get the GC table of the whole sequence (lib/scanner.py:74-75, lib/gcx.py:4-13). */
+int rmd_synth_counts(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, int64_t *counts);
 /* copy the resident job's sequence codes / one window's bpp list back (tests) */
 int rmd_download_codes(rmd_ctx *ctx, uint8_t *codes, int64_t n);
 int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint16_t *j, double *p, int64_t cap, int64_t *n);

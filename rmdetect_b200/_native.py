@@ -55,8 +55,8 @@ HIT_DTYPE = np.dtype([("window", "<i8"), ("start", "<i8"), ("seq", "<i4"), ("wle
 assert HIT_DTYPE.itemsize == 72
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
-           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_scan_resident", "rmd_scan", "rmd_eval",
-           "rmd_calibrate", "rmd_calibrate_synth", "rmd_synth_job", "rmd_download_codes", "rmd_download_bpp",
+           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_scan_resident", "rmd_scan", "rmd_eval",
+           "rmd_calibrate", "rmd_calibrate_synth", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
 
 _lib = None
@@ -84,6 +84,7 @@ def load_library():
     L.rmd_gc_counts.argtypes = [vp, vp]
     L.rmd_set_gc.argtypes = [vp, vp, vp]
     L.rmd_set_return_dropped.argtypes = [vp, C.c_int]
+    L.rmd_set_min_score.argtypes = [vp, C.c_int, f64]
     L.rmd_scan_resident.argtypes = [vp, i64, i64, C.POINTER(ScanResult)]
     L.rmd_scan.argtypes = [vp, C.POINTER(ScanInput), C.POINTER(ScanResult)]
     L.rmd_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
@@ -93,6 +94,8 @@ def load_library():
                                       C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
     L.rmd_synth_job.argtypes = [vp, i64, i64, C.c_uint64, C.c_uint64, i32, i32, f64, f64, vp, vp,
                                 C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
+    L.rmd_synth_strand.argtypes = [vp, i64, i32]
+    L.rmd_synth_counts.argtypes = [vp, i64, i64, C.c_uint64, vp]
     L.rmd_download_codes.argtypes = [vp, vp, i64]
     L.rmd_download_bpp.argtypes = [vp, i64, vp, vp, vp, i64, C.POINTER(i64)]
     L.rmd_download_job.argtypes = [vp, vp, vp, vp, vp]
@@ -277,6 +280,21 @@ class Context:
                                            cutoff, gc_log.ctypes.data, _ptr(gcc), C.byref(n_win), C.byref(n_bpp),
                                            C.byref(ms)), "rmd_synth_job")
         return n_win.value, n_bpp.value, ms.value
+
+    def set_min_score(self, min_score):
+        """Drop hits with score <= min_score on the device (reference rmdetect.py:44); None switches the filter off."""
+        self._check(self.lib.rmd_set_min_score(self.h, 0 if min_score is None else 1, 0.0 if min_score is None else float(min_score)),
+                    "rmd_set_min_score")
+
+    def synth_strand(self, total, reverse):
+        """Strand of the synthetic stream that synth_job / synth_counts read from now on (reference
+        lib/sequences.py:138-143 for the reverse one)."""
+        self._check(self.lib.rmd_synth_strand(self.h, total, 1 if reverse else 0), "rmd_synth_strand")
+
+    def synth_counts(self, n, first, seq_seed):
+        out = np.zeros(4, dtype=np.int64)
+        self._check(self.lib.rmd_synth_counts(self.h, n, first, seq_seed, out.ctypes.data), "rmd_synth_counts")
+        return out
 
     def download_codes(self, n):
         out = np.zeros(n, dtype=np.uint8)

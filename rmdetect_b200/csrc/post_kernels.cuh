@@ -116,11 +116,15 @@ __global__ void finalize_hits_kernel(const DevJob J, long long w_begin, const Ra
 // coordinates overlap, holds a hit of the same model with the same first position in every chain.
 // (Scores of such twins are equal — same letters, same GC — so the reference always drops the
 // earlier one.)  Hits are ordered, so the twin is found by binary search in the later window's group.
+// With `filter_score` the score filter of the command line (rmdetect.py:44, lib/candidates.py:84: drop
+// score <= min_score) is applied here as well, so that a genome-scale scan downloads only what the CLI keeps;
+// twins have equal scores, so filtering before or after the duplicate rule gives the same list.
 __global__ void dedupe_kernel(const DevJob J, long long w_begin, long long w_end, rmd_hit *hits, long long n,
-                              const uint32_t *group_off, uint32_t *keep) {
+                              const uint32_t *group_off, uint32_t *keep, const int filter_score, const double min_score) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const rmd_hit h = hits[i];
+    if (filter_score && h.score <= min_score) { keep[i] = 0; hits[i].keep = 0; return; }
     const long long a0 = h.start + h.p0, a1 = h.start + h.p1, e1 = h.start + h.wlen;
     const long long w_last = J.win_base[h.seq + 1];
     uint32_t k = 1;

@@ -42,6 +42,8 @@ struct rmd_ctx {
     int teams = 8, ctas_per_sm = 1;      // shape of the persistent scan kernel (rmd_set_models)
     size_t scan_smem = 0;
     bool tables_in_smem = true;
+    long long strand_total = 0;         // rmd_synth_strand: letters of the whole synthetic stream (0: unbounded forward stream)
+    bool strand_reverse = false;
     bool local_stack = false;           // gap trees branch deeper than STK_SLOTS: the engine's save slots live in local memory
     // resident job
     bool have_job = false;
@@ -60,6 +62,8 @@ struct rmd_ctx {
     size_t h_gate_cap = 0;
     long long raw_cap = 0;
     bool return_dropped = false;
+    bool filter_score = false;          // rmd_set_min_score: drop hits with score <= min_score before the download
+    double min_score = 0.0;
     // eval / calibrate scratch
     DBuf d_e0, d_e1, d_e2, d_e3, d_e4, d_e5, d_e6, d_e7;
 };
@@ -558,6 +562,14 @@ extern "C" int rmd_set_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_
     return RMD_OK;
 }
 
+extern "C" int rmd_set_min_score(rmd_ctx *ctx, int enable, double min_score) {
+    if (!ctx) return fail(ctx, RMD_E_INVALID, "rmd_set_min_score: NULL context");
+    if (enable && !(min_score == min_score)) return fail(ctx, RMD_E_INVALID, "rmd_set_min_score: min_score is not a number");
+    ctx->filter_score = enable != 0;
+    ctx->min_score = min_score;
+    return RMD_OK;
+}
+
 extern "C" int rmd_set_return_dropped(rmd_ctx *ctx, int enable) {
     if (!ctx) return fail(ctx, RMD_E_INVALID, "rmd_set_return_dropped: NULL context");
     ctx->return_dropped = enable != 0;
@@ -725,7 +737,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                                                      std::log(2.0), (rmd_hit *)ctx->d_final.p);
         launches++;
         dedupe_kernel<<<blocks, 256, 0, st>>>(J, w_begin, w_end, (rmd_hit *)ctx->d_final.p, n_raw, (const uint32_t *)ctx->d_group_off.p,
-                                              (uint32_t *)ctx->d_keep.p);
+                                              (uint32_t *)ctx->d_keep.p, ctx->filter_score ? 1 : 0, ctx->min_score);
         launches += 2;
         if ((r = device_scan(ctx, (const uint32_t *)ctx->d_keep.p, n_raw, (uint32_t *)ctx->d_keep_off.p, &launches))) return r;
         compact_hits_kernel<<<blocks, 256, 0, st>>>((const rmd_hit *)ctx->d_final.p, n_raw, (const uint32_t *)ctx->d_keep.p,
@@ -908,7 +920,10 @@ extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t se
     J.min_bpp = min_bpp_mean; J.cutoff = cutoff;
     CK(cudaEventRecord(ctx->ev[0], st));
     const long long words = (n + 15) / 16;
-    synth_codes_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(seq_seed, first, n, (uint32_t *)ctx->d_codes2.p);
+    if (ctx->strand_total > 0 && (first < 0 || first + n > ctx->strand_total))
+        return fail(ctx, RMD_E_INVALID, "rmd_synth_job: letters [%lld, %lld) leave the strand of %lld letters", (long long)first, (long long)(first + n), ctx->strand_total);
+    synth_codes_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(seq_seed, first, n, ctx->strand_reverse ? ctx->strand_total : 0,
+                                                                        (uint32_t *)ctx->d_codes2.p);
     synth_bpp_kernel<false><<<(unsigned)J.n_win, SYN_THREADS, 0, st>>>(J, bpp_seed, (uint32_t *)ctx->d_bpp_cnt.p, nullptr, nullptr, nullptr, nullptr);
     // offsets: 32-bit scan per window, widened on the host (lists stay far below 4 G entries per job)
     int launches = 0;
@@ -935,6 +950,31 @@ extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t se
     if (n_win) *n_win = J.n_win;
     if (n_bpp) *n_bpp = nb;
     ctx->have_job = true;
+    return RMD_OK;
+}
+
+extern "C" int rmd_synth_strand(rmd_ctx *ctx, int64_t total, int32_t reverse) {
+    if (!ctx || total < 0 || (reverse && total < 1)) return fail(ctx, RMD_E_INVALID, "rmd_synth_strand: bad arguments");
+    ctx->strand_total = total;
+    ctx->strand_reverse = reverse != 0;
+    return RMD_OK;
+}
+
+extern "C" int rmd_synth_counts(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, int64_t *counts) {
+    if (!ctx || !counts || n < 0 || first < 0) return fail(ctx, RMD_E_INVALID, "rmd_synth_counts: bad arguments");
+    if (ctx->strand_total > 0 && first + n > ctx->strand_total)
+        return fail(ctx, RMD_E_INVALID, "rmd_synth_counts: letters [%lld, %lld) leave the strand of %lld letters", (long long)first, (long long)(first + n), ctx->strand_total);
+    CK(cudaSetDevice(ctx->device));
+    RESERVE(ctx->d_counts, sizeof(unsigned long long) * RMD_N_CODES);
+    CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
+    if (n > 0) {
+        const unsigned grid = (unsigned)std::min<long long>((n + 256 * 64 - 1) / (256 * 64), 148 * 16);
+        synth_counts_kernel<<<grid, 256, 0, ctx->stream>>>(seq_seed, first, n, ctx->strand_reverse ? ctx->strand_total : 0,
+                                                           (unsigned long long *)ctx->d_counts.p);
+    }
+    CK(cudaMemcpyAsync(counts, ctx->d_counts.p, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     return RMD_OK;
 }
 

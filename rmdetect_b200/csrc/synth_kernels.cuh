@@ -9,15 +9,41 @@
 #define SYN_THREADS 128
 #define SYN_GOLDEN 0x9E3779B97F4A7C15ULL
 
-// letter at stream position g: top two bits of mix64(seed + GOLDEN * (g + 1))
-__global__ void synth_codes_kernel(unsigned long long seed, long long first, long long n, uint32_t *codes2) {
+// letter at stream position g: top two bits of mix64(seed + GOLDEN * (g + 1)).  rev_total > 0 reads the reverse
+// strand of a stream of rev_total letters (lib/sequences.py:138-143: reversed, A<->U, C<->G): position k of the
+// strand is 3 - letter(rev_total - 1 - k).
+__device__ __forceinline__ uint32_t synth_letter(unsigned long long seed, long long k, long long rev_total) {
+    const long long g = rev_total > 0 ? rev_total - 1 - k : k;
+    const uint32_t c = (uint32_t)(mix64_dev(seed + SYN_GOLDEN * (unsigned long long)(g + 1)) >> 62);
+    return rev_total > 0 ? 3u - c : c;
+}
+
+__global__ void synth_codes_kernel(unsigned long long seed, long long first, long long n, long long rev_total, uint32_t *codes2) {
     const long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long base = wi * 16;
     if (base >= n) return;
     uint32_t word = 0;
-    for (int k = 0; k < 16 && base + k < n; k++)
-        word |= (uint32_t)(mix64_dev(seed + SYN_GOLDEN * (unsigned long long)(first + base + k + 1)) >> 62) << (2 * k);
+    for (int k = 0; k < 16 && base + k < n; k++) word |= synth_letter(seed, first + base + k, rev_total) << (2 * k);
     codes2[wi] = word;
+}
+
+// letter counts of strand positions [first, first + n): nothing is stored (GC table of a strand that is scanned in pieces)
+__global__ void __launch_bounds__(256) synth_counts_kernel(unsigned long long seed, long long first, long long n, long long rev_total,
+                                                           unsigned long long *counts /* [4] */) {
+    __shared__ unsigned int local[4];
+    if (threadIdx.x < 4) local[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int c4[4] = {0, 0, 0, 0};
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        c4[synth_letter(seed, first + k, rev_total)]++;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        unsigned int v = c4[c];
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(FULL_MASK, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&local[c], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)local[threadIdx.x]);
 }
 
 __device__ __forceinline__ bool can_pair_dev(int a, int b) {

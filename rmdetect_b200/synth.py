@@ -45,16 +45,20 @@ def mix64(x):
     return x
 
 
-def synth_codes(n, seed, start=0):
-    """iid uniform letter codes 0..3 for positions start..start+n-1."""
-    pos = np.arange(start, start + n, dtype=U64)
+def synth_codes(n, seed, start=0, reverse_total=0):
+    """iid uniform letter codes 0..3 for positions start..start+n-1 of the stream, or, with `reverse_total`,
+    of the reverse-complement strand of a stream of that many letters (reference lib/sequences.py:138-143:
+    reversed, A<->U, C<->G; with A,C,G,U = 0..3 the complement of c is 3 - c)."""
+    k = np.arange(start, start + n, dtype=np.int64)
+    pos = (reverse_total - 1 - k if reverse_total else k).astype(U64)
     with np.errstate(over="ignore"):
         h = mix64(U64(seed) + GOLDEN * (pos + U64(1)))
-    return (h >> U64(62)).astype(np.uint8)
+    c = (h >> U64(62)).astype(np.uint8)
+    return (3 - c).astype(np.uint8) if reverse_total else c
 
 
-def synth_sequence(n, seed, start=0) -> str:
-    return np.array([65, 67, 71, 85], dtype=np.uint8)[synth_codes(n, seed, start)].tobytes().decode()
+def synth_sequence(n, seed, start=0, reverse_total=0) -> str:
+    return np.array([65, 67, 71, 85], dtype=np.uint8)[synth_codes(n, seed, start, reverse_total)].tobytes().decode()
 
 
 def _hash_bytes(seq: str) -> np.ndarray:

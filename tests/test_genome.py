@@ -1,0 +1,128 @@
+"""Genome-scale driver (rmdetect_b200/genome.py): piece geometry and strands on the CPU; on the GPU the pieces of
+both strands must add up to the scan of each whole strand, and the reverse strand must equal the oracle's
+scan of the reverse-complement string."""
+import numpy as np
+import pytest
+
+from helpers import LN_CUTOFF, LN_UNKNOWN, MODEL_ORDER, evalues_path, load_evalues, load_model
+from rmdetect_b200.dist import plan_chunks
+from rmdetect_b200.genome import hit_checksum, rank_pieces, strand_gc, strand_windows, window_start
+from rmdetect_b200.scanner import window_starts
+from rmdetect_b200.synth import synth_codes, synth_sequence
+
+
+@pytest.mark.parametrize("n", [1, 149, 150, 151, 225, 226, 1000, 12345])
+def test_window_arithmetic_equals_the_window_list(n):
+    starts = window_starts(n, 150, 75)
+    assert strand_windows(n, 150, 75) == len(starts)
+    assert [window_start(k, len(starts), n, 150, 75) for k in range(len(starts))] == starts.tolist()
+
+
+@pytest.mark.parametrize("n,world,piece", [(12345, 1, 1000), (12345, 3, 20), (5000, 4, 7), (300, 8, 50), (100, 2, 5)])
+def test_pieces_partition_the_windows(n, world, piece):
+    n_win = strand_windows(n, 150, 75)
+    seen = []
+    for r in range(world):
+        plan, _ = plan_chunks(n, 150, 75, world)
+        pieces = rank_pieces(n, 150, 75, r, world, piece)
+        if pieces:                                    # the rank's pieces tile the chunk dist.plan_chunks gives it
+            assert pieces[0][0] == plan[r][0] and pieces[-1][1] == plan[r][1]
+        for a, b, bh, lo, hi in pieces:
+            seen.extend(range(a, b))
+            assert 0 < b - a <= piece and b <= bh <= min(n_win, b + 2)
+            assert lo == window_start(a, n_win, n, 150, 75)
+            # scanned as a sequence of its own, the piece has exactly the windows [a, bh) of the parent
+            own = window_starts(hi - lo, 150, 75) + lo
+            assert own.tolist() == [window_start(k, n_win, n, 150, 75) for k in range(a, bh)]
+    assert seen == list(range(n_win))
+
+
+def test_reverse_strand_twin():
+    n, seed = 1000, 7
+    fwd = synth_codes(n, seed)
+    rev = synth_codes(n, seed, 0, reverse_total=n)
+    assert np.array_equal(rev, 3 - fwd[::-1])
+    assert np.array_equal(synth_codes(100, seed, 250, reverse_total=n), rev[250:350])
+    comp = {"A": "U", "C": "G", "G": "C", "U": "A"}
+    assert synth_sequence(n, seed, 0, reverse_total=n) == "".join(comp[c] for c in reversed(synth_sequence(n, seed)))
+    g = strand_gc(np.bincount(fwd, minlength=4), True)
+    want = np.bincount(rev, minlength=4)
+    assert all(abs(np.exp(g[b]) * n - want[k]) < 1e-9 for k, b in enumerate("ACGU"))
+
+
+def _engine():
+    from rmdetect_b200.scanner import ScanEngine
+    return ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+
+
+@pytest.mark.gpu
+def test_pieces_of_both_strands_add_up_to_the_whole_strands():
+    from rmdetect_b200.gcx import gc_table
+    from rmdetect_b200.genome import scan_synthetic_genome
+    total, seed = 40_000, 20261019
+    eng = _engine()
+    want = dict(tests_all=0, tests_pairs=0, hits=0, checksum=0)
+    counts = np.bincount(synth_codes(total, seed), minlength=4)
+    for strand in (0, 1):                             # each whole strand as one resident job
+        gc = strand_gc(counts, strand == 1)
+        cls = []
+        for ev in eng.evalues:
+            ev.select_gc(gc)
+            cls.append(ev.selected)
+        eng.ctx.synth_strand(total, strand == 1)
+        n_win, _, _ = eng.ctx.synth_job(total, 0, seed, seed, 150, 75, 0.001, LN_CUTOFF, gc_table(gc), cls)
+        if strand == 1:
+            assert np.array_equal(eng.ctx.download_codes(total), synth_codes(total, seed, 0, reverse_total=total))
+        r = eng.ctx.scan_resident(0, n_win)
+        h = r["hits"]
+        want["tests_all"] += r["tries"][0]; want["tests_pairs"] += r["tries"][1]; want["hits"] += len(h)
+        want["checksum"] = (want["checksum"] + hit_checksum(strand, h["start"], h["p0"], h["p1"], h["model"], h["leaf"],
+                                                            h["score"])) & ((1 << 64) - 1)
+    assert want["hits"] > 1000
+    for world, piece in ((1, 1000), (1, 37), (3, 50)):
+        got = dict(tests_all=0, tests_pairs=0, hits=0, checksum=0)
+        for rank in range(world):                     # ranks one after the other on the one GPU: no collective needed
+            r = scan_synthetic_genome(eng, total, True, seed, 150, 75, 0.001, LN_CUTOFF, rank=rank, world=world,
+                                      piece_windows=piece, forward_counts=None if world == 1 else counts)
+            for k in ("tests_all", "tests_pairs", "hits"):
+                got[k] += r[k]
+            got["checksum"] = (got["checksum"] + r["checksum"]) & ((1 << 64) - 1)
+        assert got == want, (world, piece)
+    # the command line's score filter in front of the download: same hits as filtering afterwards
+    kept = []
+    r = scan_synthetic_genome(eng, total, True, seed, 150, 75, 0.001, LN_CUTOFF, piece_windows=90, min_score=5.0,
+                              on_hits=lambda strand, lo, h: kept.append(h.copy()))
+    kept = np.concatenate(kept)
+    every = []
+    scan_synthetic_genome(eng, total, True, seed, 150, 75, 0.001, LN_CUTOFF, piece_windows=90,
+                          on_hits=lambda strand, lo, h: every.append(h.copy()))
+    every = np.concatenate(every)
+    assert r["tests_pairs"] == want["tests_pairs"] and r["hits"] == len(kept) == int((every["score"] > 5.0).sum()) > 0
+    assert np.array_equal(kept, every[every["score"] > 5.0])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_reverse_strand_scan_matches_oracle():
+    from oracle import pyoracle
+    from rmdetect_b200.genome import scan_synthetic_genome
+    total, seed = 3000, 5
+    eng = _engine()
+    got = []
+    r = scan_synthetic_genome(eng, total, True, seed, 150, 75, 0.001, LN_CUTOFF, piece_windows=11,
+                              on_hits=lambda strand, lo, h: got.extend(
+                                  (strand, int(x["model"]), int(x["start"]) + lo, int(x["p0"]), int(x["p1"]), int(x["leaf"]),
+                                   float(x["score"]), float(x["evalue"])) for x in h))
+    eng.close()
+    oms = [pyoracle.OracleModel(load_model(n)) for n in MODEL_ORDER]
+    oes = [pyoracle.OracleEValues(evalues_path(n)) for n in MODEL_ORDER]
+    want, tests = [], [0, 0]
+    for strand in (0, 1):
+        seq = synth_sequence(total, seed, 0, reverse_total=total if strand else 0)
+        starts = pyoracle.windows(len(seq), 150, 75)
+        hits, tries, _ = pyoracle.scan_sequence(oms, oes, 0, seq, 150, 75, [pyoracle.synth_bpp(seq[s:s + 150], seed) for s in starts],
+                                                0.001, LN_UNKNOWN, LN_CUTOFF)
+        tests[0] += tries[0]; tests[1] += tries[1]
+        want.extend((strand, w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"], w["score"], w["evalue"]) for w in hits)
+    assert [r["tests_all"], r["tests_pairs"]] == tests
+    assert got == want
