@@ -77,6 +77,31 @@ static_assert(sizeof(XNode) == 32, "XNode layout");
 #define XNODE_END 0xffffu
 #define LETTER_GAP_SLOT RMD_FAST_WINDOW      // letters[LETTER_GAP_SLOT] holds the gap code (4)
 
+// Prefix screens of the search trees.  The first levels of a top-level subtree read only a handful of letters
+// (nine for the sixteen-leaf CL tree down to level 8), so whether ANY node of the screen's last level stays alive
+// — the same fp64 sums, the same prune test as the walk itself, lib/node.py:227-248 — is a function of those letters
+// and of the sequence's GC table: one bit per letter combination, tabulated per sequence by screen_build_kernel.
+// A gate survivor all of whose screens say "dead" cannot reach a leaf and is not walked at all.  The separation
+// test (lib/node.py:184-192) is ignored while tabulating, which only errs towards "alive".
+#define SCREEN_MAX_LETTERS 9
+#define SCREEN_MAX_RUNS 4
+#define SCREEN_MAX_PER_MODEL 4
+#define SCREEN_CAP (RMD_MAX_MODELS * SCREEN_MAX_PER_MODEL)
+struct ScreenDesc {                 // what the scan kernel needs: index = OR of ((letters >> shift) & mask) << dst over the runs
+    uint32_t word_off;              // first 32-bit word of this screen's table inside the sequence's block
+    uint8_t shift[SCREEN_MAX_RUNS], dst[SCREEN_MAX_RUNS];
+    uint32_t mask[SCREEN_MAX_RUNS];
+    uint32_t pad_;
+};
+static_assert(sizeof(ScreenDesc) == 32, "ScreenDesc layout");
+struct ScreenBuild {                // what screen_build_kernel needs
+    int model, t0, t1, level, npos;
+    uint32_t word_off;
+    uint8_t pos[SCREEN_MAX_LETTERS + 3];   // letter selectors 2 * offset + 32 * chain, ascending: combination digit k is letter pos[k]
+};
+__constant__ ScreenBuild c_screen_build[SCREEN_CAP];
+__constant__ ScreenDesc c_screens[SCREEN_CAP];
+
 // A resident scan job (device pointers).
 struct DevJob {
     int n_seq, n_models, win_len, win_step;
@@ -96,6 +121,10 @@ struct DevJob {
     int n_xnodes, n_xcpt;
     int motif_ok;                // every chain of every model fits the scoring engine's letter word
     int debug;                   // profiling experiments only (RMD_DEBUG): 1 skip scoring, 2 skip the exact gate
+    const uint32_t *screen_bits; // prefix-screen tables of the sequences that have them
+    const long long *screen_off; // [n_seq] first word of a sequence's block in screen_bits, -1: not tabulated (nullptr: no screens)
+    int n_screens;               // screens of all models (c_screens); model m owns [screen0[m], screen0[m + 1])
+    unsigned char screen0[RMD_MAX_MODELS + 1];
 };
 
 // Unordered hit record written by the scan kernels; `rank` is its position inside its
@@ -229,6 +258,69 @@ __device__ __forceinline__ EvalOut eval_placement(const CModel &M, LetterFn lett
         t++;
     }
     return out;
+}
+
+// One screen bit: the walk of tree nodes [t0, t1) (one top-level subtree) restricted to levels <= `level`, on the
+// letters `lt` (index = selector / 2: 16 letters of chain 0, then 16 of chain 1).  True when a node of the last level,
+// or a shallower leaf, passes its prune test.  Same additions in the same order as eval_placement.
+__device__ __forceinline__ bool screen_walk(const CModel &M, const uint8_t *lt, const double *gc, double cutoff,
+                                            int t0, int t1, int level) {
+    double sp[RMD_MAX_BRANCH_DEPTH + 1], sr[RMD_MAX_BRANCH_DEPTH + 1];
+    sp[0] = 0.0; sr[0] = 0.0;
+    double pm = 0.0, pr = 0.0;
+    const uint4 *tree = reinterpret_cast<const uint4 *>(M.tree);
+    int t = t0;
+    while (t < t1) {
+        const uint4 raw = __ldg(tree + t);
+        const int chain = (int)(int8_t)(raw.x & 0xff), oft = (int)(int8_t)((raw.x >> 8) & 0xff);
+        const int flags = (raw.y >> 16) & 0xff, bdepth = raw.y >> 24;
+        const int skip = raw.z >> 16;
+        if (flags & RMD_F_RESTORE) { pm = sp[bdepth - 1]; pr = sr[bdepth - 1]; }
+        const int nt = oft < 0 ? 4 : lt[16 * chain + oft];
+        int row = 0;
+        const int npar = (raw.w >> 16) & 0xff;
+        if (npar > 0) {
+            const int pc0 = (int)(int8_t)((raw.x >> 16) & 0xff), po0 = (int)(int8_t)(raw.y & 0xff);
+            row = po0 < 0 ? 4 : lt[16 * pc0 + po0];
+            if (npar > 1) {
+                const int pc1 = (int)(int8_t)(raw.x >> 24), po1 = (int)(int8_t)((raw.y >> 8) & 0xff);
+                row = row * RMD_NSYM + (po1 < 0 ? 4 : lt[16 * pc1 + po1]);
+            }
+        }
+        double v = __ldg(M.cpt + ((raw.w & 0xffff) + row) * RMD_NSYM + nt);
+        const double g = gc[nt];
+        if (v == CUDART_INF) v = g;
+        pm = __dadd_rn(pm, v);
+        pr = __dadd_rn(pr, g);
+        if (!(pm >= __dadd_rn(pr, cutoff))) { t = skip; continue; }
+        if ((flags & RMD_F_LEAF) || (int)(raw.w >> 24) >= level) return true;
+        if (flags & RMD_F_SAVE) { sp[bdepth] = pm; sr[bdepth] = pr; }
+        t++;
+    }
+    return false;
+}
+
+// Tabulate the screens of one sequence per blockIdx.z: thread = letter combination, 32 combinations per word.
+__global__ void __launch_bounds__(256) screen_build_kernel(const DevJob J, const int *seqs, uint32_t *bits) {
+    const ScreenBuild &S = c_screen_build[blockIdx.y];
+    const long long combo = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_combo = 1LL << (2 * S.npos);
+    if (combo - (threadIdx.x & 31) >= n_combo) return;           // whole warps leave together
+    const int seq = seqs[blockIdx.z];
+    const double *gcs = J.gc_log + (long long)seq * RMD_N_CODES;
+    double gc[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) gc[k] = gcs[k];
+    uint8_t lt[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) lt[k] = 0;
+    bool alive = false;
+    if (combo < n_combo) {
+        for (int k = 0; k < S.npos; k++) lt[S.pos[k] >> 1] = (uint8_t)((combo >> (2 * k)) & 3);
+        alive = screen_walk(c_models[S.model], lt, gc, J.cutoff, S.t0, S.t1, S.level);
+    }
+    const uint32_t word = __ballot_sync(FULL_MASK, alive);
+    if ((threadIdx.x & 31) == 0) bits[J.screen_off[seq] + S.word_off + (combo >> 5)] = word;
 }
 
 // exclusive scan of one value per thread over a block of NT threads (NT multiple of 32, <= 1024);

@@ -42,6 +42,13 @@ struct rmd_ctx {
     int teams = 8, ctas_per_sm = 1;      // shape of the persistent scan kernel (rmd_set_models)
     size_t scan_smem = 0;
     bool tables_in_smem = true;
+    // prefix screens (device_common.cuh: ScreenDesc): per model [screen0[m], screen0[m + 1]), words of one sequence's tables
+    int n_screens = 0;
+    unsigned char screen0[RMD_MAX_MODELS + 1] = {0};
+    long long screen_words = 0;
+    bool screens_dirty = true;          // GC tables, cutoff or models changed since the tables were built
+    bool screens_off = false;           // RMD_NO_SCREEN: every gate survivor is walked (A/B runs)
+    DBuf d_screen_bits, d_screen_off, d_screen_seqs;
     long long strand_total = 0;         // rmd_synth_strand: letters of the whole synthetic stream (0: unbounded forward stream)
     bool strand_reverse = false;
     bool local_stack = false;           // gap trees branch deeper than STK_SLOTS: the engine's save slots live in local memory
@@ -184,6 +191,11 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     int n_prel = 0;
     bool prel_overflow = false;
     int stack_slots = 1;
+    int n_screens = 0;
+    long long screen_words = 0;
+    unsigned char screen0[RMD_MAX_MODELS + 1] = {0};
+    static ScreenBuild hbuild[SCREEN_CAP];
+    static ScreenDesc hdesc[SCREEN_CAP];
     std::vector<double> hcpt;
     for (int m = 0; m < n_models; m++) {
         const rmd_model_desc &d = models[m];
@@ -267,7 +279,68 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         for (int t = 0; t < d.n_tree; t++)
             if (d.tree[t].npar > 2 || d.tree[t].bdepth > RMD_MAX_BRANCH_DEPTH || d.tree[t].leaf >= d.n_leaves)
                 return fail(ctx, RMD_E_LIMIT, "model %d: tree node %d out of range", m, t);
-        if ((r = to_device(ctx, d.tree, (size_t)d.n_tree, &tree, ctx->model_allocs))) return r;
+        // level of every tree node (depth along ORDER), kept in the node's spare byte for the screen tabulation
+        std::vector<rmd_tree_node> ltree(d.tree, d.tree + d.n_tree);
+        std::vector<int> level((size_t)d.n_tree, 0);
+        {
+            std::vector<std::pair<int, int>> open;                  // (end of subtree, level) of the ancestors
+            for (int t = 0; t < d.n_tree; t++) {
+                while (!open.empty() && open.back().first <= t) open.pop_back();
+                level[t] = open.empty() ? 0 : open.back().second + 1;
+                if (d.tree[t].skip <= t || d.tree[t].skip > d.n_tree) return fail(ctx, RMD_E_INVALID, "model %d: tree node %d has a bad skip link", m, t);
+                open.push_back({d.tree[t].skip, level[t]});
+                ltree[t].pad_ = (uint8_t)std::min(level[t], 255);
+            }
+        }
+        if ((r = to_device(ctx, ltree.data(), (size_t)d.n_tree, &tree, ctx->model_allocs))) return r;
+        screen0[m] = (unsigned char)n_screens;
+        if (motif_ok && !getenv("RMD_NO_SCREEN")) {
+            // one screen per top-level subtree, all of the same depth: the deepest level whose letters fit
+            // SCREEN_MAX_LETTERS (small trees: 6, their tables stay in L1) in at most SCREEN_MAX_RUNS runs of
+            // neighbouring offsets
+            const int max_letters = d.n_tree > 100 ? SCREEN_MAX_LETTERS : 6;
+            std::vector<std::pair<int, int>> roots;
+            for (int t = 0; t < d.n_tree; t = d.tree[t].skip) roots.push_back({t, (int)d.tree[t].skip});
+            int deepest = 0;
+            for (int t = 0; t < d.n_tree; t++) deepest = std::max(deepest, level[t]);
+            auto letters_of = [&](int t0, int t1, int L) {
+                std::vector<int> pos;
+                auto add = [&](int chain, int oft) { if (oft >= 0) { const int k = 2 * oft + 32 * (chain ? 1 : 0); if (std::find(pos.begin(), pos.end(), k) == pos.end()) pos.push_back(k); } };
+                for (int t = t0; t < t1; t++) {
+                    if (level[t] > L) continue;
+                    add(d.tree[t].chain, d.tree[t].oft);
+                    for (int k = 0; k < d.tree[t].npar; k++) add(d.tree[t].par_chain[k], d.tree[t].par_oft[k]);
+                }
+                std::sort(pos.begin(), pos.end());
+                return pos;
+            };
+            auto runs_of = [](const std::vector<int> &pos) { int n = 0; for (size_t k = 0; k < pos.size(); k++) if (k == 0 || pos[k] != pos[k - 1] + 2 || pos[k] == 32) n++; return n; };
+            int best = -1;
+            for (int L = 0; L <= std::min(deepest, 254); L++) {
+                bool fits = true;
+                for (auto &rt : roots) { auto pos = letters_of(rt.first, rt.second, L); if ((int)pos.size() > max_letters || runs_of(pos) > SCREEN_MAX_RUNS) fits = false; }
+                if (!fits) break;
+                best = L;
+            }
+            if (best >= 1 && (int)roots.size() <= SCREEN_MAX_PER_MODEL) {
+                for (auto &rt : roots) {
+                    const std::vector<int> pos = letters_of(rt.first, rt.second, best);
+                    ScreenBuild &B = hbuild[n_screens];
+                    ScreenDesc &D = hdesc[n_screens];
+                    memset(&B, 0, sizeof B); memset(&D, 0, sizeof D);
+                    B.model = m; B.t0 = rt.first; B.t1 = rt.second; B.level = best; B.npos = (int)pos.size();
+                    B.word_off = D.word_off = (uint32_t)screen_words;
+                    int run = -1;
+                    for (size_t k = 0; k < pos.size(); k++) {
+                        B.pos[k] = (uint8_t)pos[k];
+                        if (k == 0 || pos[k] != pos[k - 1] + 2 || pos[k] == 32) { run++; D.shift[run] = (uint8_t)pos[k]; D.dst[run] = (uint8_t)(2 * k); D.mask[run] = 0; }
+                        D.mask[run] = (D.mask[run] << 2) | 3u;
+                    }
+                    screen_words += std::max<long long>(1, (1LL << (2 * pos.size())) / 32);
+                    n_screens++;
+                }
+            }
+        }
         if ((r = to_device(ctx, d.leaf_dist, (size_t)d.n_leaves * 2, &ld, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.cpt, (size_t)d.n_cpt_rows * RMD_NSYM, &cpt, ctx->model_allocs))) return r;
         if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, ctx->model_allocs))) return r;
@@ -350,16 +423,22 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     CK(cudaMemcpyToSymbol(c_trie, htrie, sizeof htrie));
     ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size(); ctx->motif_ok = motif_ok;
     ctx->local_stack = stack_slots > STK_SLOTS || getenv("RMD_LOCAL_STACK");
+    for (int m = n_models; m <= RMD_MAX_MODELS; m++) screen0[m] = (unsigned char)n_screens;
+    memcpy(ctx->screen0, screen0, sizeof screen0);
+    ctx->n_screens = n_screens; ctx->screen_words = screen_words; ctx->screens_dirty = true;
+    CK(cudaMemcpyToSymbol(c_screen_build, hbuild, sizeof hbuild));
+    CK(cudaMemcpyToSymbol(c_screens, hdesc, sizeof hdesc));
     {   // shape of the persistent scan kernel: tables + one FastSmem per team within the SM's shared memory
         int smem_max = 0;
         CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        const size_t screens = sizeof(ScreenDesc) * (size_t)n_screens;          // always in shared memory
         const size_t tables = sizeof(XNode) * hx.size() + 16 * ((hcpt.size() + 1) / 2);
         int teams = getenv("RMD_TEAMS") ? atoi(getenv("RMD_TEAMS")) : 8;
         ctx->ctas_per_sm = getenv("RMD_CTAS_PER_SM") ? atoi(getenv("RMD_CTAS_PER_SM")) : 1;
         teams = std::max(1, std::min(teams, SCAN_MAX_THREADS / SCAN_THREADS));
-        ctx->tables_in_smem = tables + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctx->ctas_per_sm;
-        const size_t fixed = ctx->tables_in_smem ? tables : 0;
+        ctx->tables_in_smem = tables + screens + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctx->ctas_per_sm;
+        const size_t fixed = (ctx->tables_in_smem ? tables : 0) + screens;
         while (teams > 1 && fixed + teams * sizeof(FastSmem) > (size_t)smem_max / ctx->ctas_per_sm) teams--;
         ctx->teams = teams;
         ctx->scan_smem = fixed + teams * sizeof(FastSmem);
@@ -444,6 +523,39 @@ static int stage_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class)
     if (gc_class) CK(cudaMemcpyAsync(ctx->d_gc_class.p, gc_class, sizeof(int) * (size_t)J.n_seq * J.n_models, cudaMemcpyHostToDevice, ctx->stream));
     else CK(cudaMemsetAsync(ctx->d_gc_class.p, 0xff, sizeof(int) * (size_t)J.n_seq * J.n_models, ctx->stream));
     J.gc_log = (const double *)ctx->d_gc_log.p; J.gc_class = (const int *)ctx->d_gc_class.p;
+    ctx->screens_dirty = true;
+    return RMD_OK;
+}
+
+// Tabulate the prefix screens of every sequence with enough windows to repay it (the tables depend on the
+// sequence's GC table, the cutoff and the models).  Issued on the scan stream in front of the first scan.
+#define SCREEN_MIN_WINDOWS 64
+static int build_screens(rmd_ctx *ctx) {
+    DevJob &J = ctx->job;
+    ctx->screens_dirty = false;
+    J.screen_bits = nullptr; J.screen_off = nullptr; J.n_screens = ctx->n_screens;
+    memcpy(J.screen0, ctx->screen0, sizeof J.screen0);
+    if (ctx->n_screens == 0 || ctx->screen_words == 0) return RMD_OK;
+    std::vector<long long> off((size_t)J.n_seq, -1);
+    std::vector<int> seqs;
+    for (int s = 0; s < J.n_seq; s++)
+        if (ctx->h_win_base[s + 1] - ctx->h_win_base[s] >= SCREEN_MIN_WINDOWS) { off[s] = (long long)seqs.size() * ctx->screen_words; seqs.push_back(s); }
+    if (seqs.empty()) return RMD_OK;
+    RESERVE(ctx->d_screen_off, sizeof(long long) * (size_t)J.n_seq);
+    RESERVE(ctx->d_screen_seqs, sizeof(int) * seqs.size());
+    RESERVE(ctx->d_screen_bits, sizeof(uint32_t) * (size_t)ctx->screen_words * seqs.size());
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_screen_off.p, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_screen_seqs.p, seqs.data(), sizeof(int) * seqs.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                          // the host vectors go out of scope
+    J.screen_bits = (const uint32_t *)ctx->d_screen_bits.p;
+    J.screen_off = (const long long *)ctx->d_screen_off.p;
+    const unsigned gx = (unsigned)(((1LL << (2 * SCREEN_MAX_LETTERS)) + 255) / 256);
+    for (size_t z0 = 0; z0 < seqs.size(); z0 += 65535) {
+        const unsigned gz = (unsigned)std::min<size_t>(65535, seqs.size() - z0);
+        screen_build_kernel<<<dim3(gx, (unsigned)ctx->n_screens, gz), 256, 0, st>>>(J, (const int *)ctx->d_screen_seqs.p + z0, (uint32_t *)ctx->d_screen_bits.p);
+    }
+    CK(cudaGetLastError());
     return RMD_OK;
 }
 
@@ -625,6 +737,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     if (ngroups >= (1LL << 31)) return fail(ctx, RMD_E_LIMIT, "window range too large for one call (%lld windows x %d models)", nwin, J.n_models);
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev[8], st));
+    if (ctx->screens_dirty) { int rs = build_screens(ctx); if (rs) return rs; }
     RESERVE(ctx->d_counters, 128);
     RESERVE(ctx->d_next, sizeof(unsigned int) * (STREAM_CHUNKS + 1));
     RESERVE(ctx->d_gate_pass, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));

@@ -46,7 +46,8 @@
 #define SCAN_THREADS 128
 #define SCAN_WARPS (SCAN_THREADS / 32)
 #define Q1_CAP 64                       // gate candidates per warp: < 32 waiting + 32 pushed at once
-#define Q2_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
+#define QS_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
+#define Q2_CAP 64                       // walks waiting for the scoring engine: < 32 waiting + 32 from one screen batch
 #define WL_CAP 48                       // < 16 waiting + 32 from one chunk of entries
 #define S2_CAP 64                       // < 32 waiting + 32 pushed at once
 #ifndef CB_SLOTS
@@ -68,7 +69,8 @@ struct WarpQueues {                      // one warp's work lists (one base addr
     uint32_t wl[WL_CAP];                 // big entries waiting for a full row, i | j << 8 | sure-mask << 16
     uint32_t s2[S2_CAP];                 // (placement, trie node) pairs that passed the parent test
     uint32_t q1[Q1_CAP];                 // gate candidates  p0 | p1 << 8 | model << 16
-    uint32_t q2[Q2_CAP];                 // gate survivors, same format
+    uint32_t qs[QS_CAP];                 // gate survivors, same format: on their way through the prefix screens
+    uint32_t q2[Q2_CAP];                 // survivors some screen calls alive: the scoring engine's queue
 };
 
 struct FastSmem {
@@ -85,6 +87,7 @@ struct FastSmem {
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
     int8_t cb_slot[RMD_MAX_MODELS];
+    uint8_t screen0[RMD_MAX_MODELS + 1]; // model m owns screens [screen0[m], screen0[m + 1])
     uint32_t chunk_ctr[2];               // next entry chunk of the window, per model group (alternating)
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
@@ -156,9 +159,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const int n_models = J.n_models;
     // ---- CTA-wide tables ------------------------------------------------------------------------
     const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;      // in uint4
+    const int s_words = 2 * J.n_screens;
     uint4 *sx = dyn_smem;
     double *scpt = reinterpret_cast<double *>(dyn_smem + x_words);
-    FastSmem &sm = reinterpret_cast<FastSmem *>(dyn_smem + x_words + c_words)[team];
+    const ScreenDesc *const scr = reinterpret_cast<const ScreenDesc *>(dyn_smem + x_words + c_words);
+    FastSmem &sm = reinterpret_cast<FastSmem *>(dyn_smem + x_words + c_words + s_words)[team];
+    for (int k = threadIdx.x; k < s_words; k += blockDim.x) dyn_smem[x_words + c_words + k] = reinterpret_cast<const uint4 *>(c_screens)[k];
     if (TABLES) {
         const uint4 *gx = reinterpret_cast<const uint4 *>(J.xnodes);
         for (int k = threadIdx.x; k < x_words; k += blockDim.x) sx[k] = __ldg(gx + k);
@@ -175,6 +181,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const double slots = (double)M.cfg_begin[M.n_cfg];
         sm.sure_min[tid] = J.min_bpp * slots * (1.0 + 1e-12);
     }
+    if (tid <= RMD_MAX_MODELS) sm.screen0[tid] = J.screen0[tid];
     if (tid < 32) sm.prel[tid] = c_prel[tid];
     if (tid == 0) sm.zero2 = make_double2(0.0, 0.0);
     {
@@ -188,11 +195,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const bool no_score = !root_ok || (J.debug & 1);
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
     WarpQueues &wq = sm.wq[wid];
-    uint32_t *const q1 = wq.q1, *const q2 = wq.q2;
+    uint32_t *const q1 = wq.q1, *const q2 = wq.q2, *const qs = wq.qs;
 
     uint32_t win_local = 0;                                 // window being generated (records are relative to w_base)
-    int qn1 = 0, qn2 = 0;                                   // warp-uniform queue fills
+    int qn1 = 0, qn2 = 0, qns = 0;                          // warp-uniform queue fills
     int cur_seq = -1;                                       // sequence whose GC table is in sm.gc
+    const uint32_t *tbl = nullptr;                          // its prefix-screen tables (nullptr: every survivor is walked)
 
     // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ------
     // A walk needs nothing of its window but the chains' letters (a register pair) and the sequence's GC table,
@@ -308,6 +316,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             if (last) break;
             team_sync(team);
             cur_seq = seq;
+            const long long so = J.screen_off ? J.screen_off[seq] : -1;
+            tbl = so >= 0 ? J.screen_bits + so : nullptr;
         }
         if (wlen < min_wlen || wlen > FAST_W) continue;       // long or degenerate windows: scan_generic_kernel
 #ifdef RMD_STATS
@@ -375,7 +385,40 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const long long ck1 = clock64();
 #endif
         auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
-        qn1 = 0; qn2 = 0;
+        qn1 = 0; qn2 = 0; qns = 0;
+
+        // ---- prefix screens on up to 32 gate survivors: one table bit per top-level subtree of the model's search
+        // tree says whether the walk can get past the screen's last level; if none can, there is nothing to score
+        auto screen_batch = [&](const int nbatch) {
+            const bool act = lane < nbatch;
+            const uint32_t c = act ? qs[qns - nbatch + lane] : 0;
+            qns -= nbatch;
+            __syncwarp();
+            bool alive = act;
+            if (tbl != nullptr) {
+                const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu, m = c >> 16;
+                int q = sm.screen0[m];
+                const int qe = sm.screen0[m + 1];
+                if (act && q < qe) {
+                    const unsigned long long em = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
+                                                  ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
+                    alive = false;
+                    for (; q < qe; q++) {
+                        const uint4 d0 = reinterpret_cast<const uint4 *>(scr + q)[0], d1 = reinterpret_cast<const uint4 *>(scr + q)[1];
+                        // d0 = word_off, shift[4], dst[4], mask[0]; d1 = mask[1..3], pad
+                        uint32_t idx = ((uint32_t)(em >> (d0.y & 0xffu)) & d0.w) << (d0.z & 0xffu);
+                        idx |= ((uint32_t)(em >> ((d0.y >> 8) & 0xffu)) & d1.x) << ((d0.z >> 8) & 0xffu);
+                        idx |= ((uint32_t)(em >> ((d0.y >> 16) & 0xffu)) & d1.y) << ((d0.z >> 16) & 0xffu);
+                        idx |= ((uint32_t)(em >> (d0.y >> 24)) & d1.z) << (d0.z >> 24);
+                        if ((__ldg(tbl + d0.x + (idx >> 5)) >> (idx & 31u)) & 1u) alive = true;
+                    }
+                }
+            }
+            const uint32_t am = __ballot_sync(FULL_MASK, alive);
+            if (alive) q2[qn2 + __popc(am & lt_mask)] = c;
+            qn2 += __popc(am);
+            __syncwarp();
+        };
 
         // ---- gate on up to 32 queued candidates ----------------------------------------------------
         auto gate_batch = [&](const int nbatch, const int brute_model) {
@@ -413,15 +456,20 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 }
             }
             const uint32_t pmask = __ballot_sync(FULL_MASK, pass);
-            if (pass) { q2[qn2 + __popc(pmask & lt_mask)] = c; atomicAdd(&sm.gate_pass[m], 1u); }
-            qn2 += __popc(pmask);
+            if (pass) { qs[qns + __popc(pmask & lt_mask)] = c; atomicAdd(&sm.gate_pass[m], 1u); }
+            qns += __popc(pmask);
             __syncwarp();
         };
+        // Every stage below is instantiated once: the kernel's code has to stay inside the instruction cache.
         auto consume = [&](const bool drain, const int brute_model) {
-            if (drain) { while (qn1 > 0) gate_batch(min(qn1, 32), brute_model); }
-            else if (qn1 >= 32) gate_batch(32, brute_model);
-            if (no_score) qn2 = 0;
-            if (qn2 >= 32) engine(false);
+            while (qn1 >= 32 || (drain && qn1 > 0)) gate_batch(min(qn1, 32), brute_model);
+            if (no_score) qns = 0;
+            bool again;
+            do {
+                again = qns >= 32 || (drain && qns > 0);
+                if (again) screen_batch(min(qns, 32));
+                if (qn2 >= 32 || (drain && !again)) engine(false);   // at the end of a window: until the queue is empty; walks in flight carry over
+            } while (again);
         };
 
         if (BRUTE) {
@@ -466,6 +514,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             uint32_t *const wl = wq.wl, *const s2 = wq.s2;
             const int n_prel = c_n_prel;
             const int n_groups = c_n_groups;
+            int nl = 0, ns = 0;                                  // warp-uniform fills of wl and s2
             for (int grp = 0; grp < n_groups; grp++) {
                 const int g0 = c_groups[grp], g1 = c_groups[grp + 1];
                 if (grp > 0) {                                   // bitmaps of the next group of models
@@ -474,52 +523,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     if (tid == 0) sm.chunk_ctr[(grp + 1) & 1] = 0;
                     team_sync(team);
                 }
-                int nl = 0, ns = 0;                              // warp-uniform fills of wl and s2
-
-                // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
-                auto stage2 = [&](const int n) {
-                    const bool act = lane < n;
-                    const uint32_t it = act ? s2[ns - n + lane] : 0;
-                    ns -= n;
-                    __syncwarp();
-                    const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
-                    const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
-                    bool ok = act;
-                    int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
-                    while (__any_sync(FULL_MASK, ok && a >= 0)) {  // every pair before it must be non-zero
-                        if (ok && a >= 0) {
-                            const TrieNode an = sm.trie[a];
-                            ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
-                            a = an.parent;
-                        }
-                    }
-                    if (ok) {                                    // a placement is queued once
-                        const int slot = sm.cb_slot[tn.model];
-                        if (slot >= 0) {
-                            const uint32_t bit = 1u << (p1 & 31);
-                            ok = !(atomicOr(&sm.CB[slot][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);
-                        } else {
-                            // a trie of two nodes: the first node produces the placement whenever its own pair is big,
-                            // the second one only otherwise (one entry and one node give one placement)
-                            const int t0 = sm.trie0[tn.model];
-                            if ((int)((it >> 16) & 0x7f) != t0) {
-                                const TrieNode fn = sm.trie[t0];
-                                ok = !(lookup(p0 + fn.ro, p1 + fn.co) >= big_min);
-                            }
-                        }
-                    }
-                    const bool sure = ok && (it >> 31);
-                    const uint32_t om = __ballot_sync(FULL_MASK, ok);
-                    const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
-                    const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
-                    if (sure) { q2[qn2 + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
-                    else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
-                    qn2 += __popc(smask);
-                    qn1 += __popc(cmask);
-                    __syncwarp();
-                    consume(false, 0);
-                };
-
+                const int tg0 = sm.trie0[g0], tg1 = sm.trie_end[g1 - 1];   // the group's trie nodes are contiguous
+                const bool last_group = grp + 1 == n_groups;
                 for (bool more = true;;) {
                     // rows shrink towards the end of the list so that the four warps finish together
                     const int want = (int)sm.chunk_ctr[grp & 1] + TAIL_ENTRIES < nnz ? 16 : TAIL_ROW;
@@ -546,7 +551,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                         nl += __popc(bm);
                         __syncwarp();
                     }
-                    if (nl == 0) break;
+                    const bool flush = nl == 0;                   // the group's entries are used up: empty s2 (its bitmaps belong to this group)
                     // a row of items: lane = (entry, orientation)
                     const int take = min(nl, 16);
                     const bool valid = (lane >> 1) < take;
@@ -556,41 +561,94 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const int er = (lane & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
                     const int ec = (lane & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
                     uint32_t PM = 0x80000000u;                    // which parent-relative pairs are present (bit 31: no parent)
-                    for (int k = 0; k < n_prel; k++) {
-                        const uint32_t d = sm.prel[k];
-                        if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
-                    }
-                    for (int m = g0; m < g1; m++) {
-                        const uint32_t bd = sm.bounds[m];
-                        const uint32_t n0 = bd & 0xffu;
-                        const int hi = (int)((bd >> 8) & 0xffu);
-                        const bool sym = bd >> 16;
-                        const uint32_t sure_m = ((en >> (16 + m)) & 1u) << 31;
-                        const int t1 = sm.trie_end[m];
-                        for (int t = sm.trie0[m]; t < t1; t++) {  // warp-uniform trie node
+                    if (!flush)
+                        for (int k = 0; k < n_prel; k++) {
+                            const uint32_t d = sm.prel[k];
+                            if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
+                        }
+                    int m = g0 - 1;                               // model of the current trie node
+                    int t = flush ? tg1 : tg0, t1m = t;           // t1m: end of that model's nodes
+                    uint32_t n0 = 0, sure_m = 0;
+                    int hi = 0;
+                    bool sym = false;
+                    for (;;) {
+                        while (t < t1m && ns < 32) {              // warp-uniform trie node
                             const TrieNode tn = sm.trie[t];
                             const int p0 = er - tn.ro, p1 = ec - tn.co;
                             bool ok = valid && ((PM >> tn.pbit) & 1u) && (uint32_t)p0 < n0;
                             if (sym) ok = ok && p1 >= p0 && (p1 <= hi || p1 == p0);
                             else ok = ok && (uint32_t)p1 <= (uint32_t)hi;
                             const uint32_t om = __ballot_sync(FULL_MASK, ok);
-                            if (om == 0) continue;
-                            if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | sure_m;
-                            ns += __popc(om);
-                            __syncwarp();
-                            if (ns >= 32) stage2(32);
+                            if (om) {
+                                if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | sure_m;
+                                ns += __popc(om);
+                                __syncwarp();
+                            }
+                            t++;
                         }
+                        const bool row_done = flush && t >= tg1;  // the closing pass of the group: whatever is left in s2
+                        if (ns < 32 && !row_done) {
+                            if (t >= tg1) break;
+                            m++;                                  // the next model's nodes begin
+                            const uint32_t bd = sm.bounds[m];
+                            n0 = bd & 0xffu; hi = (int)((bd >> 8) & 0xffu); sym = bd >> 16;
+                            sure_m = ((en >> (16 + m)) & 1u) << 31;
+                            t1m = sm.trie_end[m];
+                            continue;
+                        }
+                        {
+                            // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
+                            const int n = min(ns, 32);
+                            const bool act = lane < n;
+                            const uint32_t it = act ? s2[ns - n + lane] : 0;
+                            ns -= n;
+                            __syncwarp();
+                            const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
+                            const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
+                            bool ok = act;
+                            int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
+                            while (__any_sync(FULL_MASK, ok && a >= 0)) {  // every pair before it must be non-zero
+                                if (ok && a >= 0) {
+                                    const TrieNode an = sm.trie[a];
+                                    ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
+                                    a = an.parent;
+                                }
+                            }
+                            if (ok) {                                    // a placement is queued once
+                                const int slot = sm.cb_slot[tn.model];
+                                if (slot >= 0) {
+                                    const uint32_t bit = 1u << (p1 & 31);
+                                    ok = !(atomicOr(&sm.CB[slot][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);
+                                } else {
+                                    // a trie of two nodes: the first node produces the placement whenever its own pair is big,
+                                    // the second one only otherwise (one entry and one node give one placement)
+                                    const int t0 = sm.trie0[tn.model];
+                                    if ((int)((it >> 16) & 0x7f) != t0) {
+                                        const TrieNode fn = sm.trie[t0];
+                                        ok = !(lookup(p0 + fn.ro, p1 + fn.co) >= big_min);
+                                    }
+                                }
+                            }
+                            const bool sure = ok && (it >> 31);
+                            const uint32_t om = __ballot_sync(FULL_MASK, ok);
+                            const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
+                            const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
+                            if (sure) { qs[qns + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
+                            else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
+                            qns += __popc(smask);
+                            qn1 += __popc(cmask);
+                            __syncwarp();
+                            consume(row_done && last_group, 0);
+                        }
+                        if (row_done) break;
                     }
+                    if (flush) break;
                 }
-                if (ns > 0) stage2(ns);                          // the bitmaps belong to this group
             }
-            consume(true, 0);
         }
 #ifdef RMD_STATS
         const long long ck2 = clock64();
 #endif
-        if (no_score) qn2 = 0;
-        engine(false);                                        // until the queue is empty; walks in flight carry over
 #ifdef RMD_STATS
         const long long ck3 = clock64();
 #endif
