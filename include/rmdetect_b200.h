@@ -66,7 +66,7 @@ typedef struct rmd_tree_node {
     uint16_t leaf;                  /* gap configuration id (leaf and distance-check nodes) */
     uint16_t skip;                  /* index of the first node after this subtree */
     uint16_t cpt_row;               /* first CPT row of the model node */
-    uint8_t npar, pad_;
+    uint8_t npar, pad_;             /* pad_: left 0 by the caller (the library keeps the node's tree level there) */
 } rmd_tree_node;
 #define RMD_F_LEAF 1
 #define RMD_F_CHECK_DIST 2
@@ -163,6 +163,11 @@ int rmd_set_return_dropped(rmd_ctx *ctx, int enable);
    command line's own filter (rmdetect.py:44 -> lib/candidates.py:78-97, --min-score, default 5.0) moved in front of
    the copy; the Scanner drop-in leaves it off because the reference's callbacks see unfiltered candidates. */
 int rmd_set_min_score(rmd_ctx *ctx, int enable, double min_score);
+/* Prefix screens (an optimisation with no effect on results): for sequences of at least min_windows windows the
+   library tabulates, per sequence, which letter combinations let the first levels of each search tree survive
+   (lib/node.py:176-248 evaluated for every combination with the sequence's GC table), and skips the tree walk of
+   gate survivors that cannot get past them.  Default 1024; 0: every sequence; < 0: never. */
+int rmd_set_screen_policy(rmd_ctx *ctx, int64_t min_windows);
 /* scan windows [w_begin, w_end) of the resident job */
 int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out);
 /* upload + scan of all windows + download, host buffers in, host buffers out */

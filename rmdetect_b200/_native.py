@@ -55,7 +55,7 @@ HIT_DTYPE = np.dtype([("window", "<i8"), ("start", "<i8"), ("seq", "<i4"), ("wle
 assert HIT_DTYPE.itemsize == 72
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
-           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_scan_resident", "rmd_scan", "rmd_eval",
+           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
            "rmd_calibrate", "rmd_calibrate_synth", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
 
@@ -85,6 +85,7 @@ def load_library():
     L.rmd_set_gc.argtypes = [vp, vp, vp]
     L.rmd_set_return_dropped.argtypes = [vp, C.c_int]
     L.rmd_set_min_score.argtypes = [vp, C.c_int, f64]
+    L.rmd_set_screen_policy.argtypes = [vp, i64]
     L.rmd_scan_resident.argtypes = [vp, i64, i64, C.POINTER(ScanResult)]
     L.rmd_scan.argtypes = [vp, C.POINTER(ScanInput), C.POINTER(ScanResult)]
     L.rmd_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
@@ -280,6 +281,10 @@ class Context:
                                            cutoff, gc_log.ctypes.data, _ptr(gcc), C.byref(n_win), C.byref(n_bpp),
                                            C.byref(ms)), "rmd_synth_job")
         return n_win.value, n_bpp.value, ms.value
+
+    def set_screen_policy(self, min_windows):
+        """Sequences with at least `min_windows` windows get prefix-screen tables (no effect on results); < 0: none."""
+        self._check(self.lib.rmd_set_screen_policy(self.h, int(min_windows)), "rmd_set_screen_policy")
 
     def set_min_score(self, min_score):
         """Drop hits with score <= min_score on the device (reference rmdetect.py:44); None switches the filter off."""

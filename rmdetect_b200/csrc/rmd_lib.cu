@@ -47,7 +47,7 @@ struct rmd_ctx {
     unsigned char screen0[RMD_MAX_MODELS + 1] = {0};
     long long screen_words = 0;
     bool screens_dirty = true;          // GC tables, cutoff or models changed since the tables were built
-    bool screens_off = false;           // RMD_NO_SCREEN: every gate survivor is walked (A/B runs)
+    long long screen_min_windows = 1024; // sequences with fewer windows are scanned without screens; < 0: no screens at all
     DBuf d_screen_bits, d_screen_off, d_screen_seqs;
     long long strand_total = 0;         // rmd_synth_strand: letters of the whole synthetic stream (0: unbounded forward stream)
     bool strand_reverse = false;
@@ -529,7 +529,9 @@ static int stage_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class)
 
 // Tabulate the prefix screens of every sequence with enough windows to repay it (the tables depend on the
 // sequence's GC table, the cutoff and the models).  Issued on the scan stream in front of the first scan.
-#define SCREEN_MIN_WINDOWS 64
+// Tabulating costs about as much as scanning a hundred windows and a block of tables is 66 KB for the shipped
+// models, so short sequences go without (rmd_set_screen_policy), and the blocks of one job stay within a budget.
+#define SCREEN_BUDGET_BYTES (256LL << 20)
 static int build_screens(rmd_ctx *ctx) {
     DevJob &J = ctx->job;
     ctx->screens_dirty = false;
@@ -538,8 +540,12 @@ static int build_screens(rmd_ctx *ctx) {
     if (ctx->n_screens == 0 || ctx->screen_words == 0) return RMD_OK;
     std::vector<long long> off((size_t)J.n_seq, -1);
     std::vector<int> seqs;
-    for (int s = 0; s < J.n_seq; s++)
-        if (ctx->h_win_base[s + 1] - ctx->h_win_base[s] >= SCREEN_MIN_WINDOWS) { off[s] = (long long)seqs.size() * ctx->screen_words; seqs.push_back(s); }
+    const long long max_blocks = std::max<long long>(1, SCREEN_BUDGET_BYTES / (4 * ctx->screen_words));
+    for (int s = 0; s < J.n_seq && (long long)seqs.size() < max_blocks; s++)
+        if (ctx->screen_min_windows >= 0 && ctx->h_win_base[s + 1] - ctx->h_win_base[s] >= ctx->screen_min_windows) {
+            off[s] = (long long)seqs.size() * ctx->screen_words;
+            seqs.push_back(s);
+        }
     if (seqs.empty()) return RMD_OK;
     RESERVE(ctx->d_screen_off, sizeof(long long) * (size_t)J.n_seq);
     RESERVE(ctx->d_screen_seqs, sizeof(int) * seqs.size());
@@ -679,6 +685,13 @@ extern "C" int rmd_set_min_score(rmd_ctx *ctx, int enable, double min_score) {
     if (enable && !(min_score == min_score)) return fail(ctx, RMD_E_INVALID, "rmd_set_min_score: min_score is not a number");
     ctx->filter_score = enable != 0;
     ctx->min_score = min_score;
+    return RMD_OK;
+}
+
+extern "C" int rmd_set_screen_policy(rmd_ctx *ctx, int64_t min_windows) {
+    if (!ctx) return fail(ctx, RMD_E_INVALID, "rmd_set_screen_policy: NULL context");
+    ctx->screen_min_windows = min_windows;
+    ctx->screens_dirty = true;
     return RMD_OK;
 }
 

@@ -52,7 +52,9 @@ def test_reverse_strand_twin():
 
 def _engine():
     from rmdetect_b200.scanner import ScanEngine
-    return ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    eng.ctx.set_screen_policy(0)                      # prefix-screen tables even for these short strands
+    return eng
 
 
 @pytest.mark.gpu

@@ -145,6 +145,7 @@ def test_synthetic_job_generated_on_device_matches_oracle():
     from rmdetect_b200.synth import synth_bpp_coo, synth_codes, synth_sequence
     n, seed = 30000, 20261019
     eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    eng.ctx.set_screen_policy(0)                      # with prefix-screen tables (the default spares sequences this short)
     codes = synth_codes(n, seed)
     seq = synth_sequence(n, seed)
     gc = gc_of_codes(codes, "")
@@ -331,6 +332,43 @@ def test_model_groups_and_two_node_tries():
     assert res["tries"][1] > 5000
     _scan_vs_oracle(["TGA_1.0", "GB_1.0", "KT_1.0"], seq, _TableFold(fold), 0.001)
     _scan_vs_oracle(names, synth_sequence(700, 13), SynthFold(5), 0.001)
+
+
+@pytest.mark.parametrize("letters", ["ACGU", "AAACGUU", "GGGCCCAU", "ACGUN"])
+def test_prefix_screens_do_not_change_results(letters):
+    """Screens on (tables for every sequence), default (none for short sequences) and off: same hits as the oracle,
+    for balanced and skewed GC tables and with a letter outside ACGU in the sequence."""
+    from oracle import pyoracle
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold
+    rng = random.Random(len(letters))
+    seqs = [("a", "".join(rng.choice(letters) for _ in range(2400)), None),
+            ("b", "".join(rng.choice("ACGU") for _ in range(700)), None)]
+    names = MODEL_ORDER + ["ARICH_1.0"]
+    fold = SynthFold(21)
+    eng = ScanEngine([load_model(n) for n in names], [load_evalues(n) for n in names], LN_UNKNOWN)
+    job = eng.build_job(seqs, 150, 75, fold, "", 0.001, LN_CUTOFF)
+    runs = []
+    for policy in (0, 1024, -1):
+        eng.ctx.set_screen_policy(policy)
+        r = eng.scan_job(job)
+        runs.append((r["tries"], r["hits"].tobytes(), r["gate_pass"].tobytes(), r["raw_count"].tobytes()))
+    eng.close()
+    assert runs[0] == runs[1] == runs[2]
+    oms = [pyoracle.OracleModel(load_model(n)) for n in names]
+    oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+    hits = np.frombuffer(runs[0][1], dtype=r["hits"].dtype)
+    at, tests = 0, [0, 0]
+    for si, (_, seq, _) in enumerate(seqs):
+        starts = pyoracle.windows(len(seq), 150, 75)
+        want, tries, _ = pyoracle.scan_sequence(oms, oes, si, seq, 150, 75, [fold.coo(seq[s:s + 150]) for s in starts],
+                                                0.001, LN_UNKNOWN, LN_CUTOFF)
+        tests[0] += tries[0]; tests[1] += tries[1]
+        for w in want:
+            g = hits[at]; at += 1
+            assert (g["seq"], g["model"], g["start"], g["p0"], g["p1"], g["leaf"]) == (si, w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"])
+            assert (g["prob_model"], g["prob_rand"], g["score"], g["evalue"]) == (w["prob_model"], w["prob_rand"], w["score"], w["evalue"])
+    assert at == len(hits) and runs[0][0] == tests
 
 
 def test_malformed_bpp_list_is_rejected():
