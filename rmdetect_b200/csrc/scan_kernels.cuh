@@ -73,7 +73,7 @@ struct WarpQueues {                      // one warp's work lists (one base addr
     uint32_t q2[Q2_CAP];                 // survivors some screen calls alive: the scoring engine's queue
 };
 
-struct FastSmem {
+struct __align__(16) FastSmem {
     uint32_t Ub[UWORDS];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
     uint16_t Ur[UWORDS];                 // entries before this word in list order
     uint32_t CB[CB_SLOTS][UWORDS];       // placements already queued, per bitmap-using model of the current group
@@ -157,14 +157,19 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     uint32_t lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     const int n_models = J.n_models;
-    // ---- CTA-wide tables ------------------------------------------------------------------------
-    const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;      // in uint4
+    // ---- shared memory: the teams' state first (a team's base is team * sizeof(FastSmem)), then the CTA-wide tables.
+    // The team's byte offset goes through an opaque move: left to itself the compiler re-derives it from
+    // %tid and the kernel parameters in front of most shared-memory accesses (13 % of all instructions).
+    uint32_t sm_off = (uint32_t)team * (uint32_t)sizeof(FastSmem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sm_off));
+    FastSmem &sm = *reinterpret_cast<FastSmem *>(reinterpret_cast<char *>(dyn_smem) + sm_off);
+    const int t_words = (int)(blockDim.x / SCAN_THREADS) * (int)(sizeof(FastSmem) / 16);               // in uint4
+    const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;
     const int s_words = 2 * J.n_screens;
-    uint4 *sx = dyn_smem;
-    double *scpt = reinterpret_cast<double *>(dyn_smem + x_words);
-    const ScreenDesc *const scr = reinterpret_cast<const ScreenDesc *>(dyn_smem + x_words + c_words);
-    FastSmem &sm = reinterpret_cast<FastSmem *>(dyn_smem + x_words + c_words + s_words)[team];
-    for (int k = threadIdx.x; k < s_words; k += blockDim.x) dyn_smem[x_words + c_words + k] = reinterpret_cast<const uint4 *>(c_screens)[k];
+    uint4 *sx = dyn_smem + t_words;
+    double *scpt = reinterpret_cast<double *>(dyn_smem + t_words + x_words);
+    const ScreenDesc *const scr = reinterpret_cast<const ScreenDesc *>(dyn_smem + t_words + x_words + c_words);
+    for (int k = threadIdx.x; k < s_words; k += blockDim.x) dyn_smem[t_words + x_words + c_words + k] = reinterpret_cast<const uint4 *>(c_screens)[k];
     if (TABLES) {
         const uint4 *gx = reinterpret_cast<const uint4 *>(J.xnodes);
         for (int k = threadIdx.x; k < x_words; k += blockDim.x) sx[k] = __ldg(gx + k);
