@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
     extern __shared__ uint4 dyn_smem[];
-    const int tid = threadIdx.x & (SCAN_THREADS - 1), lane = tid & 31, wid = tid >> 5, team = threadIdx.x / SCAN_THREADS;
+    int tid = threadIdx.x & (SCAN_THREADS - 1), lane = tid & 31;
+    asm volatile("mov.u32 %0, %0;" : "+r"(tid));          // opaque like the team offset below: no re-derivation from %tid
+    asm volatile("mov.u32 %0, %0;" : "+r"(lane));
+    const int wid = tid >> 5, team = threadIdx.x / SCAN_THREADS;
     uint32_t lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     const int n_models = J.n_models;
@@ -199,7 +202,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (lib/node.py:248)
     const bool no_score = !root_ok || (J.debug & 1);
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
-    WarpQueues &wq = sm.wq[wid];
+    uint32_t wq_off = sm_off + (uint32_t)offsetof(FastSmem, wq) + (uint32_t)wid * (uint32_t)sizeof(WarpQueues);
+    asm volatile("mov.u32 %0, %0;" : "+r"(wq_off));
+    WarpQueues &wq = *reinterpret_cast<WarpQueues *>(reinterpret_cast<char *>(dyn_smem) + wq_off);
     uint32_t *const q1 = wq.q1, *const q2 = wq.q2, *const qs = wq.qs;
 
     uint32_t win_local = 0;                                 // window being generated (records are relative to w_base)
@@ -333,6 +338,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const int nnz = (int)(b1 - b0);
         const double *vals = J.bpp_p + b0;                    // values stay in global memory (L1)
         win_local = (uint32_t)(w - w_base);
+        // the values are first needed after the staging pass: have their lines on the way (one 128-byte line per thread)
+        for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
 
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
         for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
