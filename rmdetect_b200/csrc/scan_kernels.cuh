@@ -79,6 +79,8 @@ struct __align__(16) FastSmem {
     uint32_t CB[CB_SLOTS][UWORDS];       // placements already queued, per bitmap-using model of the current group
     WarpQueues wq[SCAN_WARPS];
     double2 stk[STK_SLOTS][SCAN_THREADS]; // running sums saved at gap branches, [slot][thread]: conflict-free 16-byte accesses
+    double best_pr[SCAN_THREADS];         // per lane: random-model sum of the walk's best leaf so far (read when the walk ends)
+    uint32_t walk_win[SCAN_THREADS];      // per lane: window of the walk in flight
     double2 zero2;                       // (0, 0)
     TrieNode trie[TRIE_CAP];
     double gc[RMD_N_CODES];
@@ -216,10 +218,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     // A walk needs nothing of its window but the chains' letters (a register pair) and the sequence's GC table,
     // so walks in flight carry over into the team's next window: the engine drains only when the sequence
     // changes and at the end of the kernel.
-    uint32_t e_c = 0, e_t = XNODE_END, e_win = 0;       // placement p0 | p1 << 16; node (XNODE_END: lane idle); its window
+    uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
     unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
     int e_leaf = -1;                                    // best leaf | model << 16
-    double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0, e_bpr = -500.0;
+    double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0;      // the best leaf's other sum and the walk's window wait in shared memory
+    double *const s_bpr = &sm.best_pr[tid];
+    uint32_t *const s_win = &sm.walk_win[tid];
     // sums saved at gap branches: slot k - 1 holds the sums of the branch node at (renumbered) depth k; a node that
     // restores at depth 0 is a child of the implicit root and restarts from zero
     double2 e_stk[LSTK ? RMD_MAX_BRANCH_DEPTH + 2 : 1];
@@ -239,11 +243,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const uint32_t c = q2[qn2 - 1 - r];
                     const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu;
                     e_c = p0 | (p1 << 16);
-                    e_win = win_local;
+                    *s_win = win_local;
                     e_t = sm.xnode0[c >> 16];
                     e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
                           ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
-                    e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_bpr = -500.0;    // lib/node.py:250-251
+                    e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0;    // lib/node.py:250-251 (a hit always stores its own best_pr)
                 }
                 qn2 -= min(qn2, __popc(im));
                 bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
@@ -276,7 +280,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 // a node that fails is left through its skip link, and whatever comes next restores the sums
                 const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);       // :248
                 if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {            // :265-275
-                    e_bpm = e_pm; e_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
+                    e_bpm = e_pm; *s_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
                 }
                 if (alive && (fl & (RMD_F_SAVE << 24))) {
                     if (LSTK) e_stk[bdepth + 1] = make_double2(e_pm, e_pr);
@@ -297,14 +301,14 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const int model = e_leaf >> 16;
                     if ((long long)slot < O.raw_cap) {
                         RawHit h;
-                        h.window = e_win;
+                        h.window = *s_win;
                         h.p0 = (uint16_t)(e_c & 0xffffu); h.p1 = (uint16_t)(e_c >> 16);
                         h.model = (uint16_t)model; h.leaf = (uint16_t)(e_leaf & 0xffff);
                         h.rank = 0;
-                        h.pm = e_bpm; h.pr = e_bpr;
+                        h.pm = e_bpm; h.pr = *s_bpr;
                         O.raw[slot] = h;
                     }
-                    atomicAdd(&O.group_hits[(long long)e_win * n_models + model], 1u);
+                    atomicAdd(&O.group_hits[(long long)*s_win * n_models + model], 1u);
                 }
             }
             bm &= ~dm;
