@@ -81,6 +81,10 @@ struct __align__(16) FastSmem {
     double2 stk[STK_SLOTS][SCAN_THREADS]; // running sums saved at gap branches, [slot][thread]: conflict-free 16-byte accesses
     double best_pr[SCAN_THREADS];         // per lane: random-model sum of the walk's best leaf so far (read when the walk ends)
     uint32_t walk_win[SCAN_THREADS];      // per lane: window of the walk in flight
+    int walk_leaf[SCAN_THREADS];          // per lane: best leaf | model << 16 of the walk in flight, -1: none yet
+    const uint32_t *tbl;                  // prefix-screen tables of the current sequence (nullptr: every survivor is walked)
+    int cur_seq;                          // sequence whose GC table is in gc
+    uint32_t win_local;                   // window being generated (records are relative to w_base)
     double2 zero2;                       // (0, 0)
     TrieNode trie[TRIE_CAP];
     double gc[RMD_N_CODES];
@@ -209,10 +213,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     WarpQueues &wq = *reinterpret_cast<WarpQueues *>(reinterpret_cast<char *>(dyn_smem) + wq_off);
     uint32_t *const q1 = wq.q1, *const q2 = wq.q2, *const qs = wq.qs;
 
-    uint32_t win_local = 0;                                 // window being generated (records are relative to w_base)
     int qn1 = 0, qn2 = 0, qns = 0;                          // warp-uniform queue fills
-    int cur_seq = -1;                                       // sequence whose GC table is in sm.gc
-    const uint32_t *tbl = nullptr;                          // its prefix-screen tables (nullptr: every survivor is walked)
+    if (tid == 0) { sm.cur_seq = -1; sm.tbl = nullptr; }    // team-wide state lives in shared memory: registers are the scarce resource
 
     // ---- scoring engine: one tree node per busy lane per iteration (lib/node.py:176-277) ------
     // A walk needs nothing of its window but the chains' letters (a register pair) and the sequence's GC table,
@@ -220,7 +222,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     // changes and at the end of the kernel.
     uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
     unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
-    int e_leaf = -1;                                    // best leaf | model << 16
+    int *const s_leaf = &sm.walk_leaf[tid];
     double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0;      // the best leaf's other sum and the walk's window wait in shared memory
     double *const s_bpr = &sm.best_pr[tid];
     uint32_t *const s_win = &sm.walk_win[tid];
@@ -243,11 +245,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const uint32_t c = q2[qn2 - 1 - r];
                     const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu;
                     e_c = p0 | (p1 << 16);
-                    *s_win = win_local;
+                    *s_win = sm.win_local;
                     e_t = sm.xnode0[c >> 16];
                     e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
                           ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
-                    e_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0;    // lib/node.py:250-251 (a hit always stores its own best_pr)
+                    *s_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0;    // lib/node.py:250-251 (a hit always stores its own best_pr)
                 }
                 qn2 -= min(qn2, __popc(im));
                 bm = __ballot_sync(FULL_MASK, e_t != XNODE_END);
@@ -280,7 +282,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 // a node that fails is left through its skip link, and whatever comes next restores the sums
                 const bool alive = apart && e_pm >= __dadd_rn(e_pr, J.cutoff);       // :248
                 if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) {            // :265-275
-                    e_bpm = e_pm; *s_bpr = e_pr; e_leaf = (int)(fl & 0xffffffu);
+                    e_bpm = e_pm; *s_bpr = e_pr; *s_leaf = (int)(fl & 0xffffffu);
                 }
                 if (alive && (fl & (RMD_F_SAVE << 24))) {
                     if (LSTK) e_stk[bdepth + 1] = make_double2(e_pm, e_pr);
@@ -290,6 +292,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             }
             const uint32_t dm = __ballot_sync(FULL_MASK, busy && e_t == XNODE_END);
             if (dm == 0) continue;
+            const int e_leaf = *s_leaf;
             const bool hit = busy && e_t == XNODE_END && e_leaf >= 0;
             const uint32_t hm = __ballot_sync(FULL_MASK, hit);
             if (hm) {                                     // append records: one atomic per warp iteration
@@ -320,6 +323,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         team_sync(team);
         const long long w = w_begin + sm.next[turn];
         const bool last = w >= w_end;
+        const int cur_seq = sm.cur_seq;
         int seq = cur_seq, wlen = 0;
         long long start = 0;
         if (!last) window_geom(J, w, seq, start, wlen);
@@ -329,9 +333,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             engine(true);
             if (last) break;
             team_sync(team);
-            cur_seq = seq;
-            const long long so = J.screen_off ? J.screen_off[seq] : -1;
-            tbl = so >= 0 ? J.screen_bits + so : nullptr;
+            if (tid == 0) {
+                sm.cur_seq = seq;
+                const long long so = J.screen_off ? J.screen_off[seq] : -1;
+                sm.tbl = so >= 0 ? J.screen_bits + so : nullptr;
+            }
         }
         if (wlen < min_wlen || wlen > FAST_W) continue;       // long or degenerate windows: scan_generic_kernel
 #ifdef RMD_STATS
@@ -341,7 +347,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const long long b0 = J.bpp_off[w], b1 = J.bpp_off[w + 1];
         const int nnz = (int)(b1 - b0);
         const double *vals = J.bpp_p + b0;                    // values stay in global memory (L1)
-        win_local = (uint32_t)(w - w_base);
+        const uint32_t win_local = (uint32_t)(w - w_base);
+        if (tid == 0) sm.win_local = win_local;
         // the values are first needed after the staging pass: have their lines on the way (one 128-byte line per thread)
         for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
 
@@ -411,6 +418,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             qns -= nbatch;
             __syncwarp();
             bool alive = act;
+            const uint32_t *const tbl = sm.tbl;
             if (tbl != nullptr) {
                 const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu, m = c >> 16;
                 int q = sm.screen0[m];
