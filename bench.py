@@ -35,7 +35,9 @@ MODEL_FILES = ["cl_1", "tga_1", "gb_1", "kt_1"]         # the order os.listdir g
 DATA = os.path.join(ROOT, "tests", "golden", "ref_data", "models")
 LN_UNKNOWN, LN_CUTOFF, MIN_BPP = math.log(1e-4), math.log(0.1), 0.001
 CAL_SAMPLES = 1 << 20                                    # calibration samples per model and GPU
-NCU_DRAM_BYTES_PER_LAUNCH = 1047918000 + 27238912        # one scan_fast_kernel launch over the 10 Mb workload (ncu --set full)
+NCU_DRAM_BYTES_PER_LAUNCH = 1035679000 + 25620736        # one scan_fast_kernel launch over the 10 Mb workload (ncu --set full)
+NCU_WARP_INSTRUCTIONS_PER_LAUNCH = 13233314213           # smsp__inst_executed.sum of the same launch
+ISSUE_SLOTS_PER_SM_CYCLE = 4                             # one warp instruction per scheduler and cycle
 
 
 def load_models():
@@ -257,6 +259,13 @@ def run_ours(args):
         algo = n_win * (40 + 8 + 16) + n_bpp * 12 + n_raw * 32 + n_win * len(models) * 8
         ms_kernel = scan_ms / args.steps
         achieved = algo / (ms_kernel * 1e-3) / 1e9
+        issue = None
+        if args.mb == 10 and clocks.get("sm_max_mhz"):
+            sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+            issue_peak = sm_count * ISSUE_SLOTS_PER_SM_CYCLE * clocks["sm_max_mhz"] * 1e6
+            issue_rate = NCU_WARP_INSTRUCTIONS_PER_LAUNCH / (ms_kernel * 1e-3)
+            issue = {"achieved": issue_rate, "peak": issue_peak, "unit": "warp instructions/s", "frac": issue_rate / issue_peak,
+                     "source": "profiles/r01c_scan_fast_ncu_full.csv (smsp__inst_executed.sum)"}
         cores = os.cpu_count() or 1
         cpu_val, cpu_dt, cpu_win, _ = cpu_baseline(models, cores, 15.0)
         line = {
@@ -286,11 +295,14 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if args.mb == 10 else None,
-                         "traffic_source": "profiles/r01b_scan_fast_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, "
+                         "traffic_source": "profiles/r01c_scan_fast_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, "
                                            "ncu --set full of this command)",
                          "kernel": "scan_fast_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo),
-                         "note": "table-lookup / fp64-compare work: issue-bound, not HBM-bound (see DESIGN.md)"},
+                         "note": "table-lookup / fp64-compare work: issue-bound, not HBM-bound (see DESIGN.md); `issue` is the "
+                                 "binding resource: warp instructions of the launch (ncu) / its live duration against "
+                                 "148 SMs x 4 schedulers x the SM clock",
+                         "issue": issue},
             "cpu_baseline": {"value": cpu_val, "unit": "nt·model/s", "cores": cores, "kind": "port",
                              "sample": "first %d windows (%d nt) of the same chromosome, oracle/rmd_oracle.c with "
                                        "OpenMP on all cores, %.1f s" % (cpu_win, cpu_win * WIN_STEP, cpu_dt)},

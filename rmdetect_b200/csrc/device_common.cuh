@@ -53,7 +53,6 @@ __constant__ uint16_t c_prel[32];   // distinct (parent - node) offsets over all
 __constant__ int c_n_prel;
 __constant__ unsigned char c_groups[RMD_MAX_MODELS + 1];   // candidate generation handles models [c_groups[g], c_groups[g + 1]) together
 __constant__ int c_n_groups;
-__constant__ unsigned long long c_nodemask[32][2];   // trie nodes with pbit == k, as a 128-bit mask
 
 // Search-tree node as the scoring engine reads it (32 bytes, built by rmd_set_models from
 // rmd_tree_node; all models concatenated, indices absolute).  The engine keeps the 16 letters from
