@@ -23,6 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--models", default="")
+ap.add_argument("--e2e", action="store_true", help="also time rmd_scan from host buffers (compact transport) and print its parts")
 args = ap.parse_args()
 models, evs = load_models()
 if args.models:
@@ -37,4 +38,16 @@ for k in range(args.steps):
 print("models %s windows %d bpp %d gen %.2f ms | scan %.3f ms post %.3f ms total %.3f ms | tries %s raw %d hits %d | %.1f M nt·model/s"
       % ([m.name for m in models], n_win, n_bpp, ms_gen, r["ms_scan"], r["ms_post"], r["ms_total"], r["tries"], r["n_raw"],
          len(r["hits"]), n * len(models) / r["ms_scan"] / 1e3))
+if args.e2e:
+    off, bi, bj, bp = eng.ctx.download_job(n_win, n_bpp, pinned=True)
+    codes = _native.pinned_array(n, np.uint8)
+    codes[:] = eng.ctx.download_codes(n)
+    ij, q = _native.compact_bpp(bi, bj, bp, pinned=True)
+    job = dict(seq_off=np.array([0, n], dtype=np.int64), codes=codes, gc_log=gc.reshape(1, -1),
+               gc_class=np.full((1, len(models)), -1, dtype=np.int32), win_len=WIN_LEN, win_step=WIN_STEP, n_win=n_win,
+               bpp_off=off, bpp_i=None, bpp_j=None, bpp_p=None, bpp_ij=ij, bpp_q=q, min_bpp_mean=MIN_BPP, cutoff=LN_CUTOFF)
+    for k in range(args.steps):
+        e = eng.ctx.scan(job, copy=False)
+    print("e2e: total %.3f ms | h2d(first stage) %.3f  scan %.3f  post %.3f  d2h %.3f | launches %d"
+          % (e["ms_total"], e["ms_h2d"], e["ms_scan"], e["ms_post"], e["ms_d2h"], e["n_launches"]))
 eng.close()
