@@ -98,7 +98,7 @@ class ScanEngine:
     # one job = a list of (key, seq, col_index) scanned with one window geometry
     def build_job(self, seqs, win_len, win_step, provider, constraint, min_bpp_mean, cutoff, gc=None):
         codes_l, off, gc_tabs, gc_cls, gcs, others_l = [], [0], [], [], [], []
-        starts_l, bi, bj, bp, boff = [], [], [], [], [0]
+        starts_l, bi, bj, bp, boff, wins = [], [], [], [], [0], []
         for key, seq, _cols in seqs:
             codes, others = encode_sequence(seq)
             g = gc if gc is not None else gc_of_codes(codes, others)
@@ -118,18 +118,28 @@ class ScanEngine:
             starts = window_starts(len(seq), win_len, win_step)
             starts_l.append(starts)
             whole = win_len == 0 or win_step == 0
-            for s in starts.tolist():
-                win = seq if whole else seq[s:s + win_len]
-                if len(win) == 0:
-                    i = j = np.zeros(0, np.uint16)
-                    p = np.zeros(0, np.float64)
-                elif hasattr(provider, "coo"):
-                    i, j, p = provider.coo(win)
-                    i, j, p = to_coo(_Coo(i, j, p), len(win))
-                else:
-                    i, j, p = to_coo(provider.bpprobs(win, constraint), len(win))
-                bi.append(i); bj.append(j); bp.append(p)
-                boff.append(boff[-1] + len(i))
+            wins.extend(seq if whole else seq[s:s + win_len] for s in starts.tolist())
+        # one bpp matrix per window (reference lib/scanner.py:130); a provider with `coo_many` gets all windows of
+        # the job at once and may fold them concurrently (fold.RNAfold)
+        if hasattr(provider, "coo_many"):
+            todo = [w for w in wins if len(w)]
+            lists = iter(provider.coo_many(todo, constraint) if todo else [])
+        else:
+            lists = None
+        for win in wins:
+            if len(win) == 0:
+                i = j = np.zeros(0, np.uint16)
+                p = np.zeros(0, np.float64)
+            elif lists is not None:
+                i, j, p = next(lists)
+                i, j, p = to_coo(_Coo(i, j, p), len(win))
+            elif hasattr(provider, "coo"):
+                i, j, p = provider.coo(win)
+                i, j, p = to_coo(_Coo(i, j, p), len(win))
+            else:
+                i, j, p = to_coo(provider.bpprobs(win, constraint), len(win))
+            bi.append(i); bj.append(j); bp.append(p)
+            boff.append(boff[-1] + len(i))
         cat = lambda parts, dt: (np.ascontiguousarray(np.concatenate(parts), dtype=dt) if parts
                                  else np.zeros(0, dtype=dt))
         job = dict(
