@@ -128,3 +128,92 @@ def test_reverse_strand_scan_matches_oracle():
         want.extend((strand, w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"], w["score"], w["evalue"]) for w in hits)
     assert [r["tests_all"], r["tests_pairs"]] == tests
     assert got == want
+
+
+# ---- world size 2 on CPU (gloo): the driver's two exchanges — letter counts before, counters and checksum after ----
+class _OracleCtx:
+    """Plays the device context for the genome driver: pieces come from the numpy twin of the synthetic stream and
+    are scanned by the CPU oracle (a test of the host-side plumbing; the CUDA path is covered above)."""
+
+    def __init__(self, names):
+        from oracle import pyoracle
+        self.py = pyoracle
+        self.oms = [pyoracle.OracleModel(load_model(n)) for n in names]
+        self.oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+        self.total, self.reverse, self.min_score = 0, False, None
+
+    def synth_strand(self, total, reverse):
+        self.total, self.reverse = total, reverse
+
+    def synth_counts(self, n, first, seed):
+        return np.bincount(synth_codes(n, seed, first, reverse_total=self.total if self.reverse else 0), minlength=4).astype(np.int64)
+
+    def set_min_score(self, v):
+        self.min_score = v
+
+    def synth_job(self, n, first, seed, bpp_seed, win_len, win_step, min_bpp, cutoff, tab, cls):
+        self.seq = synth_sequence(n, seed, first, reverse_total=self.total if self.reverse else 0)
+        self.args = (bpp_seed, win_len, win_step, min_bpp, cutoff, {b: float(tab[k]) for k, b in enumerate("ACGU")}, cls)
+        return len(self.py.windows(n, win_len, win_step)), 0, 0.0
+
+    def scan_resident(self, w0, w1, copy=False):
+        from rmdetect_b200._native import HIT_DTYPE
+        bpp_seed, W, step, min_bpp, cutoff, gc, cls = self.args
+        for oe, c in zip(self.oes, cls):
+            oe.selected = c
+        starts = self.py.windows(len(self.seq), W, step)
+        bpp = [self.py.synth_bpp(self.seq[s:s + W], bpp_seed) for s in starts]
+        hits, tries, tpw = self.py.scan_sequence(self.oms, self.oes, 0, self.seq, W, step, bpp, min_bpp, LN_UNKNOWN, cutoff, gc=gc)
+        if self.min_score is not None:
+            hits = [h for h in hits if h["score"] > self.min_score]
+        out = np.zeros(len(hits), dtype=HIT_DTYPE)
+        for k, h in enumerate(hits):
+            out[k] = (int(np.searchsorted(starts, h["coords"][0])), h["coords"][0], 0, h["coords"][1] - h["coords"][0], h["p"][0], h["p"][1],
+                      h["model"], h["cfg"], 1, h["prob_model"], h["prob_rand"], h["score"], h["evalue"])
+        gate = np.zeros((len(starts), len(self.oms)), dtype=np.uint32)
+        gate[:, 0] = tpw[:len(starts), 1]
+        return dict(hits=out, gate_pass=gate, raw_count=np.zeros_like(gate), ms_scan=0.0, ms_total=0.0)
+
+
+class _OracleEngine:
+    def __init__(self, names):
+        self.models = [load_model(n) for n in names]
+        self.evalues = [load_evalues(n) for n in names]
+        self.ctx = _OracleCtx(names)
+
+
+def _genome_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from rmdetect_b200.genome import scan_synthetic_genome
+    names = ["TGA_1.0", "KT_1.0"]
+    r = scan_synthetic_genome(_OracleEngine(names), 1300, True, 17, 150, 75, 0.001, LN_CUTOFF, rank=rank, world=world, dist=dist,
+                              piece_windows=3, min_score=2.0)
+    if rank == 0:
+        one = scan_synthetic_genome(_OracleEngine(names), 1300, True, 17, 150, 75, 0.001, LN_CUTOFF, piece_windows=1000, min_score=2.0)
+        keys = ("tests_all", "tests_pairs", "hits", "windows", "checksum", "counts")
+        q.put(({k: r[k] for k in keys}, {k: one[k] for k in keys}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_share_a_genome_over_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_genome_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    two, one = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert two == one and one["hits"] > 0 and one["windows"] == 2 * 17 and sum(one["counts"]) == 1300
