@@ -106,6 +106,40 @@ class RNAfold:
             uniq[k] = v
         return [uniq[s] for s in seqs]
 
+    # ---- energies (lib/rnatools.py:41-52 `fold`, :160-174 `parse_fold`, :231-248 `parse_line`) ------------------
+    def fold(self, seq, constraint="", ensemble=False):
+        """(structure, mfe) or, with `ensemble`, (structure, free energy of the ensemble): `RNAfold --noPS [-p] [-C]`.
+        The constraint is applied (`-C`) when the driver was built with use_constraint=True; otherwise it is inert, as
+        in the reference as shipped (which sends the line but never `-C`: lib/rnatools.py:134, defect D7)."""
+        import re
+        if not self.exe:
+            raise FoldError("RNAfold not found: install ViennaRNA or set RMDETECT_RNAFOLD to the binary")
+        cmd = [self.exe, "--noPS"] + (["-p"] if ensemble else [])
+        lines = [seq]
+        if constraint and self.use_constraint:          # without -C RNAfold would read the line as another sequence
+            lines.append(constraint)
+            cmd.append("-C")
+        with tempfile.TemporaryDirectory(prefix="rmfold_", dir=self.tmp_root) as work:
+            try:
+                proc = subprocess.run(cmd, input=("\n".join(lines) + "\n").encode(), cwd=work,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            except OSError as exc:
+                raise FoldError("cannot run %s: %s" % (self.exe, exc)) from exc
+        if proc.returncode != 0:
+            raise FoldError("%s failed (%d): %s" % (self.exe, proc.returncode, proc.stderr.decode(errors="replace")[-300:]))
+        out = proc.stdout.decode(errors="replace").split("\n")
+        self.folds += 1
+        m = re.match(r"([\.\(\)]+)( \(\s*(\-?\d+\.\d+)\))?", out[1].strip()) if len(out) > 1 else None
+        if m is None:
+            raise FoldError("cannot read RNAfold's structure line: %r" % (out[1] if len(out) > 1 else ""))
+        struct, energy = m.group(1), float(m.group(3)) if m.group(3) is not None else 0.0
+        if ensemble:
+            m = re.match(r"([\.\(\)\{\}\,\|]+)( \[\s*(\-?\d+\.\d+)\])", out[2].strip()) if len(out) > 2 else None
+            if m is None:
+                raise FoldError("cannot read RNAfold's ensemble line: %r" % (out[2] if len(out) > 2 else ""))
+            energy = float(m.group(3))
+        return struct, energy
+
     # ---- the reference's call shape (lib/rnatools.py:31-39) -------------------------------------------------
     def bpprobs(self, seq, constraint=""):
         i, j, p = self.coo(seq, constraint)
