@@ -140,6 +140,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
     torch.cuda.set_device(local)
+    from rmdetect_b200.dist import bind_host_thread_to_gpu
+    affinity = bind_host_thread_to_gpu(local) if world > 1 and not os.environ.get("RMD_NO_BIND") else None   # host buffers next to the rank's GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -266,6 +268,8 @@ def run_ours(args):
             issue_rate = NCU_WARP_INSTRUCTIONS_PER_LAUNCH / (ms_kernel * 1e-3)
             issue = {"achieved": issue_rate, "peak": issue_peak, "unit": "warp instructions/s", "frac": issue_rate / issue_peak,
                      "source": "profiles/r01c_scan_fast_ncu_full.csv (smsp__inst_executed.sum)"}
+        if affinity is not None:
+            os.sched_setaffinity(0, affinity)                    # the CPU baseline may use every core again
         cores = os.cpu_count() or 1
         cpu_val, cpu_dt, cpu_win, _ = cpu_baseline(models, cores, 15.0)
         line = {

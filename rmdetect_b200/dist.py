@@ -89,3 +89,23 @@ def gather_hits(hits, tries, dist=None, dst=0):
         return np.empty(0, dtype=HIT_DTYPE), total
     parts = [np.frombuffer(g.cpu().numpy().tobytes(), dtype=HIT_DTYPE, count=c) for g, c in zip(gathered, counts)]
     return np.concatenate(parts) if parts else np.empty(0, dtype=HIT_DTYPE), total
+
+
+def bind_host_thread_to_gpu(device):
+    """Pin the calling thread (and the page-locked buffers it allocates from now on) to the CPUs next to GPU
+    `device` (NVML's ideal affinity).  With one process per GPU on a two-socket host this keeps every rank's
+    host-to-device copies off the inter-socket link; returns the previous affinity set (restore it with
+    os.sched_setaffinity(0, previous)), or None when NVML is not available."""
+    import os
+    try:
+        import pynvml
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        pynvml.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        previous = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return previous
+    except Exception:
+        return None
