@@ -8,8 +8,8 @@
 //   :35-45    get_gc_weights: weight_i = e ** (sum_{all L letters} log gc_i[c] + L log 4)
 //   :292-295  hist_i[round(score_i, 1)] += weight_i
 // One thread per sample, classes in an inner loop with the per-class logs in shared memory.
-// Score sums use the reference's order (bit-exact scores, hence exact buckets); histogram sums are
-// order-free fp64 atomics (relative difference ~1e-13, far inside the 1e-6 bound).
+// Buckets are the reference's exactly (scores near a bucket boundary are recomputed in its order, see below);
+// histogram sums are order-free fp64 atomics (relative difference ~1e-13, far inside the 1e-6 bound).
 #pragma once
 #include "device_common.cuh"
 
@@ -85,24 +85,48 @@ __global__ void __launch_bounds__(CAL_THREADS) calibrate_kernel(const CalibArgs 
         }
         atomicAdd(&s_ok, 1u);
     }
+    // letter counts: of the whole sample (weights) and of the letters the winning configuration consumed (scores)
+    double n_all[4] = {0.0, 0.0, 0.0, 0.0}, n_use[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < L; k++) {
+        const int c = (int)((bits >> (2 * k)) & 3);
+#pragma unroll
+        for (int q = 0; q < 4; q++) n_all[q] += c == q ? 1.0 : 0.0;
+    }
+    for (int k = 0; k < n_used; k++) {
+        const int c = (int)((used >> (2 * k)) & 3);
+#pragma unroll
+        for (int q = 0; q < 4; q++) n_use[q] += c == q ? 1.0 : 0.0;
+    }
+    const double inv_ln2 = 1.0 / A.ln2;
     for (int i = 0; i < A.n_class; i++) {
         const double *lg = cls + 4 * i;
-        double score = 0.0;
-        if (ok) {
-            double p = 0.0;
-            for (int k = 0; k < n_used; k++) p = __dadd_rn(p, lg[(used >> (2 * k)) & 3]);
-            score = __ddiv_rn(__dsub_rn(r.pm, p), A.ln2);
-            if (!(score > 0.0)) score = 0.0;
-        }
-        double pw = 0.0;
-        for (int k = 0; k < L; k++) pw = __dadd_rn(pw, lg[(bits >> (2 * k)) & 3]);
-        const double weight = live ? exp(__dadd_rn(pw, A.K)) : 0.0;
+        const double l0 = lg[0], l1 = lg[1], l2 = lg[2], l3 = lg[3];
+        // The weight enters the histograms only as a sum of ~1e4-1e6 terms (order-free, tolerance 1e-6): its
+        // exponent comes from the letter counts.  The score decides a bucket, which must be the reference's: it is
+        // first estimated from the counts (within 1e-12 of the reference's letter-by-letter sum) and recomputed in
+        // the reference's order only when the estimate lies within 1e-8 of a bucket boundary.
+        const double pw = n_all[0] * l0 + n_all[1] * l1 + n_all[2] * l2 + n_all[3] * l3;
+        const double weight = live ? exp(pw + A.K) : 0.0;
         int bin = 0;
-        if (score > 0.0) {
-            bin = (int)(score * 10.0 + 0.5);
+        if (ok) {
+            const double est = (r.pm - (n_use[0] * l0 + n_use[1] * l1 + n_use[2] * l2 + n_use[3] * l3)) * inv_ln2;
+            const double scaled = est * 10.0 + 0.5;
+            bin = scaled > 0.0 ? (int)scaled : 0;
+            const double frac = scaled - (double)bin;
+            if (scaled > -1e-6 && (frac < 1e-7 || frac > 1.0 - 1e-7)) {       // too close to call: the reference's own arithmetic
+                double p = 0.0;
+                for (int k = 0; k < n_used; k++) p = __dadd_rn(p, lg[(used >> (2 * k)) & 3]);
+                double score = __ddiv_rn(__dsub_rn(r.pm, p), A.ln2);
+                if (!(score > 0.0)) score = 0.0;
+                bin = 0;
+                if (score > 0.0) {
+                    bin = (int)(score * 10.0 + 0.5);
+                    if (bin > A.n_bins) bin = A.n_bins;
+                    while (bin > 0 && score < __ldg(A.thr + bin - 1)) bin--;
+                    while (bin < A.n_bins && score >= __ldg(A.thr + bin)) bin++;
+                }
+            }
             if (bin > A.n_bins) bin = A.n_bins;
-            while (bin > 0 && score < __ldg(A.thr + bin - 1)) bin--;
-            while (bin < A.n_bins && score >= __ldg(A.thr + bin)) bin++;
         }
         double w0 = bin == 0 ? weight : 0.0;          // the common bucket: reduce in the warp first
         for (int o = 16; o; o >>= 1) w0 += __shfl_down_sync(FULL_MASK, w0, o);
