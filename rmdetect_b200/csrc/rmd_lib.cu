@@ -844,7 +844,8 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     out->tries[1] = (int64_t)counters[2];
 #ifdef RMD_STATS
     fprintf(stderr, "[rmd stats] tree visits %llu in %llu warp iterations; warp cycles: staging %llu, generate+gate+score %llu, "
-            "window-end engine %llu, barrier+tail %llu\n", counters[4], counters[5], counters[8], counters[9], counters[10], counters[11]);
+            "window-end engine %llu, barrier+tail %llu; candidate funnel: %llu (entry, node) pairs -> %llu with all ancestors -> %llu new placements (%llu sure)\n",
+            counters[4], counters[5], counters[8], counters[9], counters[10], counters[11], counters[12], counters[13], counters[14], counters[15]);
 #endif
     // ---- ordering, scoring, duplicate removal, compaction ---------------------------------------
     RESERVE(ctx->d_final, sizeof(rmd_hit) * (size_t)std::max<long long>(n_raw, 1));

@@ -630,6 +630,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
                             const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
                             bool ok = act;
+#ifdef RMD_STATS
+                            if (lane == 0) atomicAdd(&O.stats[4], (unsigned long long)n);
+#endif
                             int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
                             while (__any_sync(FULL_MASK, ok && a >= 0)) {  // every pair before it must be non-zero
                                 if (ok && a >= 0) {
@@ -638,6 +641,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                                     a = an.parent;
                                 }
                             }
+#ifdef RMD_STATS
+                            { const uint32_t a1 = __ballot_sync(FULL_MASK, ok); if (lane == 0) atomicAdd(&O.stats[5], (unsigned long long)__popc(a1)); }
+#endif
                             if (ok) {                                    // a placement is queued once
                                 const int slot = sm.cb_slot[tn.model];
                                 if (slot >= 0) {
@@ -656,6 +662,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             const bool sure = ok && (it >> 31);
                             const uint32_t om = __ballot_sync(FULL_MASK, ok);
                             const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
+#ifdef RMD_STATS
+                            if (lane == 0) { atomicAdd(&O.stats[6], (unsigned long long)__popc(om)); atomicAdd(&O.stats[7], (unsigned long long)__popc(smask)); }
+#endif
                             const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
                             if (sure) { qs[qns + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
                             else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
