@@ -371,6 +371,45 @@ def test_prefix_screens_do_not_change_results(letters):
     assert at == len(hits) and runs[0][0] == tests
 
 
+def test_full_size_chromosome_invariants():
+    """BASELINE.json configs[2] at full size (10 Mb, 133 333 windows, 9.46e9 placements), where the oracle takes
+    minutes: size-independent properties instead.  tests_all equals the odometer's closed form; the hit list does not
+    depend on the prefix screens; cutting the window range changes nothing but the duplicate rule at the seams; the
+    host-buffer call (compact and fp64 transport) returns the device-resident result."""
+    from rmdetect_b200 import _native
+    from rmdetect_b200.gcx import gc_table
+    from rmdetect_b200.scanner import ScanEngine, placements_in_window
+    n, seed = 10_000_000, 20261019
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    gc = gc_table({b: math.log(0.25) for b in "ACGU"})
+    n_win, n_bpp, _ = eng.ctx.synth_job(n, 0, seed, seed, 150, 75, 0.001, LN_CUTOFF, gc)
+    assert n_win == 133333
+    whole = eng.ctx.scan_resident(0, n_win)
+    assert whole["tries"][0] == n_win * sum(placements_in_window(m, 150) for m in eng.models) == 9458509687
+    assert whole["tries"][1] == int(whole["gate_pass"].sum()) and whole["n_raw"] == int(whole["raw_count"].sum())
+    assert len(whole["hits"]) > 500000 and np.all(np.diff(whole["hits"]["window"]) >= 0)
+    eng.ctx.set_screen_policy(-1)                                             # no prefix screens
+    plain = eng.ctx.scan_resident(0, n_win)
+    assert plain["tries"] == whole["tries"] and plain["hits"].tobytes() == whole["hits"].tobytes()
+    eng.ctx.set_screen_policy(1024)
+    cuts = [0, 40000, 40001, 99999, n_win]
+    parts = [eng.ctx.scan_resident(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert [sum(p["tries"][k] for p in parts) for k in (0, 1)] == whole["tries"]
+    assert sum(p["n_raw"] for p in parts) == whole["n_raw"]
+    seams = sum(len(p["hits"]) for p in parts) - len(whole["hits"])           # duplicates across a cut survive
+    assert 0 <= seams <= 3 * 40
+    # the same job from host buffers, both transports
+    off, bi, bj, bp = eng.ctx.download_job(n_win, n_bpp)
+    job = dict(seq_off=np.array([0, n], dtype=np.int64), codes=eng.ctx.download_codes(n), gc_log=gc.reshape(1, -1),
+               gc_class=np.full((1, 4), -1, dtype=np.int32), win_len=150, win_step=75, n_win=n_win, bpp_off=off,
+               bpp_i=bi, bpp_j=bj, bpp_p=bp, min_bpp_mean=0.001, cutoff=LN_CUTOFF)
+    ij, q = _native.compact_bpp(bi, bj, bp)
+    for j in (job, dict(job, bpp_i=None, bpp_j=None, bpp_p=None, bpp_ij=ij, bpp_q=q)):
+        r = eng.ctx.scan(j)
+        assert r["tries"] == whole["tries"] and r["hits"].tobytes() == whole["hits"].tobytes()
+    eng.close()
+
+
 def test_malformed_bpp_list_is_rejected():
     """The kernel's own checks (the host layer sorts and validates; a C caller may not)."""
     from rmdetect_b200._native import NativeError
