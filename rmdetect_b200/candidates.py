@@ -146,3 +146,60 @@ def filter_candidates(cands, min_score=None, min_bpp=None, min_evalue=None):
         out.append(c)
     out.sort()
     return out
+
+
+# ---- rmfilter's selections (reference lib/candidates.py:99-207, driven by rmfilter.py:62-83) -------------------
+def _top(cands, n, key_of):
+    out, seen = [], {}
+    for c in sorted(cands):
+        k = key_of(c)
+        seen[k] = seen.get(k, 0) + 1
+        if seen[k] <= n:
+            out.append(c)
+    return out
+
+
+def top_model(cands, n):
+    """The n best hits of every model (`--top-model`, reference lib/candidates.py:99-116)."""
+    return _top(cands, n, lambda c: c.model.full_name())
+
+
+def top_seq(cands, n):
+    """The n best hits of every sequence (`--top-seq`, :118-135)."""
+    return _top(cands, n, lambda c: c.key)
+
+
+def top_seq_model(cands, n):
+    """The n best hits of every (sequence, model) (`--top-seq-model`, :137-154)."""
+    return _top(cands, n, lambda c: c.key + "_" + c.model.full_name())
+
+
+def get_model(cands, model_name):
+    """Hits of one model, sorted (`--model`, :156-169)."""
+    return [c for c in sorted(cands) if c.model.full_name().upper() == model_name.upper()]
+
+
+def nooverlap(cands):
+    """Of two hits of one sequence whose windows overlap and whose chains overlap pairwise, keep the earlier one only
+    if it scores strictly higher and has a positive bpp, else the later one (`--no-overlap`, :171-207)."""
+    cands = list(cands)
+    for i in range(len(cands)):
+        if cands[i] is None:
+            continue
+        for j in range(i + 1, len(cands)):
+            if cands[j] is None:
+                continue
+            a, b = cands[i], cands[j]
+            dup = a.coords[0] < b.coords[1] and b.coords[0] < a.coords[1] and a.key == b.key
+            if dup:
+                for pi, pj in zip(a.chains_pos, b.chains_pos):
+                    if pi[0] > pj[-1] or pi[-1] < pj[0]:
+                        dup = False
+                        break
+            if dup:
+                if a.score > b.score and a.bpp > 0:
+                    cands[j] = None
+                else:
+                    cands[i] = None
+                    break
+    return [c for c in cands if c is not None]
