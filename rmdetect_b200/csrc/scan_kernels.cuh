@@ -88,7 +88,7 @@ struct __align__(16) FastSmem {
     double2 zero2;                       // (0, 0)
     TrieNode trie[TRIE_CAP];
     double gc[RMD_N_CODES];
-    double sure_min[RMD_MAX_MODELS];     // a generating value >= this passes the gate for certain
+    uint8_t need[TRIE_CAP];              // per trie node: a generating value of at least need x min_bpp passes the gate for certain
     uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
@@ -190,17 +190,22 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         sm.trie0[tid] = (uint16_t)M.trie0;
         sm.trie_end[tid] = (uint16_t)(M.trie0 + M.n_trie);
         sm.cb_slot[tid] = (int8_t)M.cb_slot;
-        // mean = sum / count >= p / slots: sum >= p (positive terms, monotone rounding), count <= slots,
-        // division monotone; the factor covers the rounding of the product and of that division
-        const double slots = (double)M.cfg_begin[M.n_cfg];
-        sm.sure_min[tid] = J.min_bpp * slots * (1.0 + 1e-12);
     }
     if (tid <= RMD_MAX_MODELS) sm.screen0[tid] = J.screen0[tid];
     if (tid < 32) sm.prel[tid] = c_prel[tid];
     if (tid == 0) sm.zero2 = make_double2(0.0, 0.0);
     {
+        // Sure passes.  A node's value enters the reference's sum once per configuration that runs through the node
+        // (`mult` times), and the count never exceeds the model's MUST slots: mean = sum / count >= mult * p / slots
+        // (positive terms, monotone rounding, division monotone).  So p >= need * min_bpp * (1 + 1e-12) with
+        // need = ceil(slots / mult) passes for certain; the factor covers the roundings.  255: never.
         const int nt = c_models[n_models - 1].trie0 + c_models[n_models - 1].n_trie;
-        for (int k = tid; k < nt; k += SCAN_THREADS) sm.trie[k] = c_trie[k];
+        for (int k = tid; k < nt; k += SCAN_THREADS) {
+            const TrieNode tn = c_trie[k];
+            sm.trie[k] = tn;
+            const int slots = c_models[tn.model].cfg_begin[c_models[tn.model].n_cfg];
+            sm.need[k] = (uint8_t)min((slots + tn.mult - 1) / max((int)tn.mult, 1), 255);
+        }
     }
     __syncthreads();
     const uint4 *xn = TABLES ? sx : reinterpret_cast<const uint4 *>(J.xnodes);
@@ -535,6 +540,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             // big entries x trie nodes -> placements (see the header of this file).  Every warp works on its
             // own share of the entries: no team-wide barrier in this loop.
             const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
+            const double inv_sure_unit = 1.0 / (J.min_bpp * (1.0 + 1e-12));
             uint32_t *const wl = wq.wl, *const s2 = wq.s2;
             const int n_prel = c_n_prel;
             const int n_groups = c_n_groups;
@@ -565,9 +571,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
                             if (p >= big_min) {
                                 isbig = true;
-                                uint32_t sure = 0;
-                                for (int m = g0; m < g1; m++) sure |= (p >= sm.sure_min[m] ? 1u : 0u) << m;
-                                en = (uint32_t)J.bpp_i[b0 + e] | ((uint32_t)J.bpp_j[b0 + e] << 8) | (sure << 16);
+                                // the value in units of the threshold, rounded down (at most 254): compared with `need` per node
+                                const uint32_t level = (uint32_t)fmin(p * inv_sure_unit, 254.0);
+                                en = (uint32_t)J.bpp_i[b0 + e] | ((uint32_t)J.bpp_j[b0 + e] << 8) | (level << 16);
                             }
                         }
                         const uint32_t bm = __ballot_sync(FULL_MASK, isbig);
@@ -592,7 +598,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                         }
                     int m = g0 - 1;                               // model of the current trie node
                     int t = flush ? tg1 : tg0, t1m = t;           // t1m: end of that model's nodes
-                    uint32_t n0 = 0, sure_m = 0;
+                    uint32_t n0 = 0;
+                    const uint32_t level = (en >> 16) & 0xffu;
                     int hi = 0;
                     bool sym = false;
                     for (;;) {
@@ -604,7 +611,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             else ok = ok && (uint32_t)p1 <= (uint32_t)hi;
                             const uint32_t om = __ballot_sync(FULL_MASK, ok);
                             if (om) {
-                                if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | sure_m;
+                                if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | (level >= sm.need[t] ? 0x80000000u : 0u);
                                 ns += __popc(om);
                                 __syncwarp();
                             }
@@ -616,7 +623,6 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             m++;                                  // the next model's nodes begin
                             const uint32_t bd = sm.bounds[m];
                             n0 = bd & 0xffu; hi = (int)((bd >> 8) & 0xffu); sym = bd >> 16;
-                            sure_m = ((en >> (16 + m)) & 1u) << 31;
                             t1m = sm.trie_end[m];
                             continue;
                         }

@@ -410,6 +410,33 @@ def test_full_size_chromosome_invariants():
     eng.close()
 
 
+def test_sure_pass_rule_on_its_boundary():
+    """A generating value of at least ceil(slots / mult) x min_bpp x (1 + 1e-12) skips the gate walk.  Worst case for
+    that rule: every pair of the window present with a tiny value (all configurations run to their end, the count is
+    the full number of MUST slots) and single spikes sitting exactly on, one ulp under and one ulp over the
+    multiples of the threshold the rule uses (KT, GB, TGA: 2; CL: 15, 30, 60)."""
+    from rmdetect_b200.synth import synth_sequence
+    t = 0.001
+    unit = t * (1.0 + 1e-12)
+    spikes = []
+    for need in (1, 2, 15, 30, 60):
+        for v in (need * unit, need * t):
+            spikes += [np.nextafter(v, 0.0), v, np.nextafter(v, 1.0)]
+
+    def fold(win):
+        n = len(win)
+        i, j = np.triu_indices(n, 1)
+        p = np.full(len(i), 1e-5)
+        rng = np.random.default_rng(n + 7)
+        at = rng.choice(len(i), size=12 * len(spikes), replace=False)
+        p[at] = np.tile(np.array(spikes), 12)
+        return i.astype(np.uint16), j.astype(np.uint16), p
+
+    seq = synth_sequence(150, 41)
+    res = _scan_vs_oracle(MODEL_ORDER, seq, _TableFold(fold), t)
+    assert res["tries"][1] > 200
+
+
 def test_malformed_bpp_list_is_rejected():
     """The kernel's own checks (the host layer sorts and validates; a C caller may not)."""
     from rmdetect_b200._native import NativeError
