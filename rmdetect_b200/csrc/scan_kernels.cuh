@@ -567,13 +567,14 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                         uint32_t en = 0;
                         bool isbig = false;
                         if (e < nnz) {
-                            const double p = __ldg(vals + e);
+                            const double p = __ldg(vals + e);         // three independent loads: one memory latency per chunk
+                            const uint32_t ei = J.bpp_i[b0 + e], ej = J.bpp_j[b0 + e];
                             if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
                             if (p >= big_min) {
                                 isbig = true;
                                 // the value in units of the threshold, rounded down (at most 254): compared with `need` per node
                                 const uint32_t level = (uint32_t)fmin(p * inv_sure_unit, 254.0);
-                                en = (uint32_t)J.bpp_i[b0 + e] | ((uint32_t)J.bpp_j[b0 + e] << 8) | (level << 16);
+                                en = ei | (ej << 8) | (level << 16);
                             }
                         }
                         const uint32_t bm = __ballot_sync(FULL_MASK, isbig);
