@@ -49,7 +49,7 @@
 #define QS_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
 #define Q2_CAP 64                       // walks waiting for the scoring engine: < 32 waiting + 32 from one screen batch
 #define WL_CAP 48                       // < 16 waiting + 32 from one chunk of entries
-#define S2_CAP 64                       // < 32 waiting + 32 pushed at once
+#define S2_CAP 96                       // < 32 waiting + 2 x 32 pushed by one step of the node loop
 #ifndef CB_SLOTS
 #define CB_SLOTS 1                      // duplicate bitmaps resident together (models whose gate trie has more than two nodes)
 #endif
@@ -604,19 +604,29 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     int hi = 0;
                     bool sym = false;
                     for (;;) {
-                        while (t < t1m && ns < 32) {              // warp-uniform trie node
-                            const TrieNode tn = sm.trie[t];
-                            const int p0 = er - tn.ro, p1 = ec - tn.co;
-                            bool ok = valid && ((PM >> tn.pbit) & 1u) && (uint32_t)p0 < n0;
-                            if (sym) ok = ok && p1 >= p0 && (p1 <= hi || p1 == p0);
-                            else ok = ok && (uint32_t)p1 <= (uint32_t)hi;
-                            const uint32_t om = __ballot_sync(FULL_MASK, ok);
-                            if (om) {
-                                if (ok) s2[ns + __popc(om & lt_mask)] = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)t << 16) | (level >= sm.need[t] ? 0x80000000u : 0u);
-                                ns += __popc(om);
+                        // warp-uniform trie nodes, two per step: independent loads and tests keep the pipeline busy
+                        while (t < t1m && ns < 32) {
+                            const bool two = t + 1 < t1m;
+                            const TrieNode ta = sm.trie[t], tb = sm.trie[two ? t + 1 : t];
+                            const int a0 = er - ta.ro, a1 = ec - ta.co, b0p = er - tb.ro, b1p = ec - tb.co;
+                            bool oka = valid && ((PM >> ta.pbit) & 1u) && (uint32_t)a0 < n0;
+                            bool okb = two && valid && ((PM >> tb.pbit) & 1u) && (uint32_t)b0p < n0;
+                            if (sym) {
+                                oka = oka && a1 >= a0 && (a1 <= hi || a1 == a0);
+                                okb = okb && b1p >= b0p && (b1p <= hi || b1p == b0p);
+                            } else {
+                                oka = oka && (uint32_t)a1 <= (uint32_t)hi;
+                                okb = okb && (uint32_t)b1p <= (uint32_t)hi;
+                            }
+                            const uint32_t oma = __ballot_sync(FULL_MASK, oka), omb = __ballot_sync(FULL_MASK, okb);
+                            if (oma | omb) {
+                                const int na = __popc(oma);
+                                if (oka) s2[ns + __popc(oma & lt_mask)] = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)t << 16) | (level >= sm.need[t] ? 0x80000000u : 0u);
+                                if (okb) s2[ns + na + __popc(omb & lt_mask)] = (uint32_t)b0p | ((uint32_t)b1p << 8) | ((uint32_t)(t + 1) << 16) | (level >= sm.need[t + 1] ? 0x80000000u : 0u);
+                                ns += na + __popc(omb);
                                 __syncwarp();
                             }
-                            t++;
+                            t += two ? 2 : 1;
                         }
                         const bool row_done = flush && t >= tg1;  // the closing pass of the group: whatever is left in s2
                         if (ns < 32 && !row_done) {
