@@ -432,14 +432,22 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     const unsigned long long em = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
                                                   ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
                     alive = false;
-                    for (; q < qe; q++) {
-                        const uint4 d0 = reinterpret_cast<const uint4 *>(scr + q)[0], d1 = reinterpret_cast<const uint4 *>(scr + q)[1];
+                    auto bit_index = [&](const int k, uint32_t &word_off) {     // letters of the screen's runs -> table bit
+                        const uint4 d0 = reinterpret_cast<const uint4 *>(scr + k)[0], d1 = reinterpret_cast<const uint4 *>(scr + k)[1];
                         // d0 = word_off, shift[4], dst[4], mask[0]; d1 = mask[1..3], pad
                         uint32_t idx = ((uint32_t)(em >> (d0.y & 0xffu)) & d0.w) << (d0.z & 0xffu);
                         idx |= ((uint32_t)(em >> ((d0.y >> 8) & 0xffu)) & d1.x) << ((d0.z >> 8) & 0xffu);
                         idx |= ((uint32_t)(em >> ((d0.y >> 16) & 0xffu)) & d1.y) << ((d0.z >> 16) & 0xffu);
                         idx |= ((uint32_t)(em >> (d0.y >> 24)) & d1.z) << (d0.z >> 24);
-                        if ((__ldg(tbl + d0.x + (idx >> 5)) >> (idx & 31u)) & 1u) alive = true;
+                        word_off = d0.x + (idx >> 5);
+                        return idx & 31u;
+                    };
+                    for (; q < qe; q += 2) {                      // two screens per step: both table reads in flight together
+                        const bool two = q + 1 < qe;
+                        uint32_t wa, wb;
+                        const uint32_t ba = bit_index(q, wa), bb = bit_index(two ? q + 1 : q, wb);
+                        const uint32_t va = __ldg(tbl + wa), vb = __ldg(tbl + wb);
+                        if (((va >> ba) | (vb >> bb)) & 1u) alive = true;
                     }
                 }
             }
