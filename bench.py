@@ -35,8 +35,8 @@ MODEL_FILES = ["cl_1", "tga_1", "gb_1", "kt_1"]         # the order os.listdir g
 DATA = os.path.join(ROOT, "tests", "golden", "ref_data", "models")
 LN_UNKNOWN, LN_CUTOFF, MIN_BPP = math.log(1e-4), math.log(0.1), 0.001
 CAL_SAMPLES = 1 << 20                                    # calibration samples per model and GPU
-NCU_DRAM_BYTES_PER_LAUNCH = 1037378000 + 25428736        # one scan_fast_kernel launch over the 10 Mb workload (ncu --set full)
-NCU_WARP_INSTRUCTIONS_PER_LAUNCH = 12165231004           # smsp__inst_executed.sum of the same launch
+NCU_DRAM_BYTES_PER_LAUNCH = 1035021000 + 25409024        # one scan_fast_kernel launch over the 10 Mb workload (ncu --set full)
+NCU_WARP_INSTRUCTIONS_PER_LAUNCH = 11568635720           # smsp__inst_executed.sum of the same launch
 ISSUE_SLOTS_PER_SM_CYCLE = 4                             # one warp instruction per scheduler and cycle
 
 
