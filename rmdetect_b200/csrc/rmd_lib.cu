@@ -778,8 +778,8 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         // the persistent kernel and pays its tail (0.1 ms), and the first must be small so that the scan starts
         // early.  A chunk can start once its copy is complete: with the copy r times faster per window than the
         // scan, the scan never waits if every chunk END grows by at most the factor r over the previous one
-        // (compact transport on a B200: copy 10 ms, scan 16 ms per 133 k windows, r = 1.6; measured best: ends growing
-        // by 1.8, a launch more costs more than the short wait).  Doubling chunk SIZES, as an earlier version did,
+        // (compact transport on a B200: copy 10 ms, scan 13 ms per 133 k windows, r = 1.3; measured best: ends growing
+        // by 1.55-1.6, a launch more costs more than a short wait).  Doubling chunk SIZES, as an earlier version did,
         // left the last chunk (half of the data) waiting 1.7 ms for its copy.
         const bool streaming = stream_in && attempt == 0 && ctx->n_bpp > 0;
         long long bounds[STREAM_CHUNKS + 1];
@@ -789,7 +789,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             if (stream_in->bpp_q) {
                 n_chunks = 0;
                 long long end = std::max<long long>(nwin / 128, 2048);
-                while (end < nwin && n_chunks < STREAM_CHUNKS - 1) { bounds[++n_chunks] = w_begin + end; end = end + end * 4 / 5 + 1024; }
+                while (end < nwin && n_chunks < STREAM_CHUNKS - 1) { bounds[++n_chunks] = w_begin + end; end = end + end * 3 / 5 + 1024; }
                 bounds[++n_chunks] = w_end;
             } else {
                 n_chunks = (int)std::min<long long>(STREAM_CHUNKS, nwin / 2048);
