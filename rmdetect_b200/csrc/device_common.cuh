@@ -114,6 +114,8 @@ struct DevJob {
     const long long *bpp_off;    // [n_win+1]
     const uint16_t *bpp_i, *bpp_j;
     const double *bpp_p;
+    const uint16_t *bpp_ij;      // compact transport kept on the device (rmd_scan): i | j << 8 per entry, values as bpp_q;
+    const uint32_t *bpp_q;       // scan_fast_kernel<..., FUSED> then rebuilds bpp_p window by window (nullptr: bpp_i/j/p are complete)
     double min_bpp, cutoff;
     const XNode *xnodes;         // all models' search trees (scoring engine format)
     const double *xcpt;          // all models' CPTs, concatenated

@@ -27,7 +27,9 @@ struct DBuf {                      // grow-only device buffer
 struct rmd_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev[12] = {};
+    cudaStream_t stream2 = nullptr;     // streamed scans without expansion launches: chunks alternate between two compute streams, so
+                                        // the next chunk's CTAs take the SMs the previous launch's tail leaves idle
+    cudaEvent_t ev[16] = {};
     std::string error;
     // models
     int n_models = 0;
@@ -123,6 +125,7 @@ extern "C" int rmd_create(int device, rmd_ctx **out) {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
     *out = ctx;
     return RMD_OK;
@@ -153,6 +156,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 
@@ -444,6 +448,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         ctx->scan_smem = fixed + teams * sizeof(FastSmem);
         if (ctx->scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", ctx->scan_smem, smem_max);
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -567,12 +572,13 @@ static int build_screens(rmd_ctx *ctx) {
 
 // Copy bpp entries [e0, e1) of a job to the device on `copy_st`; with the compact transport the lists the scan
 // reads are rebuilt by expand_bpp_kernel, issued on the compute stream after the copy.
-static int stage_entries(rmd_ctx *ctx, const rmd_scan_input *in, long long e0, long long e1, cudaStream_t copy_st) {
+static int stage_entries(rmd_ctx *ctx, const rmd_scan_input *in, long long e0, long long e1, cudaStream_t copy_st, bool expand = true) {
     if (e1 <= e0) return RMD_OK;
     const size_t n = (size_t)(e1 - e0);
     if (in->bpp_q) {
         CK(cudaMemcpyAsync((uint16_t *)ctx->d_bpp_ij.p + e0, in->bpp_ij + e0, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, copy_st));
         CK(cudaMemcpyAsync((uint32_t *)ctx->d_bpp_q.p + e0, in->bpp_q + e0, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, copy_st));
+        if (!expand) return RMD_OK;                         // scan_fast_kernel<..., FUSED> rebuilds the values window by window
         if (copy_st != ctx->stream) {
             CK(cudaEventRecord(ctx->ev[11], copy_st));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[11], 0));
@@ -641,6 +647,7 @@ static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries)
     J.codes8 = ctx->any_other ? (const uint8_t *)ctx->d_codes8.p : nullptr;
     J.bpp_off = (const long long *)ctx->d_bpp_off.p;
     J.bpp_i = (const uint16_t *)ctx->d_bpp_i.p; J.bpp_j = (const uint16_t *)ctx->d_bpp_j.p; J.bpp_p = (const double *)ctx->d_bpp_p.p;
+    J.bpp_ij = nullptr; J.bpp_q = nullptr;
     J.min_bpp = in->min_bpp_mean; J.cutoff = in->cutoff;
     ctx->have_job = true;
     return RMD_OK;
@@ -779,7 +786,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         // early.  A chunk can start once its copy is complete: with the copy r times faster per window than the
         // scan, the scan never waits if every chunk END grows by at most the factor r over the previous one
         // (compact transport on a B200: copy 10 ms, scan 13 ms per 133 k windows, r = 1.3; measured best: ends growing
-        // by 1.55-1.6, a launch more costs more than a short wait).  Doubling chunk SIZES, as an earlier version did,
+        // by 1.6, or by 1.45 when the launches overlap — a launch more costs more than a short wait).  Doubling chunk SIZES, as an earlier version did,
         // left the last chunk (half of the data) waiting 1.7 ms for its copy.
         const bool streaming = stream_in && attempt == 0 && ctx->n_bpp > 0;
         long long bounds[STREAM_CHUNKS + 1];
@@ -788,21 +795,43 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         if (streaming && nwin >= 4096) {
             if (stream_in->bpp_q) {
                 n_chunks = 0;
+                // without expansion launches, and with the chunks' tails overlapping on two streams, a launch costs less
+                const bool will_fuse = use_fast && !need_generic && ctx->tables_in_smem && !ctx->local_stack &&
+                                       !(ctx->any_brute || !(J.min_bpp > 0.0)) && !getenv("RMD_NO_FUSED_EXPAND");
+                const int gpct = will_fuse ? 45 : 60;
                 long long end = std::max<long long>(nwin / 128, 2048);
-                while (end < nwin && n_chunks < STREAM_CHUNKS - 1) { bounds[++n_chunks] = w_begin + end; end = end + end * 3 / 5 + 1024; }
+                while (end < nwin && n_chunks < STREAM_CHUNKS - 1) { bounds[++n_chunks] = w_begin + end; end = end + end * gpct / 100 + 1024; }
                 bounds[++n_chunks] = w_end;
             } else {
                 n_chunks = (int)std::min<long long>(STREAM_CHUNKS, nwin / 2048);
                 for (int k = 0; k <= n_chunks; k++) bounds[k] = w_begin + nwin * k / n_chunks;
             }
         }
+        // Compact transport and every window the shared-memory kernel's: no expansion launches between the scan launches,
+        // the teams rebuild the values of their own windows (and keep doing so while the job stays resident).  The
+        // chunks then alternate between two compute streams: a launch does not wait for the previous one to end, its
+        // CTAs start on the SMs whose persistent CTA has run out of windows.
+        if (streaming) {
+            const bool fused = stream_in->bpp_q && use_fast && !need_generic && ctx->tables_in_smem && !ctx->local_stack &&
+                               !(ctx->any_brute || !(J.min_bpp > 0.0)) && !getenv("RMD_NO_FUSED_EXPAND");     // = will_fuse above
+            ctx->job.bpp_ij = fused ? (const uint16_t *)ctx->d_bpp_ij.p : nullptr;
+            ctx->job.bpp_q = fused ? (const uint32_t *)ctx->d_bpp_q.p : nullptr;
+        }
+        const bool fused_expand = ctx->job.bpp_q != nullptr;
+        const bool two_streams = streaming && fused_expand && n_chunks > 1;
+        if (two_streams) {                                          // the second compute stream starts after the resets above
+            CK(cudaEventRecord(ctx->ev[12], st));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[12], 0));
+        }
+        const cudaStream_t first_stream = st;
         for (int ch = 0; ch < n_chunks && nwin > 0; ch++) {
             const long long c0 = bounds[ch], c1 = bounds[ch + 1];
+            const cudaStream_t st = two_streams && (ch & 1) ? ctx->stream2 : first_stream;
             if (streaming) {                                        // entries of windows [c0, c1): copy stream, then let the scan wait for them
                 const long long e0 = stream_in->bpp_off[c0], e1 = stream_in->bpp_off[c1];
-                int r3 = stage_entries(ctx, stream_in, e0, e1, ctx->copy_stream);
+                int r3 = stage_entries(ctx, stream_in, e0, e1, ctx->copy_stream, !fused_expand);
                 if (r3) return r3;
-                if (stream_in->bpp_q && e1 > e0) launches++;
+                if (stream_in->bpp_q && e1 > e0 && !fused_expand) launches++;
                 CK(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
                 CK(cudaStreamWaitEvent(st, ctx->ev[10], 0));
             }
@@ -816,6 +845,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                     // the exact-gate and global-table variants are the rare ones: they keep the local-memory stack
                     if (brute) scan_fast_kernel<true, true, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
                     else if (ctx->local_stack) scan_fast_kernel<false, true, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
+                    else if (fused_expand) scan_fast_kernel<false, true, false, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
                     else scan_fast_kernel<false, true, false><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
                 } else {
                     if (brute) scan_fast_kernel<true, false, true><<<grid, block, ctx->scan_smem, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, next);
@@ -827,6 +857,10 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                 scan_generic_kernel<<<(unsigned)((c1 - c0) * J.n_models), GEN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
                 launches++;
             }
+        }
+        if (two_streams) {                                          // join
+            CK(cudaEventRecord(ctx->ev[13], ctx->stream2));
+            CK(cudaStreamWaitEvent(st, ctx->ev[13], 0));
         }
         CK(cudaEventRecord(ctx->ev[1], st));
         CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 128, cudaMemcpyDeviceToHost, st));
@@ -1071,6 +1105,7 @@ extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t se
     CK(cudaMemcpyAsync(ctx->d_bpp_off.p, off64.data(), sizeof(long long) * off64.size(), cudaMemcpyHostToDevice, st));
     J.bpp_off = (const long long *)ctx->d_bpp_off.p;
     J.bpp_i = (const uint16_t *)ctx->d_bpp_i.p; J.bpp_j = (const uint16_t *)ctx->d_bpp_j.p; J.bpp_p = (const double *)ctx->d_bpp_p.p;
+    J.bpp_ij = nullptr; J.bpp_q = nullptr;
     synth_bpp_kernel<true><<<(unsigned)J.n_win, SYN_THREADS, 0, st>>>(J, bpp_seed, nullptr, J.bpp_off, (uint16_t *)ctx->d_bpp_i.p,
                                                                       (uint16_t *)ctx->d_bpp_j.p, (double *)ctx->d_bpp_p.p);
     CK(cudaEventRecord(ctx->ev[1], st));
@@ -1123,9 +1158,21 @@ extern "C" int rmd_download_codes(rmd_ctx *ctx, uint8_t *codes, int64_t n) {
     return RMD_OK;
 }
 
+// a job that arrived in the compact transport keeps only that form complete on the device: expand before handing lists back
+static int ensure_expanded(rmd_ctx *ctx) {
+    if (!ctx->job.bpp_q || ctx->n_bpp <= 0) return RMD_OK;
+    expand_bpp_kernel<<<(unsigned)((ctx->n_bpp + 255) / 256), 256, 0, ctx->stream>>>(ctx->job.bpp_ij, ctx->job.bpp_q, ctx->n_bpp, (uint16_t *)ctx->d_bpp_i.p,
+                                                                                   (uint16_t *)ctx->d_bpp_j.p, (double *)ctx->d_bpp_p.p);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ctx->job.bpp_ij = nullptr; ctx->job.bpp_q = nullptr;
+    return RMD_OK;
+}
+
 extern "C" int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint16_t *j, double *p, int64_t cap, int64_t *n) {
     if (!ctx || !n) return fail(ctx, RMD_E_INVALID, "rmd_download_bpp: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_bpp: no resident job");
+    { int re = ensure_expanded(ctx); if (re) return re; }
     if (window < 0 || window >= ctx->job.n_win) return fail(ctx, RMD_E_INVALID, "rmd_download_bpp: window out of range");
     CK(cudaSetDevice(ctx->device));
     long long off[2];
@@ -1145,6 +1192,7 @@ extern "C" int rmd_download_job(rmd_ctx *ctx, int64_t *bpp_off, uint16_t *i, uin
     if (!ctx || !bpp_off) return fail(ctx, RMD_E_INVALID, "rmd_download_job: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_job: no resident job");
     CK(cudaSetDevice(ctx->device));
+    { int re = ensure_expanded(ctx); if (re) return re; }
     CK(cudaMemcpy(bpp_off, ctx->d_bpp_off.p, sizeof(long long) * (ctx->job.n_win + 1), cudaMemcpyDeviceToHost));
     const long long nb = ctx->n_bpp;
     if (i && j && p && nb > 0) {

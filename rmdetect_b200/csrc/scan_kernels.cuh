@@ -109,13 +109,15 @@ __device__ __forceinline__ bool bpp_present(const FastSmem &sm, int wlen, int b1
 }
 
 // bpp lookup by popcount rank: 0.0 unless the pair is stored
+template <bool COHERENT = false>
 __device__ __forceinline__ double bpp_fast(const FastSmem &sm, const double *vals, int wlen, int b1, int b2) {
     const int lo = min(b1, b2), hi = max(b1, b2);
     if (hi >= wlen) return 0.0;
     const int k = lo * FAST_WORDS + (hi >> 5);
     const uint32_t w = sm.Ub[k], bit = 1u << (hi & 31);
     if (!(w & bit)) return 0.0;
-    return __ldg(vals + sm.Ur[k] + __popc(w & (bit - 1)));
+    const double *at = vals + sm.Ur[k] + __popc(w & (bit - 1));
+    return COHERENT ? *at : __ldg(at);                  // coherent: the team itself wrote the value (FUSED)
 }
 
 // __get_bpp_mean (lib/scanner.py:195-214) for one placement per lane: warp-uniform loops over the
@@ -154,7 +156,9 @@ __device__ __forceinline__ void team_sync(const int team) {
 // window from a global counter, so a slow window delays nobody else.  The models' search trees and CPTs
 // sit in shared memory once per CTA (TABLES: they fit), next to the teams' window state.
 // LSTK: the model set branches deeper than STK_SLOTS, the engine's save slots go to local memory.
-template <bool BRUTE, bool TABLES, bool LSTK>
+// FUSED: the job's lists are on the device in the compact transport only (rmd_scan); every team rebuilds the values of
+// its own window while staging it and reads them back with coherent loads.
+template <bool BRUTE, bool TABLES, bool LSTK, bool FUSED = false>
 __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
@@ -355,7 +359,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const uint32_t win_local = (uint32_t)(w - w_base);
         if (tid == 0) sm.win_local = win_local;
         // the values are first needed after the staging pass: have their lines on the way (one 128-byte line per thread)
-        for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
+        if (!FUSED) for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
 
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
         for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
@@ -392,8 +396,18 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             for (int k = 0; k < 4; k++) {
                 const int e = e0 + k * SCAN_THREADS + tid;
                 ei[k] = ej[k] = 0; pi[k] = pj[k] = -1;
-                if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
-                if (e < nnz && e > 0) { pi[k] = J.bpp_i[b0 + e - 1]; pj[k] = J.bpp_j[b0 + e - 1]; }
+                if (FUSED) {                                  // compact transport: i | j << 8, and the value is rebuilt here
+                    if (e < nnz) {
+                        const uint32_t w16 = J.bpp_ij[b0 + e], v = J.bpp_q[b0 + e];
+                        ei[k] = w16 & 0xffu; ej[k] = w16 >> 8;
+                        const double x = __ddiv_rn((double)(v & 0x3fffffffu), 1e9);       // as expand_bpp_kernel (post_kernels.cuh)
+                        const_cast<double *>(vals)[e] = __longlong_as_double(__double_as_longlong(__dmul_rn(x, x)) + (long long)(v >> 30) - 1);
+                    }
+                    if (e < nnz && e > 0) { const uint32_t w16 = J.bpp_ij[b0 + e - 1]; pi[k] = w16 & 0xffu; pj[k] = w16 >> 8; }
+                } else {
+                    if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
+                    if (e < nnz && e > 0) { pi[k] = J.bpp_i[b0 + e - 1]; pj[k] = J.bpp_j[b0 + e - 1]; }
+                }
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -412,7 +426,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 #ifdef RMD_STATS
         const long long ck1 = clock64();
 #endif
-        auto lookup = [&](int a, int b) { return bpp_fast(sm, vals, wlen, a, b); };
+        auto lookup = [&](int a, int b) { return bpp_fast<FUSED>(sm, vals, wlen, a, b); };
         qn1 = 0; qn2 = 0; qns = 0;
 
         // ---- prefix screens on up to 32 gate survivors: one table bit per top-level subtree of the model's search
@@ -575,8 +589,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                         uint32_t en = 0;
                         bool isbig = false;
                         if (e < nnz) {
-                            const double p = __ldg(vals + e);         // three independent loads: one memory latency per chunk
-                            const uint32_t ei = J.bpp_i[b0 + e], ej = J.bpp_j[b0 + e];
+                            const double p = FUSED ? vals[e] : __ldg(vals + e);   // independent loads: one memory latency per chunk
+                            uint32_t ei, ej;
+                            if (FUSED) { const uint32_t w16 = J.bpp_ij[b0 + e]; ei = w16 & 0xffu; ej = w16 >> 8; }
+                            else { ei = J.bpp_i[b0 + e]; ej = J.bpp_j[b0 + e]; }
                             if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
                             if (p >= big_min) {
                                 isbig = true;
