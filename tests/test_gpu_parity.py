@@ -463,7 +463,7 @@ def test_malformed_bpp_list_is_rejected():
 
 
 def test_compact_transport_gives_identical_results():
-    """rmd_scan with the 6-byte transport (ij + q words, expanded on the device) == rmd_scan with fp64 lists."""
+    """rmd_scan with the 6-byte transport (ij + q words, values rebuilt on the device) == rmd_scan with fp64 lists."""
     from rmdetect_b200._native import compact_bpp
     from rmdetect_b200.scanner import ScanEngine
     from rmdetect_b200.synth import SynthFold, synth_sequence
@@ -482,6 +482,18 @@ def test_compact_transport_gives_identical_results():
     assert got["tries"] == want["tries"] and len(want["hits"]) > 10
     assert got["hits"].tobytes() == want["hits"].tobytes()
     assert np.array_equal(got["gate_pass"], want["gate_pass"])
+    # rmd_scan left the lists compact on the device (the scan kernel rebuilt the values itself): a resident rescan,
+    # a rescan of a window range, and handing the lists back (which expands them) all see the caller's values
+    again = eng.ctx.scan_resident(0, job["n_win"])
+    assert again["hits"].tobytes() == want["hits"].tobytes() and again["tries"] == want["tries"]
+    part = eng.ctx.scan_resident(5, 30)
+    assert part["tries"][1] == int(want["gate_pass"][5:30].sum())
+    for w in (0, 17, job["n_win"] - 1):
+        a, b = int(job["bpp_off"][w]), int(job["bpp_off"][w + 1])
+        i, j, p = eng.ctx.download_bpp(w)
+        assert np.array_equal(i, job["bpp_i"][a:b]) and np.array_equal(j, job["bpp_j"][a:b]) and np.array_equal(p, job["bpp_p"][a:b])
+    after = eng.ctx.scan_resident(0, job["n_win"])                 # now from the expanded lists
+    assert after["hits"].tobytes() == want["hits"].tobytes()
     # the resident path too (rmd_upload + rmd_scan_resident)
     eng.ctx.upload(cjob)
     res = eng.ctx.scan_resident(0, job["n_win"])
