@@ -53,7 +53,9 @@
 #ifndef CB_SLOTS
 #define CB_SLOTS 1                      // duplicate bitmaps resident together (models whose gate trie has more than two nodes)
 #endif
+#ifndef SCAN_MAX_THREADS
 #define SCAN_MAX_THREADS 1024           // a CTA holds up to 8 teams of SCAN_THREADS
+#endif
 #ifndef REFILL_MIN_IDLE
 #define REFILL_MIN_IDLE 8               // the scoring engine hands out queued work once this many lanes are idle
 #endif
