@@ -35,9 +35,31 @@ MODEL_FILES = ["cl_1", "tga_1", "gb_1", "kt_1"]         # the order os.listdir g
 DATA = os.path.join(ROOT, "tests", "golden", "ref_data", "models")
 LN_UNKNOWN, LN_CUTOFF, MIN_BPP = math.log(1e-4), math.log(0.1), 0.001
 CAL_SAMPLES = 1 << 20                                    # calibration samples per model and GPU
-NCU_DRAM_BYTES_PER_LAUNCH = 1035021000 + 25409024        # one scan_fast_kernel launch over the 10 Mb workload (ncu --set full)
-NCU_WARP_INSTRUCTIONS_PER_LAUNCH = 11568635720           # smsp__inst_executed.sum of the same launch
 ISSUE_SLOTS_PER_SM_CYCLE = 4                             # one warp instruction per scheduler and cycle
+WORKLOAD = "config3: synthetic %d Mb random chromosome per GPU, win 150/75, models CL,TGA,GB,KT, synthetic bpp (gate on)"
+
+
+def ncu_summary(kernel="scan_fast"):
+    """DRAM bytes and warp instructions of one launch of the dominant kernel over the 10 Mb workload, read from the
+    newest committed `ncu --set full` summary under profiles/ (metric,unit,value rows; tools/ncu_metrics.py)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_ncu_full.csv" % kernel)))
+    if not files:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "inst": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}
+    vals = {}
+    for line in open(files[-1]):
+        t = line.strip().split(",")
+        if len(t) == 3 and t[1] in scale:
+            try:
+                vals[t[0]] = float(t[2]) * scale[t[1]]
+            except ValueError:
+                pass
+    if "dram__bytes_read.sum" not in vals:
+        return None
+    return {"file": os.path.relpath(files[-1], ROOT),
+            "dram_bytes": vals["dram__bytes_read.sum"] + vals.get("dram__bytes_write.sum", 0.0),
+            "warp_instructions": vals.get("smsp__inst_executed.sum"), "ms": vals.get("gpu__time_duration.sum")}
 
 
 def load_models():
@@ -78,25 +100,79 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline(models, n_threads, target_s):
-    """Oracle port on the host cores over a bounded sample: a prefix of the chromosome sized, from a pilot
-    run, to take about `target_s` seconds.  Returns (nt·model/s, seconds, windows, tries)."""
+def chromosome_counts(n, first=0):
+    """(A, C, G, U) counts of the synthetic chromosome: its GC table is taken over the whole sequence (lib/scanner.py:74-75)."""
+    import numpy as np
+    from rmdetect_b200.synth import synth_codes
+    counts = np.zeros(4, dtype=np.int64)
+    for a in range(0, n, 1 << 22):
+        counts += np.bincount(synth_codes(min(1 << 22, n - a), SEED, start=first + a), minlength=4)
+    return counts
+
+
+def cpu_baseline(models, n_threads, target_s, n_total, counts):
+    """Oracle port on the host cores over a bounded sample: a prefix of the chromosome sized, from a pilot run, to take
+    about `target_s` seconds.  The stand-in bpp lists are generated outside the timed scan (as on the GPU arm, where
+    they are inputs), and the GC table is the whole chromosome's, so the sample's counts and hit checksum can be
+    compared with the GPU's for the same windows.  Returns a dict."""
     from oracle import pyoracle
     from rmdetect_b200.synth import synth_sequence
+    max_win = 1 + -(-(n_total - WIN_LEN) // WIN_STEP)
 
     def run(nwin):
-        seq = synth_sequence(nwin * WIN_STEP + WIN_LEN, SEED)
-        t0 = time.perf_counter()
-        _, tries = pyoracle.bench_scan(models, seq, WIN_LEN, WIN_STEP, 0, nwin, SEED, n_threads, MIN_BPP,
-                                       LN_UNKNOWN, LN_CUTOFF)
-        return time.perf_counter() - t0, tries
+        length = n_total if nwin >= max_win else (nwin - 1) * WIN_STEP + WIN_LEN + WIN_STEP     # never re-anchors a tail window inside the sample
+        seq = synth_sequence(length, SEED)
+        return pyoracle.bench_scan2(models, seq, WIN_LEN, WIN_STEP, 0, nwin, SEED, n_threads, MIN_BPP, LN_UNKNOWN, LN_CUTOFF,
+                                    counts=counts)
 
-    pilot = 64 * n_threads
+    pilot = min(max_win, 64 * n_threads)
     run(pilot)                                                                   # warm the threads
-    dt, _ = run(pilot)
-    nwin = int(max(pilot, min(133333, pilot * target_s / max(dt, 1e-3))))
-    dt, tries = run(nwin)
-    return nwin * WIN_STEP * len(models) / dt, dt, nwin, tries
+    r = run(pilot)
+    nwin = int(max(pilot, min(max_win, pilot * target_s / max(r["s_scan"], 1e-3))))
+    r = run(nwin)
+    r.update(windows=nwin, value=nwin * WIN_STEP * len(models) / r["s_scan"], whole=nwin >= max_win)
+    return r
+
+
+def cal_cpu_baseline(models, cores, target_s):
+    """The oracle's restatement of rmcalibrate.py:265-295 on all host cores (one model instance per thread; ctypes
+    releases the GIL), device-twin samples, for about `target_s` seconds: the calibration metric's CPU baseline."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    from rmdetect_b200.gcx import GC
+    from rmdetect_b200.synth import synth_calibration_samples
+    classes = GC.get_classes(5, 15, 85)
+    m = models[-1]                                                               # KT_1.0: L = 16
+    L = len(m.nodes)
+
+    def work(k, n):
+        om = pyoracle.OracleModel(m)
+        rows = synth_calibration_samples(SEED, k * n, n, L)
+        strings = ["".join("ACGU"[c] for c in row) for row in rows]
+        t0 = time.perf_counter()
+        pyoracle.calibrate(om, strings, classes, LN_UNKNOWN, LN_CUTOFF, 512)
+        return time.perf_counter() - t0
+
+    pilot = work(0, 2000)
+    per = int(max(2000, min(200000, 2000 * target_s / max(pilot, 1e-3))))
+    with ThreadPoolExecutor(cores) as pool:
+        secs = list(pool.map(lambda k: work(k, per), range(cores)))
+    return {"value": per * cores / max(secs), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "oracle/rmd_oracle.c orc_calibrate, %s, %d samples on each of %d threads, %.1f s"
+                      % (m.full_name(), per, cores, max(secs))}
+
+
+def python_reference(cores):
+    """The reference's own Python `Scanner.scan` and `rmcalibrate.py` loop on this host (oracle/ref_bench.py on the
+    modules staged in oracle/_ref).  A subprocess: it forks workers, this process holds CUDA."""
+    script = os.path.join(ROOT, "oracle", "ref_bench.py")
+    try:
+        out = subprocess.run([sys.executable, script, "--windows", "20", "--procs", str(min(cores, 64)), "--cal-samples", "4000"],
+                             capture_output=True, text=True, timeout=600)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:                                                      # a baseline that cannot run is reported, not fatal
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
 
 def run_reference(args):
@@ -105,23 +181,28 @@ def run_reference(args):
         return
     models, _ = load_models()
     cores = os.cpu_count() or 1
+    n = args.mb * 1_000_000
+    counts = chromosome_counts(n)
     vals = []
     for k in range(args.warmup + args.steps):
-        v, dt, sample, tries = cpu_baseline(models, cores, 4.0 if k >= args.warmup else 1.0)
+        r = cpu_baseline(models, cores, 4.0 if k >= args.warmup else 1.0, n, counts)
         if k >= args.warmup:
-            vals.append((v, dt))
-    value = sum(v for v, _ in vals) / len(vals)
-    ms = 1e3 * sum(d for _, d in vals) / len(vals)
+            vals.append(r)
+    value = sum(r["value"] for r in vals) / len(vals)
+    ms = 1e3 * sum(r["s_scan"] for r in vals) / len(vals)
+    r = vals[-1]
     line = {
         "impl": "reference", "metric": "nt·models scanned/sec", "value": value, "unit": "nt·model/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config3: synthetic %d Mb random chromosome, win 150/75, models CL,TGA,GB,KT, "
-                               "synthetic bpp (gate on)" % args.mb,
-                   "sampled": "first %d windows (%d nt) per step" % (sample, sample * WIN_STEP)},
+        "config": {"workload": WORKLOAD % args.mb},
         "cpu_baseline": {"value": value, "unit": "nt·model/s", "cores": cores, "kind": "port",
-                         "sample": "oracle/rmd_oracle.c (C restatement of the reference's Python scan), OpenMP over "
-                                   "%d windows incl. its own synthetic-bpp generation" % sample},
+                         "sample": "oracle/rmd_oracle.c (C restatement of the reference's Python scan), OpenMP over the first "
+                                   "%d windows (%d nt) of the chromosome per step, whole-chromosome GC table; stand-in bpp "
+                                   "lists generated outside the timed scan (%.2f s per step)"
+                                   % (r["windows"], r["windows"] * WIN_STEP, r["s_generate"]),
+                         "tries": r["tries"], "hits_before_dedupe": r["hits"], "hit_checksum": "%016x" % r["checksum"],
+                         "python_reference": python_reference(cores)},
         "e2e": {"value": value, "unit": "nt·model/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -183,6 +264,11 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t0
     n_hits, n_raw, tries = len(r["hits"]), r["n_raw"], r["tries"]
+    # one untimed scan that also returns the hits the duplicate rule removed: what the CPU baseline's sample is checked against
+    ctx.set_return_dropped(True)
+    full = ctx.scan_resident(0, n_win, copy=True)
+    ctx.set_return_dropped(False)
+    assert full["n_raw"] == n_raw == len(full["hits"]) and int(full["hits"]["keep"].sum()) == n_hits
 
     # ---- end to end through the C ABI with host buffers --------------------------------------------
     off, bi, bj, bp = ctx.download_job(n_win, n_bpp, pinned=True)
@@ -219,7 +305,10 @@ def run_ours(args):
 
     # ---- second metric: calibration samples per second (BASELINE.json configs[3], throughput mode) ----
     # every rank scores its own CAL_SAMPLES device-drawn samples per model against the 165 GC classes
-    from rmdetect_b200.calibrate import class_logs
+    # (a) one batch per model and GPU (kernel + histogram download); (b) the reference's loop (rmcalibrate.py:235-298):
+    # blocks of 10 000 samples per GPU, the 165 x 512 fp64 histograms all-reduced (NCCL) after every block and the
+    # reference's convergence rule run on the reduced table; min(samples, 4^L) samples per model (TGA: 65 536)
+    from rmdetect_b200.calibrate import Calibrator, calibrate_model, class_logs
     from rmdetect_b200.gcx import GC
     cl = class_logs(GC.get_classes(5, 15, 85))
     hists = [np.zeros((len(cl), 512)) for _ in models]
@@ -234,16 +323,29 @@ def run_ours(args):
         cal_kernel_ms += ms_k
     barrier()
     cal_wall = time.perf_counter() - t2
+    cal_done, cal_blocks, cal_loop_kernel_ms, cal_sum = 0, 0, 0.0, 0.0
+    barrier()
+    t3 = time.perf_counter()
+    for mi, m in enumerate(models):
+        st = {}
+        _, _, done = calibrate_model(m, None, samples=CAL_SAMPLES * world, seed=SEED, device_samples=True, log=None, dist=dist,
+                                     scorer=Calibrator(m, LN_UNKNOWN, LN_CUTOFF, ctx=ctx, model_index=mi),
+                                     save_every_block=False, stats=st)
+        cal_done += done; cal_blocks += st["blocks"]; cal_loop_kernel_ms += st["ms_kernel"]
+        cal_sum += float(st["hist"].sum())                      # the reduced table is the same on every rank
+    barrier()
+    cal_loop_wall = time.perf_counter() - t3
 
     # ---- reduce over ranks: time = max, work = sum ---------------------------------------------------
-    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall], dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall, cal_loop_wall, cal_loop_kernel_ms],
+                     dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_hits, n_raw, tries[0], tries[1]], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(gathered, cnt)                      # the only collective: small per-rank hit counts
         cnt = torch.stack(gathered).sum(0)
-    wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall = t.tolist()
+    wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall, cal_loop_wall, cal_loop_kernel_ms = t.tolist()
     total_units = units * world
     value = total_units * args.steps / wall
     e2e_value = total_units * args.steps / e2e_wall
@@ -262,22 +364,33 @@ def run_ours(args):
         ms_kernel = scan_ms / args.steps
         achieved = algo / (ms_kernel * 1e-3) / 1e9
         issue = None
-        if args.mb == 10 and clocks.get("sm_max_mhz"):
+        ncu = ncu_summary() if args.mb == 10 else None          # the committed --set full capture is of the 10 Mb launch
+        if ncu and ncu.get("warp_instructions") and clocks.get("sm_max_mhz"):
             sm_count = torch.cuda.get_device_properties(local).multi_processor_count
             issue_peak = sm_count * ISSUE_SLOTS_PER_SM_CYCLE * clocks["sm_max_mhz"] * 1e6
-            issue_rate = NCU_WARP_INSTRUCTIONS_PER_LAUNCH / (ms_kernel * 1e-3)
+            issue_rate = ncu["warp_instructions"] / (ms_kernel * 1e-3)
             issue = {"achieved": issue_rate, "peak": issue_peak, "unit": "warp instructions/s", "frac": issue_rate / issue_peak,
-                     "source": "profiles/r01c_scan_fast_ncu_full.csv (smsp__inst_executed.sum)"}
+                     "source": "%s (smsp__inst_executed.sum)" % ncu["file"]}
         if affinity is not None:
             os.sched_setaffinity(0, affinity)                    # the CPU baseline may use every core again
         cores = os.cpu_count() or 1
-        cpu_val, cpu_dt, cpu_win, _ = cpu_baseline(models, cores, 15.0)
+        cpu = cpu_baseline(models, cores, 15.0, n, counts[:4])
+        # the sample is a prefix of rank 0's chromosome with the same GC table: its counts and hits must be the GPU's
+        cw = cpu["windows"]
+        fh = full["hits"][full["hits"]["window"] < cw]
+        from rmdetect_b200.genome import hit_checksum
+        gpu_sample = {"tries": [cw * int(tries[0] // n_win), int(full["gate_pass"][:cw].sum())], "hits": int(len(fh)),
+                      "checksum": hit_checksum(0, fh["start"], fh["p0"], fh["p1"], fh["model"], fh["leaf"], fh["score"]) if len(fh) else 0}
+        if (cpu["tries"], cpu["hits"], cpu["checksum"]) != (gpu_sample["tries"], gpu_sample["hits"], gpu_sample["checksum"]):
+            raise SystemExit("bench.py: the GPU scan disagrees with the CPU oracle on the first %d windows: oracle %s, GPU %s"
+                             % (cw, {k: cpu[k] for k in ("tries", "hits", "checksum")}, gpu_sample))
+        cal_cpu = cal_cpu_baseline(models, cores, 6.0)
+        pyref = python_reference(cores)
         line = {
             "metric": "nt·models scanned/sec", "value": value, "unit": "nt·model/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config3: synthetic %d Mb random chromosome per GPU, win 150/75, models CL,TGA,GB,KT, "
-                                   "synthetic bpp (gate on)" % args.mb,
+            "config": {"workload": WORKLOAD % args.mb,
                        "windows_per_gpu": n_win, "bpp_entries_per_gpu": n_bpp, "placements_per_step": int(cnt[2]),
                        "gate_passes_per_step": int(cnt[3]), "hits_before_dedupe": int(cnt[1]), "hits": int(cnt[0]),
                        "l2": "inputs larger than L2 (%.0f MB of bpp lists per step)" % (n_bpp * 12 / 1e6),
@@ -293,23 +406,37 @@ def run_ours(args):
             "calibration": {"metric": "calibration samples scored/sec", "value": CAL_SAMPLES * len(models) * world / cal_wall,
                             "unit": "samples/s", "samples_per_model_per_gpu": CAL_SAMPLES, "classes": int(len(cl)),
                             "ms_total": 1e3 * cal_wall, "kernel_ms": cal_kernel_ms,
-                            "note": "rmd_calibrate_synth: device-drawn samples, 165 weighted scores each, histograms "
-                                    "downloaded per model; reference loop: ~3.5 k samples/s/core (SURVEY.md §6)"},
+                            "note": "rmd_calibrate_synth: one batch of device-drawn samples per model and GPU, 165 weighted "
+                                    "scores each, histograms downloaded per model",
+                            "reference_loop": {
+                                "value": cal_done / cal_loop_wall, "unit": "samples/s", "samples": int(cal_done),
+                                "blocks": int(cal_blocks), "ms_total": 1e3 * cal_loop_wall, "kernel_ms": cal_loop_kernel_ms,
+                                "reduced_table_sum": cal_sum,
+                                "note": "rmcalibrate.py:235-298 as calibrate_model runs it: blocks of 10 000 samples per GPU, "
+                                        "histograms all-reduced over the GPUs after every block, the reference's convergence "
+                                        "rule on the reduced table, min(samples, 4^L) samples per model"},
+                            "cpu_baseline": cal_cpu,
+                            "python_reference": pyref.get("calibrate_1core") if isinstance(pyref, dict) else None},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if args.mb == 10 else None,
-                         "traffic_source": "profiles/r01c_scan_fast_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, "
-                                           "ncu --set full of this command)",
+                         "traffic": ncu["dram_bytes"] if ncu else None,
+                         "traffic_source": "%s (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of this command)"
+                                           % (ncu["file"] if ncu else "none"),
                          "kernel": "scan_fast_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo),
                          "note": "table-lookup / fp64-compare work: issue-bound, not HBM-bound (see DESIGN.md); `issue` is the "
                                  "binding resource: warp instructions of the launch (ncu) / its live duration against "
                                  "148 SMs x 4 schedulers x the SM clock",
                          "issue": issue},
-            "cpu_baseline": {"value": cpu_val, "unit": "nt·model/s", "cores": cores, "kind": "port",
-                             "sample": "first %d windows (%d nt) of the same chromosome, oracle/rmd_oracle.c with "
-                                       "OpenMP on all cores, %.1f s" % (cpu_win, cpu_win * WIN_STEP, cpu_dt)},
+            "cpu_baseline": {"value": cpu["value"], "unit": "nt·model/s", "cores": cores, "kind": "port",
+                             "sample": "first %d windows (%d nt) of the same chromosome with its GC table, oracle/rmd_oracle.c with "
+                                       "OpenMP on all cores, %.1f s of scanning (stand-in bpp lists generated before, %.1f s); "
+                                       "tests_all, tests_pairs, hit count and hit checksum of these windows equal the GPU's"
+                                       % (cw, cw * WIN_STEP, cpu["s_scan"], cpu["s_generate"]),
+                             "covers_whole_chromosome": bool(cpu["whole"]), "tries": cpu["tries"],
+                             "hits_before_dedupe": cpu["hits"], "hit_checksum": "%016x" % cpu["checksum"],
+                             "python_reference": {k: v for k, v in pyref.items() if k != "calibrate_1core"} if isinstance(pyref, dict) else pyref},
         }
         print(json.dumps(line), flush=True)
     eng.close()

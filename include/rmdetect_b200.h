@@ -24,6 +24,7 @@
  *   rmd_set_min_score   rmdetect.py:44 + lib/candidates.py:78-97 (score filter of the CLI, before the download)
  *   rmd_eval            lib/node.py:176-277 called directly (rmcalibrate.py:279-281 style)
  *   rmd_calibrate       rmcalibrate.py:35-62,265-295 (sample scoring into weighted histograms)
+ *   rmd_calib_*         the same as a session whose histograms stay on the device (rmcalibrate.py:235-298 loop)
  *   rmd_parse_dot_ps    lib/rnatools.py:176-205 (parse_bpprobs: dot.ps text -> base-pair probabilities)
  *   rmd_compact_bpp     no reference counterpart: lossless 6-byte transport form of a bpp entry
  *   rmd_synth_strand    lib/sequences.py:138-143 (reverse complement), applied to the synthetic stream
@@ -189,6 +190,19 @@ int rmd_calibrate(rmd_ctx *ctx, int model, const uint8_t *samples, int64_t n, in
 int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64_t first, int64_t n, int32_t L,
                         const double *class_log, int32_t n_class, double cutoff,
                         double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel);
+
+/* Calibration session: the weighted histograms [n_class][n_bins] stay on the device between batches (rmcalibrate.py's
+   loop adds 10^4 .. 10^6 samples between two looks at the table).  rmd_calib_open zeroes them; rmd_calib_add enqueues
+   one batch — samples[n][L] codes from the host, or, with samples == NULL, drawn on the device as rmd_calibrate_synth
+   does — and returns without waiting for it; rmd_calib_device_hist waits for the batches enqueued so far and hands out
+   the histogram's device address (n_class * n_bins doubles), so that the GPUs of one job can all-reduce it in place
+   (the one collective of the calibration path); rmd_calib_read downloads histogram (may be NULL),
+   the number of samples whose eval held, the overflow flag and the device time of the batches since the last read.
+   rmd_calibrate / rmd_calibrate_synth / rmd_eval end an open session. */
+int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *class_log, int32_t n_class, double cutoff, int32_t n_bins);
+int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n);
+int rmd_calib_device_hist(rmd_ctx *ctx, void **dptr, int64_t *n_doubles);
+int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t *overflow, float *ms_device);
 
 /* synthetic job generated on the device: one sequence of n letters (positions first..first+n-1 of
    the stream keyed by seq_seed), windows per win_len/win_step, stand-in bpp keyed by bpp_seed */

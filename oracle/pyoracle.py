@@ -94,6 +94,10 @@ def lib():
         L.orc_bench_scan.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_int, C.c_int,
                                      C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.POINTER(C.c_int64)]
+        L.orc_bench_scan2.restype = C.c_int64
+        L.orc_bench_scan2.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int64, C.c_int, C.c_int,
+                                      C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_void_p, C.c_double, C.c_double,
+                                      C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.orc_calibrate.restype = C.c_int64
         L.orc_calibrate.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
                                     C.c_double, C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -265,6 +269,23 @@ def bench_scan(models, seq, win_len, win_step, w0, w1, seed, nthreads, min_bpp_m
     nh = lib().orc_bench_scan(len(dumps), arr, b, len(b), win_len, win_step, w0, w1, seed, nthreads,
                               min_bpp_mean, unknown_prob, cutoff, tries)
     return nh, [tries[0], tries[1]]
+
+
+def bench_scan2(models, seq, win_len, win_step, w0, w1, seed, nthreads, min_bpp_mean, unknown_prob, cutoff, counts=None):
+    """Windows [w0, w1) of `seq` with the stand-in bpp twin on `nthreads` cores.  `counts` = (A, C, G, U) letter
+    counts of the whole sequence the sample was cut from (its GC table); returns dict(hits, tries, checksum,
+    s_generate, s_scan): bpp generation and scan are timed apart (omp_get_wtime inside the C driver)."""
+    dumps = [dump_model(m).encode() for m in models]
+    arr = (C.c_char_p * len(dumps))(*dumps)
+    tries = (C.c_int64 * 2)()
+    secs = (C.c_double * 2)()
+    chk = C.c_uint64(0)
+    cnt = None if counts is None else np.ascontiguousarray(counts, dtype=np.int64)
+    b = seq.encode("latin-1")
+    nh = lib().orc_bench_scan2(len(dumps), arr, b, len(b), win_len, win_step, w0, w1, seed, nthreads,
+                               None if cnt is None else cnt.ctypes.data, min_bpp_mean, unknown_prob, cutoff,
+                               tries, C.byref(chk), secs)
+    return dict(hits=nh, tries=[tries[0], tries[1]], checksum=chk.value, s_generate=secs[0], s_scan=secs[1])
 
 
 def calibrate(omodel, samples, classes, unknown_prob, cutoff, nbins=512, hist=None):

@@ -37,6 +37,7 @@
  */
 #define _GNU_SOURCE
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -794,6 +795,115 @@ int64_t orc_bench_scan(int nmodels, const char **model_dumps,
     }
     free(starts);
     tries[0] = t0; tries[1] = t1;
+    return nh;
+}
+
+
+/*
+ * The same driver with the two arms of bench.py made like for like: the stand-in bpp lists of a block of windows
+ * are generated first (their time goes to secs[0], as ViennaRNA's would), the scan of the block is timed apart
+ * (secs[1]).  The GC table is the caller's (letter counts of the WHOLE chromosome, lib/scanner.py:74-75), so a
+ * prefix sample scores exactly as the full scan does.  checksum: order-independent sum over the hits before
+ * duplicate removal — the formula of rmdetect_b200/genome.py hit_checksum (absolute chain positions, model, gap
+ * configuration, score bits).
+ */
+int64_t orc_bench_scan2(int nmodels, const char **model_dumps,
+                        const char *seq, int64_t seqlen, int win_len, int win_step,
+                        int64_t w0, int64_t w1, uint64_t seed, int nthreads, const int64_t counts[4],
+                        double min_bpp_mean, double unknown_prob, double cutoff,
+                        int64_t tries[2], uint64_t *checksum, double secs[2]) {
+    gcdict gc;
+    if (counts) {                                  /* GC.compute on the whole sequence the sample was cut from */
+        memset(&gc, 0, sizeof gc);
+        double total = (double)(counts[0] + counts[1] + counts[2] + counts[3]);
+        for (int k = 0; k < 4; k++)
+            if (counts[k]) { gc.has[(unsigned char)LETTERS[k]] = 1; gc.v[(unsigned char)LETTERS[k]] = log((double)counts[k] / total); }
+    } else orc_gc_compute(seq, seqlen, &gc);
+    int64_t nwin = orc_windows(seqlen, win_len, win_step, NULL, 0);
+    int64_t *starts = malloc(sizeof(int64_t) * nwin);
+    orc_windows(seqlen, win_len, win_step, starts, nwin);
+    if (w1 > nwin) w1 = nwin;
+    const int64_t BLOCK = 8192;
+    const int64_t cap = (int64_t)win_len * win_len / 2 + 16;
+    int64_t *boff = malloc(sizeof(int64_t) * (BLOCK + 1));
+    uint16_t *bi = NULL, *bj = NULL; double *bp = NULL; int64_t bcap = 0;
+    int64_t *cnt = malloc(sizeof(int64_t) * BLOCK);
+    int64_t t0 = 0, t1 = 0, nh = 0; uint64_t sum = 0;
+    secs[0] = secs[1] = 0.0;
+    /* every thread builds its own models: the search tree holds evaluation state */
+    void ***ms = malloc(sizeof(void **) * nthreads);
+    double **mats = malloc(sizeof(double *) * nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        ms[t] = malloc(sizeof(void *) * nmodels);
+        for (int i = 0; i < nmodels; i++) ms[t][i] = orc_model_load(model_dumps[i]);
+        mats[t] = malloc(sizeof(double) * (size_t)win_len * win_len);
+    }
+    for (int64_t b0 = w0; b0 < w1; b0 += BLOCK) {
+        const int64_t b1 = b0 + BLOCK < w1 ? b0 + BLOCK : w1, nb = b1 - b0;
+        double ta = omp_get_wtime();
+        /* pass 1: sizes; pass 2: lists (the generator is deterministic) */
+#pragma omp parallel num_threads(nthreads)
+        {
+            uint16_t *ti = malloc(sizeof(uint16_t) * cap), *tj = malloc(sizeof(uint16_t) * cap);
+            double *tp = malloc(sizeof(double) * cap);
+#pragma omp for schedule(dynamic, 16)
+            for (int64_t k = 0; k < nb; k++) {
+                int64_t s = starts[b0 + k];
+                int wl = (int)((s + win_len <= seqlen ? s + win_len : seqlen) - s);
+                cnt[k] = orc_synth_bpp(seq + s, wl, seed, ti, tj, tp, cap);
+            }
+            free(ti); free(tj); free(tp);
+        }
+        boff[0] = 0;
+        for (int64_t k = 0; k < nb; k++) boff[k + 1] = boff[k] + cnt[k];
+        if (boff[nb] > bcap) {
+            bcap = boff[nb] + boff[nb] / 8 + 1024;
+            free(bi); free(bj); free(bp);
+            bi = malloc(sizeof(uint16_t) * bcap); bj = malloc(sizeof(uint16_t) * bcap); bp = malloc(sizeof(double) * bcap);
+        }
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 16)
+        for (int64_t k = 0; k < nb; k++) {
+            int64_t s = starts[b0 + k];
+            int wl = (int)((s + win_len <= seqlen ? s + win_len : seqlen) - s);
+            orc_synth_bpp(seq + s, wl, seed, bi + boff[k], bj + boff[k], bp + boff[k], cnt[k]);
+        }
+        double tb = omp_get_wtime();
+#pragma omp parallel num_threads(nthreads) reduction(+ : t0, t1, nh, sum)
+        {
+            const int me = omp_get_thread_num();
+#pragma omp for schedule(dynamic, 4)
+            for (int64_t k = 0; k < nb; k++) {
+                int64_t s = starts[b0 + k];
+                int wl = (int)((s + win_len <= seqlen ? s + win_len : seqlen) - s);
+                hitvec hv = {0};
+                int64_t t[2] = {0, 0};
+                int fault = 0;
+                search_window(ms[me], NULL, nmodels, 0, seq + s, wl, s, &gc, bi + boff[k], bj + boff[k], bp + boff[k], cnt[k],
+                              min_bpp_mean, unknown_prob, cutoff, &hv, t, &fault, mats[me]);
+                t0 += t[0]; t1 += t[1]; nh += hv.n;
+                for (int64_t q = 0; q < hv.n; q++) {
+                    const orc_hit *h = &hv.v[q];
+                    uint64_t key = (uint64_t)(h->coord0 + h->p[0]) * 0x9E3779B97F4A7C15ULL;
+                    key ^= (uint64_t)(h->coord0 + h->p[1]) * 0xC2B2AE3D27D4EB4FULL;
+                    key ^= ((uint64_t)h->model << 40) ^ ((uint64_t)h->cfg << 48);
+                    key = (key ^ (key >> 29)) * 0xBF58476D1CE4E5B9ULL;
+                    uint64_t bits;
+                    memcpy(&bits, &h->score, sizeof bits);
+                    sum += key + bits;
+                }
+                free(hv.v);
+            }
+        }
+        double tc = omp_get_wtime();
+        secs[0] += tb - ta; secs[1] += tc - tb;
+    }
+    for (int t = 0; t < nthreads; t++) {
+        for (int i = 0; i < nmodels; i++) orc_model_free(ms[t][i]);
+        free(ms[t]); free(mats[t]);
+    }
+    free(ms); free(mats); free(starts); free(boff); free(cnt); free(bi); free(bj); free(bp);
+    tries[0] = t0; tries[1] = t1;
+    if (checksum) *checksum = sum;
     return nh;
 }
 

@@ -56,7 +56,7 @@ assert HIT_DTYPE.itemsize == 72
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
            "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
-           "rmd_calibrate", "rmd_calibrate_synth", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
+           "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
 
 _lib = None
@@ -93,6 +93,10 @@ def load_library():
                                 C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
     L.rmd_calibrate_synth.argtypes = [vp, C.c_int, C.c_uint64, i64, i64, i32, vp, i32, f64, vp, i32,
                                       C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.rmd_calib_open.argtypes = [vp, C.c_int, i32, vp, i32, f64, i32]
+    L.rmd_calib_add.argtypes = [vp, vp, C.c_uint64, i64, i64]
+    L.rmd_calib_device_hist.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.rmd_calib_read.argtypes = [vp, vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
     L.rmd_synth_job.argtypes = [vp, i64, i64, C.c_uint64, C.c_uint64, i32, i32, f64, f64, vp, vp,
                                 C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
     L.rmd_synth_strand.argtypes = [vp, i64, i32]
@@ -273,6 +277,33 @@ class Context:
             raise NativeError("calibration score beyond the histogram range (%d bins)" % hist.shape[1])
         return n_ok.value, ms.value
 
+    # calibration session: histograms resident on the device (include/rmdetect_b200.h: rmd_calib_*)
+    def calib_open(self, model, L, class_log, cutoff, n_bins):
+        class_log = np.ascontiguousarray(class_log, dtype=np.float64)
+        self._check(self.lib.rmd_calib_open(self.h, model, L, class_log.ctypes.data, class_log.shape[0], cutoff, n_bins),
+                    "rmd_calib_open")
+        self._cal_shape = (class_log.shape[0], n_bins)
+
+    def calib_add(self, samples=None, seed=0, first=0, n=0):
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, dtype=np.uint8)
+            n = samples.shape[0]
+        self._check(self.lib.rmd_calib_add(self.h, _ptr(samples), seed, first, n), "rmd_calib_add")
+
+    def calib_device_hist(self):
+        """(device address, element count) of the session's fp64 histogram, after the enqueued batches have finished."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        self._check(self.lib.rmd_calib_device_hist(self.h, C.byref(p), C.byref(n)), "rmd_calib_device_hist")
+        return p.value, n.value
+
+    def calib_read(self, want_hist=True):
+        hist = np.zeros(self._cal_shape, dtype=np.float64) if want_hist else None
+        n_ok, ovf, ms = C.c_int64(0), C.c_int32(0), C.c_float(0)
+        self._check(self.lib.rmd_calib_read(self.h, _ptr(hist), C.byref(n_ok), C.byref(ovf), C.byref(ms)), "rmd_calib_read")
+        if ovf.value:
+            raise NativeError("calibration score beyond the histogram range (%d bins)" % self._cal_shape[1])
+        return hist, n_ok.value, ms.value
+
     def synth_job(self, n, first, seq_seed, bpp_seed, win_len, win_step, min_bpp_mean, cutoff, gc_log, gc_class=None):
         gc_log = np.ascontiguousarray(gc_log, dtype=np.float64).reshape(1, N_CODES)
         gcc = None if gc_class is None else np.ascontiguousarray(gc_class, dtype=np.int32)
@@ -285,6 +316,11 @@ class Context:
     def set_screen_policy(self, min_windows):
         """Sequences with at least `min_windows` windows get prefix-screen tables (no effect on results); < 0: none."""
         self._check(self.lib.rmd_set_screen_policy(self.h, int(min_windows)), "rmd_set_screen_policy")
+
+    def set_return_dropped(self, enable):
+        """Scans also return the hits the duplicate rule removed (keep = 0), in place, as the reference's per-window
+        callbacks see them (lib/scanner.py:99-109 runs before :53)."""
+        self._check(self.lib.rmd_set_return_dropped(self.h, 1 if enable else 0), "rmd_set_return_dropped")
 
     def set_min_score(self, min_score):
         """Drop hits with score <= min_score on the device (reference rmdetect.py:44); None switches the filter off."""

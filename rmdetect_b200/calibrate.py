@@ -7,6 +7,11 @@ sample checkpoints and stop rule (:237-257) and the `.evalues` text layout
 (`save_data`, :101-131).  The per-sample work — evaluating the model on the
 spliced sequence and adding 165 weighted scores to histograms (:265-295) — is
 `rmd_calibrate` / `rmd_calibrate_synth` (csrc/calib_kernels.cuh).
+
+Several GPUs (BASELINE.json configs[3]): samples are independent, so the ranks of a
+`torch.distributed` group score disjoint slices of every checkpoint block and all-reduce (sum) the block's
+165 x N_BINS fp64 histogram; the reference's table construction and stop rule then run on the reduced
+histogram, identically on every rank.  A checkpoint block is N_SAVE samples per rank.
 """
 from __future__ import annotations
 
@@ -89,6 +94,60 @@ def diff_gc_evalues(gce1, gce2, scores):
     return diff / atotal
 
 
+def score_grid(hist):
+    """The score rows `get_gc_evalues` walks (rmcalibrate.py:65-83) for a dense [class][bucket] histogram: from the
+    smallest to the largest occupied bucket in repeated `+= 0.1` steps, each rounded for use as a key — the float
+    accumulation (and with it a possibly missing last row) is the reference's."""
+    cols = np.flatnonzero(hist.any(axis=0))
+    if len(cols) == 0:
+        return []
+    score, score_max, scores = round(int(cols[0]) / 10.0, 1), round(int(cols[-1]) / 10.0, 1), []
+    while score <= score_max:
+        scores.append(round(score, 1))
+        score += 0.1
+    return scores
+
+
+def gc_evalues_dense(hist, evalue_min, classes=None):
+    """`gc_evalues` on the dense histogram: (table [class][row], scores); `classes` restricts the table to those rows
+    of the histogram (the score grid still spans all of them).  Same additions in the same order (a
+    sequential cumulative sum from the highest score down, floored at `evalue_min`; after the first row the floor
+    never binds because every term is >= 0), so the values equal the dict version's bit for bit."""
+    scores = score_grid(hist)
+    idx = np.array([int(round(s * 10)) for s in scores], dtype=np.int64)
+    sub = hist if classes is None else hist[list(classes)]
+    count = np.array([float(sum(row[np.flatnonzero(row)].tolist())) for row in sub])      # Python's own sum(), like :85
+    p = sub[:, idx[::-1]] / count[:, None]
+    p[:, 0] = np.maximum(p[:, 0], evalue_min)
+    tab = np.maximum(np.cumsum(p, axis=1), evalue_min)[:, ::-1]
+    return tab, scores
+
+
+def diff_dense(tab1, scores1, tab2, scores2, gc=None):
+    """`diff_gc_evalues` (rmcalibrate.py:134-157) for two dense tables: the middle class (row `gc` of the tables,
+    default their middle row), rows of the NEWER grid `scores2`, a row pair skipped when the older table lacks one of
+    the scores."""
+    gc = tab1.shape[0] // 2 if gc is None else gc
+    at1 = {s: k for k, s in enumerate(scores1)}
+    diff = atotal = 0.0
+    for i in range(1, len(scores2)):
+        a, b = scores2[i - 1], scores2[i]
+        if a in at1 and b in at1:
+            ya1, yb1 = float(tab1[gc, at1[a]]), float(tab1[gc, at1[b]])
+            ya2, yb2 = float(tab2[gc, i - 1]), float(tab2[gc, i])
+            x = b - a
+            a1 = x * (yb1 + abs(yb1 - ya1) / 2.0)
+            a2 = x * (yb2 + abs(yb2 - ya2) / 2.0)
+            diff += abs(a1 - a2)
+            atotal += a1
+    return diff / atotal
+
+
+def table_text_dense(gc_classes, tab, scores):
+    """`table_text` for a dense table."""
+    return table_text(gc_classes, [dict(zip(scores, row.tolist())) for row in tab], scores)
+
+
 def table_text(gc_classes, gc_evalue, scores):
     """The `.evalues` file body (rmcalibrate.py:101-131)."""
     lines = ["[GC_CLASSES]\n"]
@@ -103,8 +162,16 @@ def table_text(gc_classes, gc_evalue, scores):
     return "".join(lines)
 
 
+class _DeviceArray:
+    """A device allocation owned by the library, presented through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=2)
+
+
 class Calibrator:
-    """One model resident on one GPU, scoring calibration samples."""
+    """One model resident on one GPU, scoring calibration samples into histograms that stay on the device
+    (a calibration session of the C ABI: rmd_calib_open / _add / _device_hist / _read)."""
 
     def __init__(self, model, unknown_prob, cutoff, device=0, ctx=None, model_index=0):
         self.model = model
@@ -112,6 +179,7 @@ class Calibrator:
         self.cutoff = cutoff
         self.classes = GC.get_classes(resolution=5, min_p=15, max_p=85)     # rmcalibrate.py:224
         self.class_log = class_logs(self.classes)
+        self._own = ctx is None
         if ctx is None:
             ctx = _native.Context(device)
             ctx.set_models([flatten_model(model, unknown_prob)])
@@ -119,63 +187,130 @@ class Calibrator:
         self.ctx, self.model_index = ctx, model_index
         self.hist = np.zeros((len(self.classes), N_BINS), dtype=np.float64)
         self.ms_kernel = 0.0
+        self.n_ok = 0
+        self.ctx.calib_open(self.model_index, self.L, self.class_log, self.cutoff, N_BINS)
 
     def add_samples(self, samples):
-        n_ok, ms = self.ctx.calibrate(self.model_index, samples, self.class_log, self.cutoff, self.hist)
-        self.ms_kernel += ms
-        return n_ok
+        self.ctx.calib_add(samples=samples)
 
     def add_synthetic(self, seed, first, n):
-        n_ok, ms = self.ctx.calibrate(self.model_index, None, self.class_log, self.cutoff, self.hist,
-                                      seed=seed, first=first, n=n, L=self.L)
-        self.ms_kernel += ms
-        return n_ok
+        self.ctx.calib_add(None, seed, first, n)
+
+    def reduced_hist(self, dist=None):
+        """The histogram of everything added so far, summed over the ranks of `dist`.  With NCCL the all-reduce runs
+        on the device, on a copy of the session's histogram (the session keeps accumulating this rank's share)."""
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl":
+            import torch
+            ptr, n = self.ctx.calib_device_hist()                  # waits for the enqueued batches
+            t = torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", self.ctx.device)).clone()
+            dist.all_reduce(t)
+            self.hist = t.cpu().numpy().reshape(self.hist.shape)
+        else:
+            local, self.n_ok, ms = self.ctx.calib_read()
+            self.ms_kernel += ms
+            self.hist = all_reduce_hist(local, dist)
+        return self.hist
 
     def table(self):
-        return gc_evalues(hist_dicts(self.hist), 1.0 / float(4 ** self.L))
+        return gc_evalues(hist_dicts(self.reduced_hist()), 1.0 / float(4 ** self.L))
+
+    def close(self):
+        _, self.n_ok, ms = self.ctx.calib_read(want_hist=False)    # this rank's counters and device time
+        self.ms_kernel += ms
+        if self._own:
+            self.ctx.close()
+
+
+def all_reduce_hist(block, dist):
+    """Sum a [class][bucket] fp64 histogram over the ranks (gloo in the CPU tests; a host-side fallback for NCCL):
+    the one collective of the calibration path, 165 x N_BINS doubles per checkpoint block."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return block
+    import torch
+    nccl = dist.get_backend() == "nccl"
+    t = torch.from_numpy(np.array(block, dtype=np.float64, copy=True))
+    if nccl:
+        t = t.cuda()
+    dist.all_reduce(t)
+    return t.cpu().numpy() if nccl else t.numpy()
 
 
 def calibrate_model(model, out_file, samples=1000000, unknown_prob=math.log(0.0001), cutoff=math.log(0.1),
-                    seed=None, device=0, device_samples=False, log=sys.stderr):
-    """The main loop of rmcalibrate.py:235-298 for one model; returns (gc_evalue, scores, n_done)."""
-    cal = Calibrator(model, unknown_prob, cutoff, device)
+                    seed=None, device=0, device_samples=False, log=sys.stderr, dist=None, scorer=None,
+                    save_every_block=True, stats=None):
+    """The main loop of rmcalibrate.py:235-298 for one model; returns (table [class][row], scores, samples done).
+
+    One rank: exactly the reference's schedule — a checkpoint (table, file, convergence test) every N_SAVE samples.
+    `dist` (an initialised torch.distributed): a checkpoint block is N_SAVE samples PER RANK; rank r scores the r-th
+    slice of the block, the histograms are all-reduced, and every rank runs the stop rule on the same reduced
+    table (rank 0 writes the file).  Host-drawn samples (`device_samples=False`, the reference's `random.randint`
+    stream, seeded alike on every rank) are drawn in full by every rank so that the union of the slices is the
+    single-rank stream; `device_samples=True` draws on the GPU, sample index = position in the global stream.
+    `scorer` replaces the GPU `Calibrator` (tests: a CPU stand-in with add_samples / add_synthetic / reduced_hist).
+    `save_every_block=False` (throughput runs): a checkpoint tabulates only the class the stop rule reads (the middle
+    one) and the file is written once, at the end.  `stats` (a dict) receives blocks, kernel ms and the final
+    histogram."""
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    cal = scorer if scorer is not None else Calibrator(model, unknown_prob, cutoff, device)
     total = min(samples, 4 ** cal.L)
     if seed is not None:
         random.seed(seed)
-    last, stable, done = None, 0, 0
+    evalue_min = 1.0 / float(4 ** cal.L)
+    mid = len(cal.classes) // 2
+    block = N_SAVE * world
+    last, stable, done, blocks = None, 0, 0, 0
+    hist = None
     t0 = time.time()
+
+    def save(tab, scores):
+        if out_file and rank == 0:
+            with open(out_file, "w") as fh:
+                fh.write(table_text_dense(cal.classes, tab, scores))
+
     while done < total:
-        # every N_SAVE samples the reference recomputes the table, saves it and tests convergence
+        # every block the reference recomputes the table, saves it and tests convergence (:237-263)
         if done > 0:
-            gce, scores = cal.table()
-            if out_file:
-                with open(out_file, "w") as fh:
-                    fh.write(table_text(cal.classes, gce, scores))
+            hist = cal.reduced_hist(dist)
+            if save_every_block:
+                tab, scores = gc_evalues_dense(hist, evalue_min)
+                save(tab, scores)
+                tab_mid = tab[mid:mid + 1]
+            else:
+                tab_mid, scores = gc_evalues_dense(hist, evalue_min, classes=[mid])
             diff = 0.0
             if last is not None:
-                diff = diff_gc_evalues(last, gce, scores)
+                diff = diff_dense(last[0], last[1], tab_mid, scores, gc=0)
                 if diff < CONVERGED_DIFF:
-                    stable += N_SAVE
+                    stable += block
                     if stable > CONVERGED_SAMPLES:
-                        print("\nConverged after %d simulations" % done)
+                        if rank == 0 and log is not None:
+                            print("\nConverged after %d simulations" % done)
                         break
                 else:
                     stable = 0
-            if log is not None:
+            if log is not None and rank == 0:
                 el = time.time() - t0
                 log.write("%sdata saved after %d simulations, TTF: %ds, diff: %5.4f (%d)"
-                          % ("\b" * 100, done, (el * total / done) - el, diff, stable))
+                          % ("\b" * 100, done, (el * samples / done) - el, diff, stable))
                 log.flush()
-            last = gce
-        step = min(N_SAVE, total - done)
+            last = (tab_mid, scores)
+        step = min(block, total - done)
+        lo, hi = step * rank // world, step * (rank + 1) // world
         if device_samples:
-            cal.add_synthetic(seed or 0, done, step)
+            if hi > lo:
+                cal.add_synthetic(seed or 0, done + lo, hi - lo)
         else:
-            cal.add_samples(draw_samples(step, cal.L))
+            drawn = draw_samples(step, cal.L)     # every rank consumes the whole block of the stream
+            if hi > lo:
+                cal.add_samples(drawn[lo:hi])
         done += step
-    gce, scores = cal.table()
-    if out_file:
-        with open(out_file, "w") as fh:
-            fh.write(table_text(cal.classes, gce, scores))
-    cal.ctx.close()
-    return gce, scores, done
+        blocks += 1
+    hist = cal.reduced_hist(dist)
+    tab, scores = gc_evalues_dense(hist, evalue_min)
+    save(tab, scores)
+    if scorer is None or isinstance(cal, Calibrator):
+        cal.close()
+    if stats is not None:
+        stats.update(blocks=blocks, hist=hist, ms_kernel=getattr(cal, "ms_kernel", 0.0), n_ok=getattr(cal, "n_ok", None))
+    return tab, scores, done

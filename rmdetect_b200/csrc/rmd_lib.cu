@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,6 +20,33 @@
 #include "synth_kernels.cuh"
 
 static thread_local std::string g_error;
+
+// The model tables live in __constant__ memory, which is per device, not per context.  Every context keeps host
+// copies (rmd_ctx::sym) and `bind_tables` re-uploads them when another context (or a newer generation of this
+// one) owns the device's symbols; calls on contexts of one device are serialised by the device's mutex.
+#define RMD_MAX_DEVICES 64
+static std::recursive_mutex g_dev_mutex[RMD_MAX_DEVICES];
+static rmd_ctx *g_sym_owner[RMD_MAX_DEVICES];
+static unsigned long long g_sym_gen[RMD_MAX_DEVICES];
+static unsigned long long g_next_gen = 1;
+
+// Tuning experiments (team count, CTAs per SM, kernel variants) are compiled in only with -DRMD_TUNING: the
+// release library reads no environment variable, so a process that inherits RMD_* cannot change what runs.
+#ifdef RMD_TUNING
+static const char *tune_env(const char *name) { return getenv(name); }
+#else
+static const char *tune_env(const char *) { return nullptr; }
+#endif
+
+struct SymbolTables {              // host copies of the __constant__ tables other than c_models (rmd_ctx::hmodels)
+    TrieNode trie[TRIE_CAP];
+    uint16_t prel[32];
+    int n_prel;
+    unsigned char groups[RMD_MAX_MODELS + 1];
+    int n_groups;
+    ScreenBuild build[SCREEN_CAP];
+    ScreenDesc desc[SCREEN_CAP];
+};
 
 struct DBuf {                      // grow-only device buffer
     void *p = nullptr;
@@ -34,6 +63,8 @@ struct rmd_ctx {
     // models
     int n_models = 0;
     std::vector<CModel> hmodels;
+    SymbolTables sym{};
+    unsigned long long sym_gen = 0;     // bumped whenever hmodels / sym change; compared with the device's g_sym_gen
     std::vector<void *> model_allocs;
     std::vector<void *> ev_allocs[RMD_MAX_MODELS];
     int max_chain = 0;
@@ -75,6 +106,9 @@ struct rmd_ctx {
     double min_score = 0.0;
     // eval / calibrate scratch
     DBuf d_e0, d_e1, d_e2, d_e3, d_e4, d_e5, d_e6, d_e7;
+    // calibration session (rmd_calib_open .. rmd_calib_read): histogram in d_e3, counters in d_e4
+    CalibArgs cal{};
+    bool cal_open = false, cal_timed = false;
 };
 
 static int fail(rmd_ctx *ctx, int code, const char *fmt, ...) {
@@ -119,7 +153,7 @@ extern "C" int rmd_create(int device, rmd_ctx **out) {
     if (e != cudaSuccess || count == 0)
         return fail(nullptr, RMD_E_CUDA, "no CUDA device (%s); this library has no CPU path",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-    if (device < 0 || device >= count) return fail(nullptr, RMD_E_INVALID, "device %d out of range (%d present)", device, count);
+    if (device < 0 || device >= count || device >= RMD_MAX_DEVICES) return fail(nullptr, RMD_E_INVALID, "device %d out of range (%d present)", device, count);
     ctx = new rmd_ctx();
     ctx->device = device;
     CK(cudaSetDevice(device));
@@ -141,8 +175,10 @@ static void free_models(rmd_ctx *ctx) {
 
 extern "C" void rmd_destroy(rmd_ctx *ctx) {
     if (!ctx) return;
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (g_sym_owner[ctx->device] == ctx) g_sym_owner[ctx->device] = nullptr;   // its table pointers die with it
     free_models(ctx);
     DBuf *bufs[] = {&ctx->d_seq_off, &ctx->d_win_base, &ctx->d_codes8, &ctx->d_codes2, &ctx->d_gc_log, &ctx->d_gc_class,
                     &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt, &ctx->d_bpp_ij, &ctx->d_bpp_q,
@@ -180,37 +216,48 @@ static int to_device(rmd_ctx *ctx, const T *src, size_t n, T **dst, std::vector<
 extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_models) {
     if (!ctx || !models || n_models < 1) return fail(ctx, RMD_E_INVALID, "rmd_set_models: bad arguments");
     if (n_models > RMD_MAX_MODELS) return fail(ctx, RMD_E_LIMIT, "at most %d models per context", RMD_MAX_MODELS);
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
-    CK(cudaDeviceSynchronize());
-    free_models(ctx);
-    ctx->hmodels.assign(n_models, CModel{});
-    ctx->max_chain = 0;
-    ctx->any_brute = false;
+    // Everything is validated and staged into temporaries first: a descriptor that is refused leaves the context
+    // (its models, its resident job) exactly as it was.
+    struct Pending { std::vector<void *> allocs; bool committed = false; ~Pending() { if (!committed) for (void *p : allocs) cudaFree(p); } } pending;
+    std::vector<CModel> hmodels((size_t)n_models, CModel{});
+    std::unique_ptr<SymbolTables> symp(new SymbolTables());
+    SymbolTables &sym = *symp;
+    memset(&sym, 0, sizeof sym);
+    int max_chain = 0;
     int trie_total = 0;
-    TrieNode htrie[TRIE_CAP];
-    memset(htrie, 0, sizeof htrie);
+    TrieNode *const htrie = sym.trie;
     std::vector<XNode> hx;
     bool motif_ok = true;
-    uint16_t hprel[32] = {0};
+    uint16_t *const hprel = sym.prel;
     int n_prel = 0;
     bool prel_overflow = false;
     int stack_slots = 1;
     int n_screens = 0;
     long long screen_words = 0;
     unsigned char screen0[RMD_MAX_MODELS + 1] = {0};
-    static ScreenBuild hbuild[SCREEN_CAP];
-    static ScreenDesc hdesc[SCREEN_CAP];
+    ScreenBuild *const hbuild = sym.build;
+    ScreenDesc *const hdesc = sym.desc;
     std::vector<double> hcpt;
     for (int m = 0; m < n_models; m++) {
         const rmd_model_desc &d = models[m];
-        CModel &c = ctx->hmodels[m];
+        CModel &c = hmodels[m];
         if (d.n_gate_pairs > RMD_MAX_GATE_PAIRS || d.n_gate_cfg > RMD_MAX_GATE_CFGS || d.n_first > RMD_MAX_FIRST_PAIRS)
             return fail(ctx, RMD_E_LIMIT, "model %d: gate program too large (%d pairs, %d configurations, %d first pairs)",
                         m, d.n_gate_pairs, d.n_gate_cfg, d.n_first);
         if (d.n_tree < 1 || d.n_tree > 65535 || d.chain_len[0] < 1 || d.chain_len[1] < 1 || d.chain_len[0] > 100 || d.chain_len[1] > 100)
             return fail(ctx, RMD_E_LIMIT, "model %d: tree size %d / chain lengths %d,%d out of range", m, d.n_tree, d.chain_len[0], d.chain_len[1]);
+        if (!d.tree || !d.leaf_dist || !d.cpt || !d.gate_cfg || (d.n_gate_pairs > 0 && !d.gate_pairs) || !d.leaf_offsets)
+            return fail(ctx, RMD_E_INVALID, "model %d: NULL table", m);
+        if (d.n_gate_cfg < 0 || d.n_gate_pairs < 0 || d.n_leaves < 1 || d.n_cpt_rows < 1)
+            return fail(ctx, RMD_E_INVALID, "model %d: negative or empty table size", m);
+        if (d.gate_cfg[0] != 0 || d.gate_cfg[d.n_gate_cfg] != d.n_gate_pairs)
+            return fail(ctx, RMD_E_INVALID, "model %d: gate_cfg does not span the %d gate pairs", m, d.n_gate_pairs);
+        for (int k = 0; k < d.n_gate_cfg; k++)
+            if (d.gate_cfg[k + 1] < d.gate_cfg[k]) return fail(ctx, RMD_E_INVALID, "model %d: gate_cfg is not monotone", m);
         c.chain_len[0] = d.chain_len[0]; c.chain_len[1] = d.chain_len[1];
-        ctx->max_chain = std::max(ctx->max_chain, std::max(d.chain_len[0], d.chain_len[1]));
+        max_chain = std::max(max_chain, std::max(d.chain_len[0], d.chain_len[1]));
         c.symmetric = d.symmetric; c.n_tree = d.n_tree; c.n_cfg = d.n_gate_cfg;
         c.brute = d.brute_candidates; c.n_leaves = d.n_leaves;
         for (int k = 0; k <= d.n_gate_cfg; k++) c.cfg_begin[k] = (unsigned short)d.gate_cfg[k];
@@ -281,7 +328,9 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         int r;
         rmd_tree_node *tree = nullptr; int32_t *ld = nullptr; double *cpt = nullptr; int8_t *lo = nullptr;
         for (int t = 0; t < d.n_tree; t++)
-            if (d.tree[t].npar > 2 || d.tree[t].bdepth > RMD_MAX_BRANCH_DEPTH || d.tree[t].leaf >= d.n_leaves)
+            if (d.tree[t].npar > 2 || d.tree[t].bdepth > RMD_MAX_BRANCH_DEPTH || d.tree[t].leaf >= d.n_leaves ||
+                (int)d.tree[t].cpt_row + (d.tree[t].npar == 2 ? RMD_NSYM * RMD_NSYM : d.tree[t].npar == 1 ? RMD_NSYM : 1) > d.n_cpt_rows ||
+                (d.tree[t].chain & ~1) || d.tree[t].oft >= d.chain_len[d.tree[t].chain & 1])
                 return fail(ctx, RMD_E_LIMIT, "model %d: tree node %d out of range", m, t);
         // level of every tree node (depth along ORDER), kept in the node's spare byte for the screen tabulation
         std::vector<rmd_tree_node> ltree(d.tree, d.tree + d.n_tree);
@@ -296,9 +345,9 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
                 ltree[t].pad_ = (uint8_t)std::min(level[t], 255);
             }
         }
-        if ((r = to_device(ctx, ltree.data(), (size_t)d.n_tree, &tree, ctx->model_allocs))) return r;
+        if ((r = to_device(ctx, ltree.data(), (size_t)d.n_tree, &tree, pending.allocs))) return r;
         screen0[m] = (unsigned char)n_screens;
-        if (motif_ok && !getenv("RMD_NO_SCREEN")) {
+        if (motif_ok && !tune_env("RMD_NO_SCREEN")) {
             // one screen per top-level subtree, all of the same depth: the deepest level whose letters fit
             // SCREEN_MAX_LETTERS (small trees: 6, their tables stay in L1) in at most SCREEN_MAX_RUNS runs of
             // neighbouring offsets
@@ -345,9 +394,9 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
                 }
             }
         }
-        if ((r = to_device(ctx, d.leaf_dist, (size_t)d.n_leaves * 2, &ld, ctx->model_allocs))) return r;
-        if ((r = to_device(ctx, d.cpt, (size_t)d.n_cpt_rows * RMD_NSYM, &cpt, ctx->model_allocs))) return r;
-        if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, ctx->model_allocs))) return r;
+        if ((r = to_device(ctx, d.leaf_dist, (size_t)d.n_leaves * 2, &ld, pending.allocs))) return r;
+        if ((r = to_device(ctx, d.cpt, (size_t)d.n_cpt_rows * RMD_NSYM, &cpt, pending.allocs))) return r;
+        if ((r = to_device(ctx, d.leaf_offsets, (size_t)d.n_leaves * (d.chain_len[0] + d.chain_len[1]), &lo, pending.allocs))) return r;
         {   // the scoring engine's view: pre-decoded nodes, absolute indices, all models concatenated
             const size_t x0 = hx.size(), cpt0 = hcpt.size();
             if (x0 + (size_t)d.n_tree >= XNODE_END) return fail(ctx, RMD_E_LIMIT, "search trees of the model set exceed %u nodes", XNODE_END - 1);
@@ -407,46 +456,37 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         unsigned char groups[RMD_MAX_MODELS + 1] = {0};
         int n_groups = 0, used = 0;
         for (int m = 0; m < n_models; m++) {
-            CModel &c = ctx->hmodels[m];
+            CModel &c = hmodels[m];
             const bool bitmap = c.n_trie > 2;
             if (bitmap && used == CB_SLOTS) { groups[++n_groups] = (unsigned char)m; used = 0; }
             c.cb_slot = bitmap ? used++ : -1;
         }
         groups[++n_groups] = (unsigned char)n_models;
-        CK(cudaMemcpyToSymbol(c_groups, groups, sizeof groups));
-        CK(cudaMemcpyToSymbol(c_n_groups, &n_groups, sizeof n_groups));
+        memcpy(sym.groups, groups, sizeof groups);
+        sym.n_groups = n_groups;
     }
-    for (const CModel &c : ctx->hmodels) if (c.brute) ctx->any_brute = true;
-    if (prel_overflow) ctx->any_brute = true;     // too many distinct pair geometries for the candidate filter: exact path
-    CK(cudaMemcpyToSymbol(c_prel, hprel, sizeof hprel));
-    CK(cudaMemcpyToSymbol(c_n_prel, &n_prel, sizeof n_prel));
-    RESERVE(ctx->d_xnodes, sizeof(XNode) * std::max<size_t>(hx.size(), 1));
-    RESERVE(ctx->d_xcpt, sizeof(double) * std::max<size_t>(hcpt.size(), 1));
-    CK(cudaMemcpy(ctx->d_xnodes.p, hx.data(), sizeof(XNode) * hx.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_xcpt.p, hcpt.data(), sizeof(double) * hcpt.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpyToSymbol(c_trie, htrie, sizeof htrie));
-    ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size(); ctx->motif_ok = motif_ok;
-    ctx->local_stack = stack_slots > STK_SLOTS || getenv("RMD_LOCAL_STACK");
+    sym.n_prel = n_prel;
+    bool any_brute = prel_overflow;               // too many distinct pair geometries for the candidate filter: exact path
+    for (const CModel &c : hmodels) if (c.brute) any_brute = true;
     for (int m = n_models; m <= RMD_MAX_MODELS; m++) screen0[m] = (unsigned char)n_screens;
-    memcpy(ctx->screen0, screen0, sizeof screen0);
-    ctx->n_screens = n_screens; ctx->screen_words = screen_words; ctx->screens_dirty = true;
-    CK(cudaMemcpyToSymbol(c_screen_build, hbuild, sizeof hbuild));
-    CK(cudaMemcpyToSymbol(c_screens, hdesc, sizeof hdesc));
+    int teams_new = 8, ctas_new = 1, sm_count = 0;
+    size_t scan_smem = 0;
+    bool tables_in_smem = true;
     {   // shape of the persistent scan kernel: tables + one FastSmem per team within the SM's shared memory
         int smem_max = 0;
-        CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+        CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
         const size_t screens = sizeof(ScreenDesc) * (size_t)n_screens;          // always in shared memory
         const size_t tables = sizeof(XNode) * hx.size() + 16 * ((hcpt.size() + 1) / 2);
-        int teams = getenv("RMD_TEAMS") ? atoi(getenv("RMD_TEAMS")) : 8;
-        ctx->ctas_per_sm = getenv("RMD_CTAS_PER_SM") ? atoi(getenv("RMD_CTAS_PER_SM")) : 1;
+        int teams = tune_env("RMD_TEAMS") ? atoi(tune_env("RMD_TEAMS")) : 8;
+        ctas_new = tune_env("RMD_CTAS_PER_SM") ? std::max(1, atoi(tune_env("RMD_CTAS_PER_SM"))) : 1;
         teams = std::max(1, std::min(teams, SCAN_MAX_THREADS / SCAN_THREADS));
-        ctx->tables_in_smem = tables + screens + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctx->ctas_per_sm;
-        const size_t fixed = (ctx->tables_in_smem ? tables : 0) + screens;
-        while (teams > 1 && fixed + teams * sizeof(FastSmem) > (size_t)smem_max / ctx->ctas_per_sm) teams--;
-        ctx->teams = teams;
-        ctx->scan_smem = fixed + teams * sizeof(FastSmem);
-        if (ctx->scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", ctx->scan_smem, smem_max);
+        tables_in_smem = tables + screens + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctas_new;
+        const size_t fixed = (tables_in_smem ? tables : 0) + screens;
+        while (teams > 1 && fixed + teams * sizeof(FastSmem) > (size_t)smem_max / ctas_new) teams--;
+        teams_new = teams;
+        scan_smem = fixed + teams * sizeof(FastSmem);
+        if (scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", scan_smem, smem_max);
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -454,16 +494,58 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     }
+    // ---- commit: nothing below can be refused for the descriptors' sake ------------------------------------------
+    CK(cudaDeviceSynchronize());
+    RESERVE(ctx->d_xnodes, sizeof(XNode) * std::max<size_t>(hx.size(), 1));
+    RESERVE(ctx->d_xcpt, sizeof(double) * std::max<size_t>(hcpt.size(), 1));
+    CK(cudaMemcpy(ctx->d_xnodes.p, hx.data(), sizeof(XNode) * hx.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_xcpt.p, hcpt.data(), sizeof(double) * hcpt.size(), cudaMemcpyHostToDevice));
+    ctx->have_job = false;                         // a resident job was staged for the old model count
+    free_models(ctx);
+    ctx->model_allocs.swap(pending.allocs);
+    pending.committed = true;
+    ctx->hmodels.swap(hmodels);
+    ctx->sym = sym;
+    ctx->sym_gen = g_next_gen++;                   // bind_tables() uploads the __constant__ copies before the next launch
     ctx->n_models = n_models;
-    CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * n_models));
-    ctx->have_job = false;
+    ctx->max_chain = max_chain;
+    ctx->any_brute = any_brute;
+    ctx->n_xnodes = (int)hx.size(); ctx->n_xcpt = (int)hcpt.size(); ctx->motif_ok = motif_ok;
+    ctx->local_stack = stack_slots > STK_SLOTS || tune_env("RMD_LOCAL_STACK");
+    memcpy(ctx->screen0, screen0, sizeof screen0);
+    ctx->n_screens = n_screens; ctx->screen_words = screen_words; ctx->screens_dirty = true;
+    ctx->teams = teams_new; ctx->ctas_per_sm = ctas_new; ctx->sm_count = sm_count;
+    ctx->scan_smem = scan_smem; ctx->tables_in_smem = tables_in_smem;
+    return RMD_OK;
+}
+
+// Make the device's __constant__ tables this context's (see g_sym_owner).  Called, under the device lock, by every
+// entry point that launches a kernel reading c_models / c_trie / c_prel / c_groups / c_screen*.
+static int bind_tables(rmd_ctx *ctx) {
+    const int dev = ctx->device;
+    if (g_sym_owner[dev] == ctx && g_sym_gen[dev] == ctx->sym_gen) return RMD_OK;
+    if (ctx->n_models == 0) return fail(ctx, RMD_E_STATE, "no models: call rmd_set_models first");
+    CK(cudaDeviceSynchronize());                    // kernels of the previous owner may still be reading the symbols
+    g_sym_owner[dev] = nullptr;
+    const SymbolTables &t = ctx->sym;
+    CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * ctx->n_models));
+    CK(cudaMemcpyToSymbol(c_trie, t.trie, sizeof t.trie));
+    CK(cudaMemcpyToSymbol(c_prel, t.prel, sizeof t.prel));
+    CK(cudaMemcpyToSymbol(c_n_prel, &t.n_prel, sizeof t.n_prel));
+    CK(cudaMemcpyToSymbol(c_groups, t.groups, sizeof t.groups));
+    CK(cudaMemcpyToSymbol(c_n_groups, &t.n_groups, sizeof t.n_groups));
+    CK(cudaMemcpyToSymbol(c_screen_build, t.build, sizeof t.build));
+    CK(cudaMemcpyToSymbol(c_screens, t.desc, sizeof t.desc));
+    g_sym_owner[dev] = ctx; g_sym_gen[dev] = ctx->sym_gen;
     return RMD_OK;
 }
 
 extern "C" int rmd_set_evalues(rmd_ctx *ctx, int model, const double *table, int n_class, int n_rows, const double *thresholds) {
     if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_set_evalues: bad model index");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
+    ctx->sym_gen = g_next_gen++;                  // c_models changes: re-bound before the next launch
     for (void *p : ctx->ev_allocs[model]) cudaFree(p);
     ctx->ev_allocs[model].clear();
     CModel &c = ctx->hmodels[model];
@@ -475,7 +557,6 @@ extern "C" int rmd_set_evalues(rmd_ctx *ctx, int model, const double *table, int
         if ((r = to_device(ctx, thresholds, (size_t)n_rows, &th, ctx->ev_allocs[model]))) return r;
         c.ev_table = t; c.ev_thr = th; c.ev_nclass = n_class; c.ev_nrows = n_rows;
     }
-    CK(cudaMemcpyToSymbol(c_models, ctx->hmodels.data(), sizeof(CModel) * ctx->n_models));
     return RMD_OK;
 }
 
@@ -513,7 +594,7 @@ static int stage_layout(rmd_ctx *ctx, int n_seq, const int64_t *seq_off, int win
     DevJob &J = ctx->job;
     J.n_seq = n_seq; J.n_models = ctx->n_models; J.win_len = win_len; J.win_step = win_step;
     J.n_win = ctx->h_win_base[n_seq];
-    J.debug = getenv("RMD_DEBUG") ? atoi(getenv("RMD_DEBUG")) : 0;
+    J.debug = tune_env("RMD_DEBUG") ? atoi(tune_env("RMD_DEBUG")) : 0;      // -DRMD_TUNING builds only
     J.seq_off = (const long long *)ctx->d_seq_off.p; J.win_base = (const long long *)ctx->d_win_base.p;
     J.xnodes = (const XNode *)ctx->d_xnodes.p; J.xcpt = (const double *)ctx->d_xcpt.p;
     J.n_xnodes = ctx->n_xnodes; J.n_xcpt = ctx->n_xcpt; J.motif_ok = ctx->motif_ok ? 1 : 0;
@@ -598,6 +679,7 @@ static int stage_entries(rmd_ctx *ctx, const rmd_scan_input *in, long long e0, l
 static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries) {
     if (!ctx || !in) return fail(ctx, RMD_E_INVALID, "rmd_upload: NULL argument");
     if (ctx->n_models == 0) return fail(ctx, RMD_E_STATE, "rmd_upload: call rmd_set_models first");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     if (!in->gc_log) return fail(ctx, RMD_E_INVALID, "rmd_upload: gc_log is required (use rmd_gc_counts + rmd_set_gc to derive it on the device)");
     CK(cudaSetDevice(ctx->device));
     ctx->have_job = false;
@@ -658,6 +740,7 @@ extern "C" int rmd_upload(rmd_ctx *ctx, const rmd_scan_input *in) { return uploa
 extern "C" int rmd_gc_counts(rmd_ctx *ctx, int64_t *counts) {
     if (!ctx || !counts) return fail(ctx, RMD_E_INVALID, "rmd_gc_counts: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_gc_counts: no resident job");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     const DevJob &J = ctx->job;
     RESERVE(ctx->d_counts, sizeof(unsigned long long) * RMD_N_CODES * J.n_seq);
@@ -680,6 +763,7 @@ extern "C" int rmd_gc_counts(rmd_ctx *ctx, int64_t *counts) {
 extern "C" int rmd_set_gc(rmd_ctx *ctx, const double *gc_log, const int32_t *gc_class) {
     if (!ctx || !gc_log) return fail(ctx, RMD_E_INVALID, "rmd_set_gc: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_set_gc: no resident job");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     int r = stage_gc(ctx, gc_log, gc_class);
     if (r) return r;
@@ -750,11 +834,13 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_scan_resident: no resident job");
     const DevJob &J = ctx->job;
     if (w_begin < 0 || w_end > J.n_win || w_begin > w_end) return fail(ctx, RMD_E_INVALID, "window range [%lld, %lld) outside [0, %lld)", (long long)w_begin, (long long)w_end, J.n_win);
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
+    { int rb = bind_tables(ctx); if (rb) return rb; }
     memset(out, 0, sizeof *out);
     const long long nwin = w_end - w_begin;
     const long long ngroups = nwin * J.n_models;
-    if (ngroups >= (1LL << 31)) return fail(ctx, RMD_E_LIMIT, "window range too large for one call (%lld windows x %d models)", nwin, J.n_models);
+    if (ngroups >= (1LL << 31)) return fail(ctx, RMD_E_LIMIT, "window range too large for one call (%lld windows x %d models): stage the job with rmd_upload and scan it in ranges with rmd_scan_resident", nwin, J.n_models);
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev[8], st));
     if (ctx->screens_dirty) { int rs = build_screens(ctx); if (rs) return rs; }
@@ -797,7 +883,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                 n_chunks = 0;
                 // without expansion launches, and with the chunks' tails overlapping on two streams, a launch costs less
                 const bool will_fuse = use_fast && !need_generic && ctx->tables_in_smem && !ctx->local_stack &&
-                                       !(ctx->any_brute || !(J.min_bpp > 0.0)) && !getenv("RMD_NO_FUSED_EXPAND");
+                                       !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");
                 const int gpct = will_fuse ? 45 : 60;
                 long long end = std::max<long long>(nwin / 128, 2048);
                 while (end < nwin && n_chunks < STREAM_CHUNKS - 1) { bounds[++n_chunks] = w_begin + end; end = end + end * gpct / 100 + 1024; }
@@ -813,7 +899,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         // CTAs start on the SMs whose persistent CTA has run out of windows.
         if (streaming) {
             const bool fused = stream_in->bpp_q && use_fast && !need_generic && ctx->tables_in_smem && !ctx->local_stack &&
-                               !(ctx->any_brute || !(J.min_bpp > 0.0)) && !getenv("RMD_NO_FUSED_EXPAND");     // = will_fuse above
+                               !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");     // = will_fuse above
             ctx->job.bpp_ij = fused ? (const uint16_t *)ctx->d_bpp_ij.p : nullptr;
             ctx->job.bpp_q = fused ? (const uint32_t *)ctx->d_bpp_q.p : nullptr;
         }
@@ -940,11 +1026,19 @@ extern "C" int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, r
 }
 
 extern "C" int rmd_scan(rmd_ctx *ctx, const rmd_scan_input *in, rmd_scan_result *out) {
+    if (!ctx || !in || !out) return fail(ctx, RMD_E_INVALID, "rmd_scan: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     int r = upload_job(ctx, in, false);
     if (r) return r;
     // the copy stream must not start before the staging above has been issued ... it has been synchronised
     r = scan_core(ctx, 0, ctx->job.n_win, out, in);
-    if (r) return r;
+    if (r) {                                       // the lists may be on the device only in part: the job is not resident
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream2);
+        ctx->have_job = false;
+        return r;
+    }
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     out->ms_h2d = ms;
@@ -959,8 +1053,11 @@ extern "C" int rmd_eval(rmd_ctx *ctx, int model, const uint8_t *codes, const int
                         int32_t *leaf, double *prob_model, double *prob_rand) {
     if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_eval: bad model index");
     if (n <= 0) return RMD_OK;
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
+    { int rb = bind_tables(ctx); if (rb) return rb; }
     cudaStream_t st = ctx->stream;
+    ctx->cal_open = false;                         // the scratch buffers below are a calibration session's too
     const long long nl = seq_off[n];
     const CModel &M = ctx->hmodels[model];
     for (int64_t k = 0; k < n; k++) {            // the reference would raise IndexError past the end
@@ -992,21 +1089,14 @@ extern "C" int rmd_eval(rmd_ctx *ctx, int model, const uint8_t *codes, const int
     return RMD_OK;
 }
 
-static int calibrate_common(rmd_ctx *ctx, int model, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n, int32_t L,
-                            const double *class_log, int32_t n_class, double cutoff, double *hist, int32_t n_bins,
-                            int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
-    if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: bad model index");
-    const CModel &M = ctx->hmodels[model];
-    if (L != M.chain_len[0] + M.chain_len[1]) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: L is %d, the model has %d positions", L, M.chain_len[0] + M.chain_len[1]);
-    if (L > 32) return fail(ctx, RMD_E_LIMIT, "rmd_calibrate: at most 32 positions");
-    if (n_class < 1 || n_class > CAL_MAX_CLASS || n_bins < 2) return fail(ctx, RMD_E_LIMIT, "rmd_calibrate: class count %d / bin count %d out of range", n_class, n_bins);
-    if (n <= 0) return RMD_OK;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    std::vector<double> thr(n_bins);
-    // thresholds of Python's round(x, 1): computed by the caller-independent exact rule on the host
+// ---- calibration (rmcalibrate.py:235-298): a session keeps the weighted histograms on the device ---------------
+// rmd_calib_open stages the class logs and rounding thresholds and zeroes the histogram; rmd_calib_add enqueues the
+// scoring of a batch of samples (no synchronisation: batches queue up behind each other); rmd_calib_device_hist hands
+// out the histogram's device address so that several GPUs can all-reduce it in place; rmd_calib_read downloads it.
+static int calib_thresholds(std::vector<double> &thr, int n_bins) {
+    thr.resize(n_bins);
     for (int k = 0; k < n_bins; k++) {
-        // smallest double whose decimal rounding to one place reaches (k+1)/10: probe around the midpoint
+        // smallest double whose decimal rounding to one place (Python's round(x, 1)) reaches (k+1)/10: probe around the midpoint
         double mid = (2.0 * k + 1.0) / 20.0, lo = nextafter(mid, 0.0), best = nextafter(mid, 1e300);
         char a[32];
         for (double c : {lo, mid}) {
@@ -1015,36 +1105,104 @@ static int calibrate_common(rmd_ctx *ctx, int model, const uint8_t *samples, uin
         }
         thr[k] = best;
     }
-    RESERVE(ctx->d_e0, samples ? (size_t)n * L : 16);
+    return RMD_OK;
+}
+
+extern "C" int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *class_log, int32_t n_class, double cutoff, int32_t n_bins) {
+    if (!ctx || model < 0 || model >= ctx->n_models) return fail(ctx, RMD_E_INVALID, "rmd_calib_open: bad model index");
+    const CModel &M = ctx->hmodels[model];
+    if (L != M.chain_len[0] + M.chain_len[1]) return fail(ctx, RMD_E_INVALID, "rmd_calib_open: L is %d, the model has %d positions", L, M.chain_len[0] + M.chain_len[1]);
+    if (L > 32) return fail(ctx, RMD_E_LIMIT, "rmd_calib_open: at most 32 positions");
+    if (!class_log || n_class < 1 || n_class > CAL_MAX_CLASS || n_bins < 2) return fail(ctx, RMD_E_LIMIT, "rmd_calib_open: class count %d / bin count %d out of range", n_class, n_bins);
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<double> thr;
+    calib_thresholds(thr, n_bins);
     RESERVE(ctx->d_e1, sizeof(double) * 4 * n_class);
     RESERVE(ctx->d_e2, sizeof(double) * n_bins);
     RESERVE(ctx->d_e3, sizeof(double) * (size_t)n_class * n_bins);
     RESERVE(ctx->d_e4, 64);
-    if (samples) CK(cudaMemcpyAsync(ctx->d_e0.p, samples, (size_t)n * L, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_e1.p, class_log, sizeof(double) * 4 * n_class, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_e2.p, thr.data(), sizeof(double) * n_bins, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->d_e3.p, 0, sizeof(double) * (size_t)n_class * n_bins, st));
     CK(cudaMemsetAsync(ctx->d_e4.p, 0, 64, st));
-    CalibArgs A;
-    A.model = model; A.L = L; A.n_class = n_class; A.n_bins = n_bins; A.n = n; A.first = first;
-    A.samples = samples ? (const uint8_t *)ctx->d_e0.p : nullptr; A.seed = seed;
+    CK(cudaStreamSynchronize(st));                 // thr goes out of scope
+    CalibArgs &A = ctx->cal;
+    A.model = model; A.L = L; A.n_class = n_class; A.n_bins = n_bins; A.n = 0; A.first = 0;
+    A.samples = nullptr; A.seed = 0;
     A.class_log = (const double *)ctx->d_e1.p; A.thr = (const double *)ctx->d_e2.p;
     A.cutoff = cutoff; A.ln2 = std::log(2.0); A.K = L * std::log(4.0);
     A.hist = (double *)ctx->d_e3.p;
     A.n_ok = (unsigned long long *)ctx->d_e4.p; A.overflow = (int *)((char *)ctx->d_e4.p + 8);
-    CK(cudaEventRecord(ctx->ev[0], st));
+    ctx->cal_open = true; ctx->cal_timed = false;
+    return RMD_OK;
+}
+
+extern "C" int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n) {
+    if (!ctx || !ctx->cal_open) return fail(ctx, RMD_E_STATE, "rmd_calib_add: call rmd_calib_open first");
+    if (n <= 0) return RMD_OK;
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    CK(cudaSetDevice(ctx->device));
+    { int rb = bind_tables(ctx); if (rb) return rb; }
+    cudaStream_t st = ctx->stream;
+    CalibArgs A = ctx->cal;
+    if (samples) {
+        CK(cudaStreamSynchronize(st));             // the previous batch may still be reading the staging buffer
+        RESERVE(ctx->d_e0, (size_t)n * A.L);
+        CK(cudaMemcpyAsync(ctx->d_e0.p, samples, (size_t)n * A.L, cudaMemcpyHostToDevice, st));
+        A.samples = (const uint8_t *)ctx->d_e0.p;
+    }
+    A.n = n; A.first = first; A.seed = seed;
+    if (!ctx->cal_timed) { CK(cudaEventRecord(ctx->ev[0], st)); ctx->cal_timed = true; }
     calibrate_kernel<<<(unsigned)((n + CAL_THREADS - 1) / CAL_THREADS), CAL_THREADS, 0, st>>>(A);
     CK(cudaEventRecord(ctx->ev[1], st));
-    std::vector<double> h((size_t)n_class * n_bins);
+    CK(cudaGetLastError());
+    if (samples) CK(cudaStreamSynchronize(st));    // the caller's buffer may be reused on return
+    return RMD_OK;
+}
+
+extern "C" int rmd_calib_device_hist(rmd_ctx *ctx, void **dptr, int64_t *n_doubles) {
+    if (!ctx || !dptr || !ctx->cal_open) return fail(ctx, RMD_E_STATE, "rmd_calib_device_hist: no open calibration session");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));        // the batches enqueued so far are in the histogram
+    CK(cudaGetLastError());
+    *dptr = ctx->cal.hist;
+    if (n_doubles) *n_doubles = (int64_t)ctx->cal.n_class * ctx->cal.n_bins;
+    return RMD_OK;
+}
+
+extern "C" int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t *overflow, float *ms_device) {
+    if (!ctx || !ctx->cal_open) return fail(ctx, RMD_E_STATE, "rmd_calib_read: no open calibration session");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     unsigned long long small[2] = {0, 0};
-    CK(cudaMemcpyAsync(h.data(), ctx->d_e3.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    if (hist) CK(cudaMemcpyAsync(hist, ctx->cal.hist, sizeof(double) * (size_t)ctx->cal.n_class * ctx->cal.n_bins, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(small, ctx->d_e4.p, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    for (size_t k = 0; k < h.size(); k++) hist[k] += h[k];
     if (n_ok) *n_ok = (int64_t)small[0];
     if (overflow) *overflow = (int32_t)(small[1] & 0xffffffffu);
-    if (ms_kernel) CK(cudaEventElapsedTime(ms_kernel, ctx->ev[0], ctx->ev[1]));
+    if (ms_device) { *ms_device = 0.0f; if (ctx->cal_timed) CK(cudaEventElapsedTime(ms_device, ctx->ev[0], ctx->ev[1])); }
+    ctx->cal_timed = false;
+    return RMD_OK;
+}
+
+static int calibrate_once(rmd_ctx *ctx, int model, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n, int32_t L,
+                          const double *class_log, int32_t n_class, double cutoff, double *hist, int32_t n_bins,
+                          int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
+    if (!ctx || !hist) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: NULL argument");
+    if (n <= 0) return RMD_OK;
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    int r;
+    if ((r = rmd_calib_open(ctx, model, L, class_log, n_class, cutoff, n_bins))) return r;
+    if ((r = rmd_calib_add(ctx, samples, seed, first, n))) return r;
+    std::vector<double> h((size_t)n_class * n_bins);
+    if ((r = rmd_calib_read(ctx, h.data(), n_ok, overflow, ms_kernel))) return r;
+    for (size_t k = 0; k < h.size(); k++) hist[k] += h[k];
+    ctx->cal_open = false;
     return RMD_OK;
 }
 
@@ -1052,13 +1210,13 @@ extern "C" int rmd_calibrate(rmd_ctx *ctx, int model, const uint8_t *samples, in
                              const double *class_log, int32_t n_class, double cutoff,
                              double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
     if (!samples) return fail(ctx, RMD_E_INVALID, "rmd_calibrate: samples is NULL");
-    return calibrate_common(ctx, model, samples, 0, 0, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
+    return calibrate_once(ctx, model, samples, 0, 0, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
 }
 
 extern "C" int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64_t first, int64_t n, int32_t L,
                                    const double *class_log, int32_t n_class, double cutoff,
                                    double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel) {
-    return calibrate_common(ctx, model, nullptr, seed, first, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
+    return calibrate_once(ctx, model, nullptr, seed, first, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
 }
 
 extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, uint64_t bpp_seed,
@@ -1068,6 +1226,7 @@ extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t se
     if (ctx->n_models == 0) return fail(ctx, RMD_E_STATE, "rmd_synth_job: call rmd_set_models first");
     if (win_len < 1 || win_len > RMD_FAST_WINDOW || win_step < 1) return fail(ctx, RMD_E_LIMIT, "rmd_synth_job: window length must be 1..%d", RMD_FAST_WINDOW);
     if (!gc_log) return fail(ctx, RMD_E_INVALID, "rmd_synth_job: gc_log is required");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     ctx->have_job = false;
     int64_t seq_off[2] = {0, n};
@@ -1129,6 +1288,7 @@ extern "C" int rmd_synth_counts(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t
     if (!ctx || !counts || n < 0 || first < 0) return fail(ctx, RMD_E_INVALID, "rmd_synth_counts: bad arguments");
     if (ctx->strand_total > 0 && first + n > ctx->strand_total)
         return fail(ctx, RMD_E_INVALID, "rmd_synth_counts: letters [%lld, %lld) leave the strand of %lld letters", (long long)first, (long long)(first + n), ctx->strand_total);
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     RESERVE(ctx->d_counts, sizeof(unsigned long long) * RMD_N_CODES);
     CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
@@ -1147,6 +1307,7 @@ extern "C" int rmd_download_codes(rmd_ctx *ctx, uint8_t *codes, int64_t n) {
     if (!ctx || !codes) return fail(ctx, RMD_E_INVALID, "rmd_download_codes: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_codes: no resident job");
     if (n > ctx->n_letters) n = ctx->n_letters;
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     if (ctx->any_other) {
         CK(cudaMemcpy(codes, ctx->d_codes8.p, (size_t)n, cudaMemcpyDeviceToHost));
@@ -1172,9 +1333,10 @@ static int ensure_expanded(rmd_ctx *ctx) {
 extern "C" int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint16_t *j, double *p, int64_t cap, int64_t *n) {
     if (!ctx || !n) return fail(ctx, RMD_E_INVALID, "rmd_download_bpp: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_bpp: no resident job");
-    { int re = ensure_expanded(ctx); if (re) return re; }
     if (window < 0 || window >= ctx->job.n_win) return fail(ctx, RMD_E_INVALID, "rmd_download_bpp: window out of range");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
+    { int re = ensure_expanded(ctx); if (re) return re; }
     long long off[2];
     CK(cudaMemcpy(off, (const long long *)ctx->d_bpp_off.p + window, sizeof off, cudaMemcpyDeviceToHost));
     const long long cnt = off[1] - off[0];
@@ -1191,6 +1353,7 @@ extern "C" int rmd_download_bpp(rmd_ctx *ctx, int64_t window, uint16_t *i, uint1
 extern "C" int rmd_download_job(rmd_ctx *ctx, int64_t *bpp_off, uint16_t *i, uint16_t *j, double *p) {
     if (!ctx || !bpp_off) return fail(ctx, RMD_E_INVALID, "rmd_download_job: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_download_job: no resident job");
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     { int re = ensure_expanded(ctx); if (re) return re; }
     CK(cudaMemcpy(bpp_off, ctx->d_bpp_off.p, sizeof(long long) * (ctx->job.n_win + 1), cudaMemcpyDeviceToHost));

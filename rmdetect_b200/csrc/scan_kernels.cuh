@@ -217,7 +217,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const uint4 *xn = TABLES ? sx : reinterpret_cast<const uint4 *>(J.xnodes);
     const double *xcpt = TABLES ? scpt : J.xcpt;
     const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (lib/node.py:248)
-    const bool no_score = !root_ok || (J.debug & 1);
+#ifdef RMD_TUNING
+    const bool no_score = !root_ok || (J.debug & 1);      // profiling experiment: gate only
+#else
+    const bool no_score = !root_ok;
+#endif
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
     uint32_t wq_off = sm_off + (uint32_t)offsetof(FastSmem, wq) + (uint32_t)wid * (uint32_t)sizeof(WarpQueues);
     asm volatile("mov.u32 %0, %0;" : "+r"(wq_off));
@@ -821,7 +825,9 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
             const bool act = p1 <= hi;
             const bool pass = gate_pass(M, lookup, act, p0, p1, J.min_bpp);
             EvalOut r; r.leaf = -1;
-            if (pass) { npass++; r = eval_placement(M, letter, gc, p0, p1, J.cutoff); }
+            // a window shorter than a chain still has its placement (0, 0) tried (lib/scanner.py:137-141); scoring it would
+            // read letters past the window's end, where the reference raises IndexError: such a placement yields no hit
+            if (pass) { npass++; if (p0 + L0 <= wlen && p1 + L1 <= wlen) r = eval_placement(M, letter, gc, p0, p1, J.cutoff); }
             uint32_t total;
             const uint32_t rank = block_exclusive_scan<GEN_THREADS>(r.leaf >= 0 ? 1u : 0u, scan_tmp, &total);
             if (total) {

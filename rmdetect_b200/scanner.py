@@ -227,69 +227,112 @@ class Scanner:
                 if not isinstance(m.pairs_list, list):
                     m.pairs_list = list(m.pairs_list)
             self._engine = ScanEngine(self.config.models, self.config.evalues, self.config.unknown_prob, self.device)
-            self._engine.ctx.lib.rmd_set_return_dropped(self._engine.ctx.h, 1)
+            self._engine.ctx.set_return_dropped(True)
             self._engine_key = key
         return self._engine
 
+    # windows per GPU job when `scan` batches sequences (an alignment of short sequences becomes ONE job: one upload,
+    # one launch sequence, one download, instead of one of each per sequence); a longer input is cut at sequence ends
+    max_batch_windows = 1 << 19
+
     def scan(self, seqs, gc=None):
+        """lib/scanner.py:29-68.  The sequences are scanned in batches (all windows of a batch are folded through one
+        `coo_many` call and scanned by one GPU job), then the reference's callbacks are replayed in its order with its
+        arguments: before_sequence, per window before_window / after_window (candidates and tries of the sequence so
+        far), after_sequence (after the duplicate rule), and after_scan at the end."""
         sequences = seqs.sequence_list
         cands, tries = [], [0, 0]
         self.cback_before_scan(len(sequences))
-        for i, sequence in enumerate(sequences):
-            self.cback_before_sequence(len(sequences), i, sequence.key)
-            if self.config.win_len == 0 or self.config.win_step == 0:
-                cands_seq, tries_seq = self.search(sequence.key, sequence.seq, gc)
-                for cand in cands_seq:
-                    cand.update_chains_cols(sequence.col_index)
-            else:
-                cands_seq, tries_seq = self.slide(sequence.key, sequence.seq, sequence.col_index, gc)
-            cands_seq = [c for c in cands_seq if c._keep]          # duplicate rule, decided on the device
-            self.cback_after_sequence(cands_seq, tries_seq)
-            cands.extend(cands_seq)
-            tries[0] += tries_seq[0]
-            tries[1] += tries_seq[1]
+        whole = self.config.win_len == 0 or self.config.win_step == 0
+        W, step = (0, 0) if whole else (self.config.win_len, self.config.win_step)
+        i = 0
+        while i < len(sequences):
+            batch, n_win = [], 0
+            while i + len(batch) < len(sequences) and (not batch or n_win < self.max_batch_windows):
+                q = sequences[i + len(batch)]
+                n_win += len(window_starts(len(q.seq), W, step))
+                batch.append(q)
+            triples = [(q.key, q.seq, None if whole else q.col_index) for q in batch]
+            live = [t for t in triples if len(t[1])]                    # search() skips an empty sequence (lib/scanner.py:118-123)
+            run = self._run_many(live if whole else triples, W, step, gc) if (live if whole else triples) else None
+            at = 0                                                       # index into the job's sequences
+            for k, q in enumerate(batch):
+                self.cback_before_sequence(len(sequences), i + k, q.key)
+                if whole:
+                    if len(q.seq) == 0:
+                        cands_seq, tries_seq = [], [0, 0]
+                    else:
+                        cands_seq, tries_seq = self._replay_search(run, at)
+                        at += 1
+                        for cand in cands_seq:
+                            cand.update_chains_cols(q.col_index)
+                else:
+                    cands_seq, tries_seq = self._replay_slide(run, at)
+                    at += 1
+                cands_seq = [c for c in cands_seq if c._keep]          # duplicate rule, decided on the device
+                self.cback_after_sequence(cands_seq, tries_seq)
+                cands.extend(cands_seq)
+                tries[0] += tries_seq[0]
+                tries[1] += tries_seq[1]
+            i += len(batch)
         self.cback_after_scan(cands, tries)
         return cands, tries
 
-    def _run(self, key, seq, col_index, win_len, win_step, gc):
+    def _run_many(self, triples, win_len, win_step, gc):
         eng = self._get_engine()
-        seqs = [(key, seq, col_index)]
-        job = eng.build_job(seqs, win_len, win_step, self.rna_tools, self.config.constraint,
+        job = eng.build_job(triples, win_len, win_step, self.rna_tools, self.config.constraint,
                             self.config.min_bpp_mean, self.config.cutoff, gc)
         res = eng.scan_job(job)
-        return eng, seqs, job, res
-
-    def slide(self, key, seq, col_index, gc=None):
-        W, step = self.config.win_len, self.config.win_step
-        eng, seqs, job, res = self._run(key, seq, col_index, W, step, gc)
         hits = res["hits"]
-        starts = job["starts"][0]
-        bounds = np.searchsorted(hits["window"], np.arange(len(starts) + 1))
+        win_base = np.concatenate([[0], np.cumsum([len(s) for s in job["starts"]])]).astype(np.int64)
+        bounds = np.searchsorted(hits["window"], np.arange(job["n_win"] + 1))
+        return dict(eng=eng, seqs=triples, job=job, res=res, win_base=win_base, bounds=bounds)
+
+    def _replay_slide(self, run, si):
+        """The window loop of `slide` (lib/scanner.py:80-111) for sequence `si` of a scanned job."""
+        eng, res, hits, bounds = run["eng"], run["res"], run["res"]["hits"], run["bounds"]
+        W, step = self.config.win_len, self.config.win_step
+        seq = run["seqs"][si][1]
+        w0 = int(run["win_base"][si])
         cands, tries = [], [0, 0]
-        for k, s in enumerate(starts.tolist()):
+        for k, s in enumerate(run["job"]["starts"][si].tolist()):
             self.cback_before_window(len(seq), int(k * step))       # the value slide holds before re-anchoring
             wlen = len(seq[s:s + W])
-            for h in hits[bounds[k]:bounds[k + 1]]:
-                cand = eng.make_candidate(h, seqs, self.candidate_factory)
+            for h in hits[bounds[w0 + k]:bounds[w0 + k + 1]]:
+                cand = eng.make_candidate(h, run["seqs"], self.candidate_factory)
                 cand._keep = bool(h["keep"])
                 cands.append(cand)
             tries[0] += sum(placements_in_window(m, wlen) for m in self.config.models)
-            tries[1] += int(res["gate_pass"][k].sum())
+            tries[1] += int(res["gate_pass"][w0 + k].sum())
             self.cback_after_window(cands, tries)
-        assert tries == res["tries"], (tries, res["tries"])
+        return cands, tries
+
+    def _replay_search(self, run, si):
+        eng, res, hits, bounds = run["eng"], run["res"], run["res"]["hits"], run["bounds"]
+        w = int(run["win_base"][si])
+        seq = run["seqs"][si][1]
+        cands = []
+        for h in hits[bounds[w]:bounds[w + 1]]:
+            cand = eng.make_candidate(h, run["seqs"], self.candidate_factory)
+            cand._keep = bool(h["keep"])
+            cand.chains_cols = []                                   # search leaves columns to its caller
+            cands.append(cand)
+        tries = [sum(placements_in_window(m, len(seq)) for m in self.config.models), int(res["gate_pass"][w].sum())]
+        return cands, tries
+
+    def slide(self, key, seq, col_index, gc=None):
+        run = self._run_many([(key, seq, col_index)], self.config.win_len, self.config.win_step, gc)
+        cands, tries = self._replay_slide(run, 0)
+        assert tries == run["res"]["tries"], (tries, run["res"]["tries"])
         return cands, tries
 
     def search(self, key, seq, gc=None):
         if len(seq) == 0:
             return [], [0, 0]
-        eng, seqs, job, res = self._run(key, seq, None, 0, 0, gc)
-        cands = []
-        for h in res["hits"]:
-            cand = eng.make_candidate(h, seqs, self.candidate_factory)
-            cand._keep = bool(h["keep"])
-            cand.chains_cols = []                                   # search leaves columns to its caller
-            cands.append(cand)
-        return cands, list(res["tries"])
+        run = self._run_many([(key, seq, None)], 0, 0, gc)
+        cands, tries = self._replay_search(run, 0)
+        assert tries == run["res"]["tries"], (tries, run["res"]["tries"])
+        return cands, tries
 
     def pointer_inc(self, model, seq_len, pointers):
         # reference lib/scanner.py:161-193 — kept for callers that drive the odometer themselves

@@ -61,6 +61,15 @@ def synth_sequence(n, seed, start=0, reverse_total=0) -> str:
     return np.array([65, 67, 71, 85], dtype=np.uint8)[synth_codes(n, seed, start, reverse_total)].tobytes().decode()
 
 
+def synth_calibration_samples(seed, first, n, L):
+    """Host twin of the draw inside rmd_calibrate_synth (csrc/calib_kernels.cuh): letter j of sample s is the top
+    two bits of mix64(seed + GOLDEN * (s * L + j + 1)), s in [first, first + n).  Returns codes [n][L]."""
+    g = (np.arange(first, first + n, dtype=np.int64)[:, None] * L + np.arange(L, dtype=np.int64)[None, :]).astype(U64)
+    with np.errstate(over="ignore"):
+        h = mix64(U64(seed) + GOLDEN * (g + U64(1)))
+    return (h >> U64(62)).astype(np.uint8)
+
+
 def _hash_bytes(seq: str) -> np.ndarray:
     """Per-letter byte used for the window key: 0..3 for ACGU, else the ASCII code."""
     raw = np.frombuffer(seq.encode("latin-1"), dtype=np.uint8).copy()

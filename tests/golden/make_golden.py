@@ -335,16 +335,131 @@ def calibrate_vectors():
     dump("calibrate.json.gz", out)
 
 
+# --------------------------------------------------------------------------- whole result files (round 2)
+def res_files(sets):
+    """BASELINE configs[0] and [1] at full size: the reference's own flow from Scanner.scan to the bytes of the
+    `.res` file (rmdetect.py:31-70,237-249 -> lib/results.py:13-40), on the complete example inputs.
+
+    Shims: D1-D3 as everywhere; D4 (`Candidate.__lt__` from its `__cmp__`, needed by `.sort()`); D5 (`filter()[0]` in
+    `CandidateParser.code`: the builtin is shadowed inside lib.candidates by a list-returning one); D2/D7 for the joint
+    bpp: RNAfold is absent and HEAD's folds ignore the constraint, so every hit gets the 1.0 all shipped result files
+    show.  The comment block (time stamps) is left empty."""
+    import lib.candidates as ref_cands
+    import results as ref_results
+    ref_cands.Candidate.__lt__ = lambda a, b: a.__cmp__(b) < 0                         # shim D4
+    ref_cands.filter = lambda fn, seq: [x for x in seq if fn(x)]                        # shim D5
+
+    def joint_bpp(cands, seqs, constraint="", cback=None):                             # shims D2 / D7
+        for c in cands:
+            c.bpp = 1.0
+        return cands
+
+    class Seqs:
+        from_stdin = False
+
+        def __init__(self, fname, triples, both=False):
+            self.fname, self.both_strands = fname, both
+            self.sequence_list = []
+            for key, seq, cols in triples:
+                q = type("S", (), {})()
+                q.key, q.seq, q.col_index = key, seq, cols
+                self.sequence_list.append(q)
+
+        def seq_count(self):                                                           # lib/sequences.py:65-69
+            return len(self.sequence_list) * 2 if self.both_strands else len(self.sequence_list)
+
+    out = []
+    plan = [("lys_seq_kt", ["KT_1.0"], "models", "lys.seq", "examples/lysine/lys.seq", False),
+            ("lys_seq_both_all", MODEL_ORDER, "models", "lys.seq.both", "examples/lysine/lys.seq", True),
+            ("rnasel_seq_all", MODEL_ORDER, "models", "rnaselci.seq", "examples/rnasel/rnaselci.seq", False),
+            ("rnasel_stk_all", MODEL_ORDER, "models", "rnaselci.stk", "examples/rnasel/rnaselci.stk", False),
+            ("lys_stk_all", MODEL_ORDER, "models", "lys.stk", "examples/lysine/lys.stk", False),
+            ("arich_stk", ["ARICH_1.0"], "arich", "arich_test.stk", "examples/arich/single_alignment/arich_test.stk", False)]
+    for name, models, data, setname, fname, both in plan:
+        path = REF + "/models" if data == "models" else REF + "/examples/arich/calibrate"
+        cfg = load_config(path, models)
+        cfg.win_len, cfg.win_step = 150, 75
+        cfg.min_bpp_mean, cfg.cutoff, cfg.unknown_prob = 0.001, math.log(0.1), math.log(1e-4)
+        sc = ref_scanner.Scanner(cfg)
+        sc.rna_tools = SynthFold(SEED, factory=RefBPProbs)
+        seqs = Seqs(fname, sets[setname], both)
+        cands, tries = sc.scan(seqs)
+        keys = [q.key for q in seqs.sequence_list]
+        names = [m.full_name() for m in cfg.models]
+        every = [[names.index(c.model.full_name()), keys.index(c.key), c.coords[0], c.chains_pos[0][0], c.chains_pos[1][0],
+                  c.score, c.evalue] for c in cands]
+        # rmdetect.py:44-47,70
+        kept = ref_cands.Candidates.filter(cands, min_score=5.0)
+        kept = joint_bpp(kept, seqs)
+        kept = ref_cands.Candidates.filter(kept, min_bpp=0.001)
+        kept.sort()
+        tmp = "/tmp/golden_%s.res" % name
+        ref_results.Results.write(tmp, kept, seqs, "w", tries, "", "")
+        # the sequence's both-strand list is already doubled when both_strands is set (lib/sequences.py:65-69 quirk)
+        out.append(dict(name=name, models=models, data=data, seqset=setname, seq_file=fname, both_strands=both,
+                        seed=SEED, tries=list(tries), n_sequences=seqs.seq_count(), all=every, res=open(tmp).read()))
+        print("res", name, tries, len(cands), "->", len(kept), "lines")
+    dump("res_files.json.gz", out)
+
+
+def calibrate_checkpoints():
+    """Convergence bookkeeping of rmcalibrate.py (:64-99 table, :134-157 diff): the reference's own functions on its
+    own histograms after 10 000 and after all samples of the seeded runs of `calibrate_vectors`."""
+    import types
+    stub = types.ModuleType("rpy2")
+    stub.robjects = types.ModuleType("rpy2.robjects")
+    stub.robjects.r = None
+    sys.modules["rpy2"] = stub
+    sys.modules["rpy2.robjects"] = stub.robjects
+    src = open(REF + "/rmcalibrate.py").read()
+    out = {}
+    for name, samples in (("KT_1.0", 20000), ("GB_1.0", 20000), ("CL_1.0", 20000), ("TGA_1.0", 70000)):
+        runs = []
+        for n in (10000, samples):
+            tmp = "/tmp/golden_ckpt_%s.evalues" % name
+            argv = sys.argv
+            sys.argv = ["rmcalibrate.py", "--data-path", REF + "/models", "--samples", str(n), name, tmp]
+            random.seed(SEED)
+            g = {"__name__": "__main__"}
+            with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+                exec(compile(src, "rmcalibrate.py", "exec"), g)
+            sys.argv = argv
+            runs.append(g)
+        a, b = runs
+        L = len(next(m for m in b["config"].models if m.full_name().upper() == name).nodes)
+        gce_a, _ = b["get_gc_evalues"](a["gc_hists"], 1.0 / float(4 ** L))
+        gce_b, scores_b = b["get_gc_evalues"](b["gc_hists"], 1.0 / float(4 ** L))
+        diff = b["diff_gc_evalues"](gce_a, gce_b, scores_b)
+        mid = len(gce_b) // 2
+        out[name] = dict(samples=[10000, samples], seed=SEED, scores=scores_b, diff=diff,
+                         hists_a=[sorted([k, v] for k, v in h.items()) for h in a["gc_hists"]],
+                         middle_a=sorted([k, v] for k, v in gce_a[mid].items()),
+                         middle_b=sorted([k, v] for k, v in gce_b[mid].items()))
+        print("checkpoint", name, "diff", diff, "rows", len(scores_b))
+    dump("calibrate_ckpt.json.gz", out)
+
+
 def main():
+    only = set(sys.argv[1:])                      # e.g. `make_golden.py res ckpt` regenerates just those parts
+    want = lambda part: not only or part in only
     copy_data()
     sets = dump_seqsets()
     cfg = load_config(REF + "/models", MODEL_ORDER)
     cfg_a = load_config(REF + "/examples/arich/calibrate", ["ARICH_1.0"])
-    dump_models([cfg, cfg_a])
-    eval_vectors([cfg, cfg_a])
-    small_vectors(cfg)
-    scan_cases(sets)
-    calibrate_vectors()
+    if want("models"):
+        dump_models([cfg, cfg_a])
+    if want("eval"):
+        eval_vectors([cfg, cfg_a])
+    if want("small"):
+        small_vectors(cfg)
+    if want("scan"):
+        scan_cases(sets)
+    if want("calibrate"):
+        calibrate_vectors()
+    if want("res"):
+        res_files(sets)
+    if want("ckpt"):
+        calibrate_checkpoints()
 
 
 if __name__ == "__main__":

@@ -82,3 +82,11 @@ def test_host_only_entry_points_work_without_a_device():
     p = np.array([0.031622780 ** 2.0])
     out = _native.compact_bpp(i, j, p)
     assert out is not None and int(out[0][0]) == 3 | (40 << 8) and int(out[1][0]) & 0x3fffffff == 31622780
+
+
+def test_release_library_reads_no_tuning_switch():
+    """RMD_DEBUG, RMD_TEAMS, RMD_CTAS_PER_SM, RMD_LOCAL_STACK, RMD_NO_SCREEN and RMD_NO_FUSED_EXPAND exist only in
+    -DRMD_TUNING builds: the shipped library must not even contain their names (nor import getenv for them)."""
+    blob = open(_native.LIB_PATH, "rb").read()
+    for name in (b"RMD_DEBUG", b"RMD_TEAMS", b"RMD_CTAS_PER_SM", b"RMD_LOCAL_STACK", b"RMD_NO_SCREEN", b"RMD_NO_FUSED_EXPAND"):
+        assert name not in blob, name

@@ -1,0 +1,132 @@
+"""Calibration bookkeeping (rmdetect_b200/calibrate.py) against the reference's own rmcalibrate.py output.
+
+tests/golden/calibrate.json.gz holds the histograms and the `.evalues` text the reference wrote for seeded runs,
+calibrate_ckpt.json.gz its table after 10 000 samples and the convergence measure between the two tables
+(make_golden.py: calibrate_vectors, calibrate_checkpoints).  The sample scoring itself is the GPU's (test_gpu_parity.py);
+here the oracle's `orc_calibrate` stands in for it so that the loop — checkpoints, stop rule, file — and its
+multi-rank form (world-size-2 gloo, histograms all-reduced per block) run on the CPU.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from helpers import LN_CUTOFF, LN_UNKNOWN, golden, load_model
+from rmdetect_b200 import calibrate as cal
+from rmdetect_b200.gcx import GC
+
+MODELS = ["KT_1.0", "GB_1.0", "CL_1.0", "TGA_1.0"]
+
+
+def dense(pairs_per_class):
+    h = np.zeros((len(pairs_per_class), cal.N_BINS))
+    for ci, pairs in enumerate(pairs_per_class):
+        for k, v in pairs:
+            h[ci, int(round(k * 10))] = v
+    return h
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_table_text_equals_the_reference_file(name):
+    g = golden("calibrate")[name]
+    L = len(load_model(name).nodes)
+    classes = GC.get_classes(5, 15, 85)
+    hist = dense(g["hists"])
+    gce, scores = cal.gc_evalues(cal.hist_dicts(hist), 1.0 / float(4 ** L))
+    assert cal.table_text(classes, gce, scores) == g["text"]
+    tab, scores_d = cal.gc_evalues_dense(hist, 1.0 / float(4 ** L))
+    assert scores_d == scores
+    for ci, row in enumerate(gce):                                  # the dense form is the dict form, bit for bit
+        assert [row[s] for s in scores] == tab[ci].tolist()
+    assert cal.table_text_dense(classes, tab, scores) == g["text"]
+    # structure: first row 1.0 (give or take the floor and a top row the float grid drops), columns non-increasing, floor 4^-L
+    assert np.allclose(tab[:, 0], 1.0, rtol=0, atol=1e-4) and np.all(np.diff(tab, axis=1) <= 0) and tab.min() >= 1.0 / float(4 ** L)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_convergence_measure_equals_the_reference(name):
+    g, full = golden("calibrate_ckpt")[name], golden("calibrate")[name]
+    L = len(load_model(name).nodes)
+    ha, hb = dense(g["hists_a"]), dense(full["hists"])
+    ga, sa = cal.gc_evalues(cal.hist_dicts(ha), 1.0 / float(4 ** L))
+    gb, sb = cal.gc_evalues(cal.hist_dicts(hb), 1.0 / float(4 ** L))
+    assert sb == g["scores"]
+    mid = len(gb) // 2
+    assert sorted([k, v] for k, v in ga[mid].items()) == g["middle_a"]
+    assert sorted([k, v] for k, v in gb[mid].items()) == g["middle_b"]
+    assert cal.diff_gc_evalues(ga, gb, sb) == g["diff"]
+    ta, sa_d = cal.gc_evalues_dense(ha, 1.0 / float(4 ** L))
+    tb, sb_d = cal.gc_evalues_dense(hb, 1.0 / float(4 ** L))
+    assert cal.diff_dense(ta, sa_d, tb, sb_d) == g["diff"]
+
+
+class OracleScorer:
+    """CPU stand-in for calibrate.Calibrator: the oracle's restatement of rmcalibrate.py:265-295."""
+
+    def __init__(self, name):
+        from oracle import pyoracle
+        self.py = pyoracle
+        self.om = pyoracle.OracleModel(load_model(name))
+        self.L = len(load_model(name).nodes)
+        self.classes = GC.get_classes(5, 15, 85)
+        self.hist = np.zeros((len(self.classes), cal.N_BINS))
+
+    def add_samples(self, samples):
+        strings = ["".join("ACGU"[c] for c in row) for row in samples]
+        _, nok = self.py.calibrate(self.om, strings, self.classes, LN_UNKNOWN, LN_CUTOFF, cal.N_BINS, self.hist)
+        return nok
+
+    def reduced_hist(self, dist=None):
+        self.total = cal.all_reduce_hist(self.hist, dist)
+        return self.total
+
+    def add_synthetic(self, seed, first, n):
+        from rmdetect_b200.synth import synth_calibration_samples
+        return self.add_samples(synth_calibration_samples(seed, first, n, self.L))
+
+
+@pytest.mark.parametrize("name", ["KT_1.0", "TGA_1.0"])
+def test_calibration_loop_writes_the_reference_file(name, tmp_path):
+    """calibrate_model with the reference's seeded sample stream: checkpoints every 10 000 samples, the stop rule,
+    min(samples, 4^L) (TGA: 65 536 of the 70 000 asked for) — the final file is the reference's, byte for byte."""
+    g = golden("calibrate")[name]
+    out = tmp_path / "x.evalues"
+    tab, scores, done = cal.calibrate_model(load_model(name), str(out), samples=g["samples"], seed=g["seed"], log=None,
+                                            scorer=OracleScorer(name))
+    assert done == min(g["samples"], 4 ** len(load_model(name).nodes))
+    assert out.read_text() == g["text"]
+
+
+def _rank_main(rank, world, port, name, samples, seed, device_samples, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = OracleScorer(name)
+        tab, scores, done = cal.calibrate_model(load_model(name), os.path.join(out_dir, "w%d.evalues" % world), samples=samples,
+                                                seed=seed, log=None, dist=dist, scorer=sc, device_samples=device_samples)
+        np.save(os.path.join(out_dir, "hist_r%d.npy" % rank), sc.total)
+        np.save(os.path.join(out_dir, "tab_r%d.npy" % rank), tab)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("device_samples", [False, True])
+def test_two_ranks_reduce_to_the_single_rank_histogram(device_samples, tmp_path):
+    """World size 2 over gloo: each rank scores half of every block, the blocks' histograms are all-reduced; the final
+    histogram equals the single-rank one (same buckets; sums agree to rounding) on both ranks, and so does the file."""
+    import torch.multiprocessing as mp
+    name, samples, seed = "GB_1.0", 30000, 4242
+    port = 29500 + random.Random(os.getpid() + device_samples).randrange(2000)
+    mp.spawn(_rank_main, args=(2, port, name, samples, seed, device_samples, str(tmp_path)), nprocs=2, join=True)
+    one = OracleScorer(name)
+    tab1, scores1, done1 = cal.calibrate_model(load_model(name), str(tmp_path / "w1.evalues"), samples=samples, seed=seed,
+                                               log=None, scorer=one, device_samples=device_samples)
+    h0, h1 = np.load(tmp_path / "hist_r0.npy"), np.load(tmp_path / "hist_r1.npy")
+    assert np.array_equal(h0, h1)                                   # the reduced histogram is the same everywhere
+    assert np.array_equal(h0 != 0, one.total != 0)
+    assert np.allclose(h0, one.total, rtol=1e-12, atol=0)
+    assert np.array_equal(np.load(tmp_path / "tab_r0.npy"), np.load(tmp_path / "tab_r1.npy"))
+    assert (tmp_path / "w2.evalues").read_text() == (tmp_path / "w1.evalues").read_text()
+    assert done1 == samples

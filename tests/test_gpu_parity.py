@@ -499,3 +499,95 @@ def test_compact_transport_gives_identical_results():
     res = eng.ctx.scan_resident(0, job["n_win"])
     assert res["hits"].tobytes() == want["hits"].tobytes()
     eng.close()
+
+
+def test_two_contexts_on_one_device_keep_their_own_models():
+    """The model tables live in per-device __constant__ memory: a context must re-bind its own before every launch
+    (an older context used after a newer one was created, a calibration context next to a scanner, a context that
+    outlives the one created after it)."""
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    seq = synth_sequence(1200, 5)
+    fold = SynthFold(3)
+    a = ScanEngine([load_model(n) for n in MODEL_ORDER], [load_evalues(n) for n in MODEL_ORDER], LN_UNKNOWN)
+    job_a = a.build_job([("s", seq, None)], 150, 75, fold, "", 0.001, LN_CUTOFF)
+    want_a = a.scan_job(job_a)
+    b = ScanEngine([load_model("ARICH_1.0"), load_model("KT_1.0")], [load_evalues("ARICH_1.0"), None], LN_UNKNOWN)
+    job_b = b.build_job([("s", seq, None)], 150, 75, fold, "", 0.001, LN_CUTOFF)
+    want_b = b.scan_job(job_b)
+    assert want_a["tries"] != want_b["tries"]
+    for _ in range(2):                                    # interleaved: each call finds the other context's tables bound
+        got_a = a.scan_job(job_a)
+        assert got_a["tries"] == want_a["tries"] and got_a["hits"].tobytes() == want_a["hits"].tobytes()
+        got_b = b.ctx.scan_resident(0, job_b["n_win"])
+        assert got_b["tries"] == want_b["tries"] and got_b["hits"].tobytes() == want_b["hits"].tobytes()
+    c = ScanEngine([load_model("TGA_1.0")], [None], LN_UNKNOWN)   # a third one, destroyed while the others live on
+    c.scan_job(c.build_job([("s", seq[:300], None)], 150, 75, fold, "", 0.001, LN_CUTOFF))
+    c.close()
+    got_a = a.ctx.scan_resident(0, job_a["n_win"])
+    assert got_a["hits"].tobytes() == want_a["hits"].tobytes()
+    b.close()
+    got_a = a.scan_job(job_a)
+    assert got_a["hits"].tobytes() == want_a["hits"].tobytes()
+    a.close()
+
+
+def test_failed_scan_leaves_no_resident_job_and_refused_models_change_nothing():
+    from rmdetect_b200._native import NativeError
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    seq = synth_sequence(600, 9)
+    eng = ScanEngine([load_model(n) for n in MODEL_ORDER], [None] * 4, LN_UNKNOWN)
+    good = eng.build_job([("s", seq, None)], 150, 75, SynthFold(1), "", 0.001, LN_CUTOFF)
+    want = eng.scan_job(good)
+    bad = dict(good, bpp_p=good["bpp_p"].copy())
+    bad["bpp_p"][5] = -1.0
+    with pytest.raises(NativeError):
+        eng.scan_job(bad)
+    with pytest.raises(NativeError, match="no resident job"):      # not a rescan of half-staged lists
+        eng.ctx.scan_resident(0, good["n_win"])
+    # descriptors that are refused leave models and job as they were
+    eng.ctx.upload(good)
+    flats = list(eng.flats)
+    import copy
+    broken = copy.copy(flats[0])
+    broken.gate_cfg = np.array(flats[0].gate_cfg, dtype=np.int32).copy()
+    broken.gate_cfg[-1] += 5                                         # reaches past the gate pairs
+    with pytest.raises(NativeError):
+        eng.ctx.set_models([broken] + flats[1:])
+    again = eng.ctx.scan_resident(0, good["n_win"])
+    assert again["tries"] == want["tries"] and again["hits"].tobytes() == want["hits"].tobytes()
+    eng.close()
+
+
+def test_window_shorter_than_a_chain_with_the_gate_open():
+    """[0, 0] is tried even when the window is shorter than a chain (lib/scanner.py:137-141); with min_bpp_mean <= 0 the
+    reference would then index past the sequence (IndexError).  Here such a placement counts in tests_all / tests_pairs
+    and yields no hit; no letter beyond the window is read."""
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold
+    eng = ScanEngine([load_model(n) for n in MODEL_ORDER], [None] * 4, LN_UNKNOWN)
+    # the second sequence would supply the letters a stray read would see: a perfect TGA/KT-looking neighbourhood
+    job = eng.build_job([("tiny", "GGA", None), ("next", "GGACUGAAGCCGAUGAGGCGAAACCC" * 3, None)], 150, 75, SynthFold(2), "", 0.0, LN_CUTOFF)
+    res = eng.scan_job(job)
+    assert res["gate_pass"][0].tolist() == [1, 1, 1, 1]
+    assert not np.any(res["hits"]["seq"] == 0)
+    eng.close()
+
+
+def test_tuning_switches_in_the_environment_are_ignored(monkeypatch):
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    seq = synth_sequence(900, 2)
+
+    def run():
+        eng = ScanEngine([load_model(n) for n in MODEL_ORDER], [load_evalues(n) for n in MODEL_ORDER], LN_UNKNOWN)
+        r = eng.scan_job(eng.build_job([("s", seq, None)], 150, 75, SynthFold(8), "", 0.001, LN_CUTOFF))
+        eng.close()
+        return r
+    want = run()
+    for k, v in (("RMD_DEBUG", "1"), ("RMD_TEAMS", "3"), ("RMD_NO_SCREEN", "1"), ("RMD_LOCAL_STACK", "1"),
+                 ("RMD_NO_FUSED_EXPAND", "1"), ("RMD_CTAS_PER_SM", "2")):
+        monkeypatch.setenv(k, v)
+    got = run()
+    assert len(want["hits"]) > 0 and got["hits"].tobytes() == want["hits"].tobytes() and got["n_launches"] == want["n_launches"]

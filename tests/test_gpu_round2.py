@@ -1,0 +1,119 @@
+"""GPU parity at the level of whole result files, full-size inputs and the calibration loop.
+
+* the complete example inputs of BASELINE configs[0] and [1] (lys.seq, lys.stk 49 sequences, rnaselci.stk 26,
+  arich_test.stk 100) from `Scanner.scan` to the BYTES of the `.res` file, against what the reference's own flow
+  (Scanner.scan -> Candidates.filter -> sort -> Results.write) wrote (tests/golden/res_files.json.gz);
+* BASELINE configs[2] at full size (10 Mb): tests_all, tests_pairs, the number of hits before duplicate removal and
+  an order-independent checksum of positions, gap configurations and score bits, against the oracle on all cores;
+* rmd_calibrate_synth against the oracle fed the host twin of the device's sample draw; the calibration loop on the
+  GPU against the reference's `.evalues` file.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from helpers import LN_CUTOFF, LN_UNKNOWN, MODEL_ORDER, Cfg, SeqList, fresh_models, golden, load_evalues, load_model
+
+pytestmark = pytest.mark.gpu
+
+RES_CASES = ["lys_seq_kt", "lys_seq_both_all", "rnasel_seq_all", "rnasel_stk_all", "lys_stk_all", "arich_stk"]
+
+
+@pytest.mark.parametrize("name", RES_CASES)
+def test_result_file_bytes_equal_the_reference(name, tmp_path):
+    from rmdetect_b200.pipeline import ScanSession
+    from rmdetect_b200.scanner import Scanner
+    from rmdetect_b200.synth import SynthFold
+    case = next(c for c in golden("res_files") if c["name"] == name)
+    triples = golden("seqsets")[case["seqset"]]
+    models, evs = fresh_models(case["models"])
+    sc = Scanner(Cfg(models, evs))
+    sc.rna_tools = SynthFold(case["seed"])
+    out = tmp_path / (name + ".res")
+    session = ScanSession(sc, SeqList(triples), str(out), min_score=5.0, min_bpp=0.001, seq_file=case["seq_file"],
+                          both_strands=case["both_strands"], n_sequences=case["n_sequences"])
+    cands, tries = session.run()
+    sc._engine.close()
+    assert tries == case["tries"]
+    keys = [t[0] for t in triples]
+    names = [m.full_name() for m in models]
+    got = [[names.index(c.model.full_name()), keys.index(c.key), c.coords[0], c.chains_pos[0][0], c.chains_pos[1][0],
+            c.score, c.evalue] for c in cands]
+    assert got == case["all"]                                   # every hit of the scan, exact floats
+    assert out.read_text() == case["res"]                       # what rmout / rmfilter / rmcluster will read
+    assert session.saves[0] == ("n", 0) and session.saves[-1][0] == "w"
+
+
+def test_ten_megabases_against_the_oracle():
+    """BASELINE configs[2]: 10 000 000 letters, 133 333 windows, 9.46e9 placements, four models."""
+    from oracle import pyoracle
+    from rmdetect_b200.genome import hit_checksum
+    from rmdetect_b200.gcx import gc_table
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import synth_sequence
+    n, seed = 10_000_000, 20261019
+    models = [load_model(m) for m in MODEL_ORDER]
+    eng = ScanEngine(models, [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    neutral = gc_table({b: math.log(0.25) for b in "ACGU"})
+    n_win, n_bpp, _ = eng.ctx.synth_job(n, 0, seed, seed, 150, 75, 0.001, LN_CUTOFF, neutral)
+    counts = eng.ctx.gc_counts(1)[0][:4]
+    gc = {b: math.log(float(counts[k]) / n) for k, b in enumerate("ACGU")}
+    cls = []
+    for ev in eng.evalues:
+        ev.select_gc(gc)
+        cls.append(ev.selected)
+    eng.ctx.set_gc(gc_table(gc).reshape(1, -1), np.array([cls], dtype=np.int32))
+    eng.ctx.set_return_dropped(True)
+    res = eng.ctx.scan_resident(0, n_win)
+    h = res["hits"]
+    assert len(h) == res["n_raw"]
+    want = pyoracle.bench_scan2(models, synth_sequence(n, seed), 150, 75, 0, n_win, seed, os.cpu_count() or 1, 0.001,
+                                LN_UNKNOWN, LN_CUTOFF, counts=counts)
+    assert res["tries"] == want["tries"] and want["tries"][0] == 9458509687
+    assert res["n_raw"] == want["hits"]
+    assert hit_checksum(0, h["start"], h["p0"], h["p1"], h["model"], h["leaf"], h["score"]) == want["checksum"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["KT_1.0", "GB_1.0", "CL_1.0", "TGA_1.0"])
+def test_device_drawn_calibration_samples_against_the_oracle(name):
+    """rmd_calibrate_synth (the variant bench.py times): its samples are those of the host twin, and its histograms
+    are the oracle's for those samples — same buckets, weights to 1e-9 (different summation order)."""
+    from oracle import pyoracle
+    from rmdetect_b200.calibrate import N_BINS, class_logs
+    from rmdetect_b200.gcx import GC
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import synth_calibration_samples
+    m = load_model(name)
+    L = len(m.nodes)
+    seed, first, n = 20261019, 123457, 40000
+    classes = GC.get_classes(5, 15, 85)
+    cl = class_logs(classes)
+    eng = ScanEngine([m], [None], LN_UNKNOWN)
+    dev = np.zeros((len(classes), N_BINS))
+    ok_a, _ = eng.ctx.calibrate(0, None, cl, LN_CUTOFF, dev, seed=seed, first=first, n=25000, L=L)      # two calls: `first`
+    ok_b, _ = eng.ctx.calibrate(0, None, cl, LN_CUTOFF, dev, seed=seed, first=first + 25000, n=n - 25000, L=L)
+    samples = synth_calibration_samples(seed, first, n, L)
+    host = np.zeros_like(dev)
+    ok_h, _ = eng.ctx.calibrate(0, samples, cl, LN_CUTOFF, host)
+    eng.close()
+    assert ok_a + ok_b == ok_h
+    assert np.array_equal(dev != 0, host != 0) and np.allclose(dev, host, rtol=1e-12, atol=0)
+    want, ok_o = pyoracle.calibrate(pyoracle.OracleModel(m), ["".join("ACGU"[c] for c in row) for row in samples], classes,
+                                    LN_UNKNOWN, LN_CUTOFF, N_BINS)
+    assert ok_o == ok_h
+    assert np.array_equal(dev != 0, want != 0)                  # exactly the reference's score buckets
+    assert np.allclose(dev, want, rtol=1e-9, atol=0)
+
+
+def test_calibration_loop_on_the_gpu_writes_the_reference_file(tmp_path):
+    """calibrate_model end to end on the device (seeded reference sample stream, checkpoints, stop rule)."""
+    from rmdetect_b200.calibrate import calibrate_model
+    for name in ("KT_1.0", "TGA_1.0"):
+        g = golden("calibrate")[name]
+        out = tmp_path / (name + ".evalues")
+        _, _, done = calibrate_model(load_model(name), str(out), samples=g["samples"], seed=g["seed"], log=None)
+        assert done == min(g["samples"], 4 ** len(load_model(name).nodes))
+        assert out.read_text() == g["text"]
