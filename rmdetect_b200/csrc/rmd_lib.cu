@@ -481,8 +481,8 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         int teams = tune_env("RMD_TEAMS") ? atoi(tune_env("RMD_TEAMS")) : 8;
         ctas_new = tune_env("RMD_CTAS_PER_SM") ? std::max(1, atoi(tune_env("RMD_CTAS_PER_SM"))) : 1;
         teams = std::max(1, std::min(teams, SCAN_MAX_THREADS / SCAN_THREADS));
-        tables_in_smem = tables + screens + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctas_new;
-        const size_t fixed = (tables_in_smem ? tables : 0) + screens;
+        tables_in_smem = tables + screens + SCAN_CTA_FIXED + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctas_new;
+        const size_t fixed = (tables_in_smem ? tables : 0) + screens + SCAN_CTA_FIXED;
         while (teams > 1 && fixed + teams * sizeof(FastSmem) > (size_t)smem_max / ctas_new) teams--;
         teams_new = teams;
         scan_smem = fixed + teams * sizeof(FastSmem);

@@ -64,6 +64,9 @@
 #define TAIL_ROW 8
 #endif
 #define STK_SLOTS 3                     // save slots of the scoring engine kept in shared memory (per lane)
+#define NODE_SYM (1u << 29)
+#define NODE_GUARD 0x800800u
+#define SCAN_CTA_FIXED (TRIE_CAP * 8)    // bytes of CTA-wide state in front of the teams' blocks: the gate tries
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
@@ -88,9 +91,14 @@ struct __align__(16) FastSmem {
     int cur_seq;                          // sequence whose GC table is in gc
     uint32_t win_local;                   // window being generated (records are relative to w_base)
     double2 zero2;                       // (0, 0)
-    TrieNode trie[TRIE_CAP];
+    // per trie node, as the node loop of candidate generation reads it (one 8-byte broadcast load per node):
+    //   x = (ro + 16) | (co + 16) << 12 | pbit << 24 | symmetric << 29      (static)
+    //   y = (n0 - 1 + 0x800) | (hi + 0x800) << 12 | need << 24               (the odometer's ranges in this window,
+    //       lib/scanner.py:161-193; need: a generating value of at least need x min_bpp passes the gate for certain, 255: never)
+    // Two 12-bit fields with a guard bit each (0x800) let one subtraction turn an item into a placement and a second
+    // one test both ranges, see the node loop.
+    uint2 nodew[TRIE_CAP];
     double gc[RMD_N_CODES];
-    uint8_t need[TRIE_CAP];              // per trie node: a generating value of at least need x min_bpp passes the gate for certain
     uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
     uint16_t xnode0[RMD_MAX_MODELS], trie0[RMD_MAX_MODELS], trie_end[RMD_MAX_MODELS];
@@ -175,10 +183,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     // ---- shared memory: the teams' state first (a team's base is team * sizeof(FastSmem)), then the CTA-wide tables.
     // The team's byte offset goes through an opaque move: left to itself the compiler re-derives it from
     // %tid and the kernel parameters in front of most shared-memory accesses (13 % of all instructions).
-    uint32_t sm_off = (uint32_t)team * (uint32_t)sizeof(FastSmem);
+    // The gate tries (static, read by every team) sit once per CTA at the very start: a compile-time address.
+    const TrieNode *const strie = reinterpret_cast<const TrieNode *>(dyn_smem);
+    uint32_t sm_off = (uint32_t)SCAN_CTA_FIXED + (uint32_t)team * (uint32_t)sizeof(FastSmem);
     asm volatile("mov.u32 %0, %0;" : "+r"(sm_off));
     FastSmem &sm = *reinterpret_cast<FastSmem *>(reinterpret_cast<char *>(dyn_smem) + sm_off);
-    const int t_words = (int)(blockDim.x / SCAN_THREADS) * (int)(sizeof(FastSmem) / 16);               // in uint4
+    const int t_words = SCAN_CTA_FIXED / 16 + (int)(blockDim.x / SCAN_THREADS) * (int)(sizeof(FastSmem) / 16);   // in uint4
     const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;
     const int s_words = 2 * J.n_screens;
     uint4 *sx = dyn_smem + t_words;
@@ -208,9 +218,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const int nt = c_models[n_models - 1].trie0 + c_models[n_models - 1].n_trie;
         for (int k = tid; k < nt; k += SCAN_THREADS) {
             const TrieNode tn = c_trie[k];
-            sm.trie[k] = tn;
+            if (team == 0) const_cast<TrieNode *>(strie)[k] = tn;
             const int slots = c_models[tn.model].cfg_begin[c_models[tn.model].n_cfg];
-            sm.need[k] = (uint8_t)min((slots + tn.mult - 1) / max((int)tn.mult, 1), 255);
+            const uint32_t need = (uint32_t)min((slots + tn.mult - 1) / max((int)tn.mult, 1), 255);
+            sm.nodew[k] = make_uint2((uint32_t)(tn.ro + 16) | ((uint32_t)(tn.co + 16) << 12) | ((uint32_t)(tn.pbit & 31) << 24) |
+                                     (c_models[tn.model].symmetric ? NODE_SYM : 0u), need << 24);
         }
     }
     __syncthreads();
@@ -382,6 +394,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                              (M.symmetric ? 1u << 16 : 0u);
         }
         team_sync(team);
+        for (int k = tid; k < sm.trie_end[n_models - 1]; k += SCAN_THREADS) {
+            const uint32_t bd = sm.bounds[strie[k].model];            // n0 | hi << 8 | symmetric << 16, n0 >= 1
+            sm.nodew[k].y = (sm.nodew[k].y & 0xff000000u) | ((bd & 0xffu) - 1u + 0x800u) | ((((bd >> 8) & 0xffu) + 0x800u) << 12);
+        }
         if (tid < FAST_W / 16 + 2) {                          // two-bit letters for the scoring engine
             uint32_t word = 0, other = 0;
             for (int k = 0; k < 16; k++) {
@@ -495,7 +511,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 int cnt = 0;
                 while (__any_sync(FULL_MASK, t < tend)) {
                     if (t < tend) {
-                        const TrieNode tn = sm.trie[t];
+                        const TrieNode tn = strie[t];
                         const double v = lookup(p0 + tn.ro, p1 + tn.co);
                         if (v != 0.0) { sum = __dadd_rn(sum, __dmul_rn(v, (double)tn.mult)); cnt += tn.mult; t++; }
                         else t = tn.skip;
@@ -513,7 +529,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 }
             }
             const uint32_t pmask = __ballot_sync(FULL_MASK, pass);
-            if (pass) { qs[qns + __popc(pmask & lt_mask)] = c; atomicAdd(&sm.gate_pass[m], 1u); }
+            if (pass) {
+                qs[qns + __popc(pmask & lt_mask)] = c;
+                atomicAdd(&sm.gate_pass[m], 1u);      // (one atomic per model through __match_any_sync measured 2 % slower)
+            }
             qns += __popc(pmask);
             __syncwarp();
         };
@@ -627,46 +646,46 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             const uint32_t d = sm.prel[k];
                             if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
                         }
-                    int m = g0 - 1;                               // model of the current trie node
-                    int t = flush ? tg1 : tg0, t1m = t;           // t1m: end of that model's nodes
-                    uint32_t n0 = 0;
+                    if (!valid) PM = 0;                           // a lane without an item never qualifies
+                    // the item's pair as two guarded 12-bit fields, biased by 16 so that subtracting a node's offsets never borrows
+                    const uint32_t ppg = (uint32_t)(er + 16 + 0x800) | ((uint32_t)(ec + 16 + 0x800) << 12);
                     const uint32_t level = (en >> 16) & 0xffu;
-                    int hi = 0;
-                    bool sym = false;
+                    int t = flush ? tg1 : tg0;
                     for (;;) {
-                        // warp-uniform trie nodes, two per step: independent loads and tests keep the pipeline busy
-                        while (t < t1m && ns < 32) {
-                            const bool two = t + 1 < t1m;
-                            const TrieNode ta = sm.trie[t], tb = sm.trie[two ? t + 1 : t];
-                            const int a0 = er - ta.ro, a1 = ec - ta.co, b0p = er - tb.ro, b1p = ec - tb.co;
-                            bool oka = valid && ((PM >> ta.pbit) & 1u) && (uint32_t)a0 < n0;
-                            bool okb = two && valid && ((PM >> tb.pbit) & 1u) && (uint32_t)b0p < n0;
-                            if (sym) {
-                                oka = oka && a1 >= a0 && (a1 <= hi || a1 == a0);
-                                okb = okb && b1p >= b0p && (b1p <= hi || b1p == b0p);
+                        // Warp-uniform trie nodes, two per step (independent loads and tests).  A node turns the item into the
+                        // placement (p0, p1) = (er - ro, ec - co).  With guarded fields: a = ppg - x holds 0x800 + p in each field
+                        // (a guard bit drops when p < 0, nothing borrows across fields), b = a without the guards, and
+                        // c = y - b keeps both of ITS guard bits exactly when 0 <= p0 <= n0 - 1 and 0 <= p1 <= hi.  The bits
+                        // above the fields (parent index, flags, need) only see borrows that go upwards.
+                        while (t < tg1 && ns < 32) {
+                            const bool two = t + 1 < tg1;
+                            const uint2 na = sm.nodew[t], nb = sm.nodew[two ? t + 1 : t];
+                            const uint32_t aa = ppg - na.x, ab = ppg - nb.x;
+                            const uint32_t ba = aa & 0x7ff7ffu, bb = ab & 0x7ff7ffu;
+                            const uint32_t ca = na.y - ba, cb = nb.y - bb;
+                            bool oka = ((PM >> ((na.x >> 24) & 31u)) & 1u);       // (a field with p < 0 leaves b >= 0x7f0: c's guard drops too)
+                            bool okb = two && ((PM >> ((nb.x >> 24) & 31u)) & 1u);
+                            if ((na.x | nb.x) & NODE_SYM) {          // SYMMETRIC (lib/scanner.py:183-188): p1 runs from p0 to max(hi, p0)
+                                const uint32_t a0 = ba & 0xfffu, a1 = ba >> 12, b0p = bb & 0xfffu, b1p = bb >> 12;
+                                const uint32_t ha = ((na.y >> 12) & 0x7ffu), hb = ((nb.y >> 12) & 0x7ffu);
+                                oka = oka && (ca & 0x800u) && ((na.x & NODE_SYM) ? (a1 >= a0 && (a1 <= ha || a1 == a0)) : (ca & 0x800000u) != 0);
+                                okb = okb && (cb & 0x800u) && ((nb.x & NODE_SYM) ? (b1p >= b0p && (b1p <= hb || b1p == b0p)) : (cb & 0x800000u) != 0);
                             } else {
-                                oka = oka && (uint32_t)a1 <= (uint32_t)hi;
-                                okb = okb && (uint32_t)b1p <= (uint32_t)hi;
+                                oka = oka && (~ca & NODE_GUARD) == 0;
+                                okb = okb && (~cb & NODE_GUARD) == 0;
                             }
                             const uint32_t oma = __ballot_sync(FULL_MASK, oka), omb = __ballot_sync(FULL_MASK, okb);
                             if (oma | omb) {
-                                const int na = __popc(oma);
-                                if (oka) s2[ns + __popc(oma & lt_mask)] = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)t << 16) | (level >= sm.need[t] ? 0x80000000u : 0u);
-                                if (okb) s2[ns + na + __popc(omb & lt_mask)] = (uint32_t)b0p | ((uint32_t)b1p << 8) | ((uint32_t)(t + 1) << 16) | (level >= sm.need[t + 1] ? 0x80000000u : 0u);
-                                ns += na + __popc(omb);
+                                const int na_cnt = __popc(oma);
+                                if (oka) s2[ns + __popc(oma & lt_mask)] = ba | ((uint32_t)t << 24) | (level >= (na.y >> 24) ? 0x80000000u : 0u);
+                                if (okb) s2[ns + na_cnt + __popc(omb & lt_mask)] = bb | ((uint32_t)(t + 1) << 24) | (level >= (nb.y >> 24) ? 0x80000000u : 0u);
+                                ns += na_cnt + __popc(omb);
                                 __syncwarp();
                             }
-                            t += two ? 2 : 1;
+                            t += 2;
                         }
                         const bool row_done = flush && t >= tg1;  // the closing pass of the group: whatever is left in s2
-                        if (ns < 32 && !row_done) {
-                            if (t >= tg1) break;
-                            m++;                                  // the next model's nodes begin
-                            const uint32_t bd = sm.bounds[m];
-                            n0 = bd & 0xffu; hi = (int)((bd >> 8) & 0xffu); sym = bd >> 16;
-                            t1m = sm.trie_end[m];
-                            continue;
-                        }
+                        if (ns < 32 && !row_done) break;          // every node has seen this row
                         {
                             // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
                             const int n = min(ns, 32);
@@ -674,16 +693,16 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             const uint32_t it = act ? s2[ns - n + lane] : 0;
                             ns -= n;
                             __syncwarp();
-                            const int p0 = it & 0xff, p1 = (it >> 8) & 0xff;
-                            const TrieNode tn = sm.trie[(it >> 16) & 0x7f];
+                            const int p0 = it & 0xff, p1 = (it >> 12) & 0xff;
+                            const TrieNode tn = strie[(it >> 24) & 0x7f];
                             bool ok = act;
 #ifdef RMD_STATS
                             if (lane == 0) atomicAdd(&O.stats[4], (unsigned long long)n);
 #endif
-                            int a = tn.parent >= 0 ? sm.trie[tn.parent].parent : -1;
+                            int a = tn.parent >= 0 ? strie[tn.parent].parent : -1;
                             while (__any_sync(FULL_MASK, ok && a >= 0)) {  // every pair before it must be non-zero
                                 if (ok && a >= 0) {
-                                    const TrieNode an = sm.trie[a];
+                                    const TrieNode an = strie[a];
                                     ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
                                     a = an.parent;
                                 }
@@ -700,8 +719,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                                     // a trie of two nodes: the first node produces the placement whenever its own pair is big,
                                     // the second one only otherwise (one entry and one node give one placement)
                                     const int t0 = sm.trie0[tn.model];
-                                    if ((int)((it >> 16) & 0x7f) != t0) {
-                                        const TrieNode fn = sm.trie[t0];
+                                    if ((int)((it >> 24) & 0x7f) != t0) {
+                                        const TrieNode fn = strie[t0];
                                         ok = !(lookup(p0 + fn.ro, p1 + fn.co) >= big_min);
                                     }
                                 }
@@ -712,9 +731,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 #ifdef RMD_STATS
                             if (lane == 0) { atomicAdd(&O.stats[6], (unsigned long long)__popc(om)); atomicAdd(&O.stats[7], (unsigned long long)__popc(smask)); }
 #endif
-                            const uint32_t item = (it & 0xffffu) | ((uint32_t)tn.model << 16);
-                            if (sure) { qs[qns + __popc(smask & lt_mask)] = item; atomicAdd(&sm.gate_pass[tn.model], 1u); }
-                            else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
+                            const uint32_t item = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)tn.model << 16);
+                            if (sure) {
+                                qs[qns + __popc(smask & lt_mask)] = item;
+                                atomicAdd(&sm.gate_pass[tn.model], 1u);
+                            } else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
                             qns += __popc(smask);
                             qn1 += __popc(cmask);
                             __syncwarp();
