@@ -294,14 +294,31 @@ def run_ours(args):
         barrier()
         return time.perf_counter() - t1, dev, r
 
-    f64_wall, f64_dev_ms, e = timed_e2e(job)                    # fp64 lists on the wire (12 bytes per entry)
+    f64_wall, f64_dev_ms, e = timed_e2e(job)                    # fp64 lists on the wire (12 bytes per entry), 72-byte hit records back
     assert e["tries"] == tries and len(e["hits"]) == n_hits
+    ctx.set_hit_format(True)                                    # 32-byte hit records on the way back (rmd_hit32)
     e2e_wall, e2e_dev_ms, e = timed_e2e(cjob)                   # compact lists on the wire: the headline e2e
+    ctx.set_hit_format(False)
+    kept = full["hits"][full["hits"]["keep"] != 0]
+    for f in ("window", "p0", "p1", "model", "leaf", "score", "evalue"):
+        assert np.array_equal(e["hits"][f], kept[f]), "e2e hit list differs from the device-resident scan in " + f
     h2d_f64 = codes.nbytes + off.nbytes + n_bpp * (2 + 2 + 8) + 16 * 8 + 4 * 4
     h2d = codes.nbytes + off.nbytes + n_bpp * (2 + 4) + 16 * 8 + 4 * 4
     clocks = sampler.summary()                                  # sampled over both timed regions
     assert e["tries"] == tries and len(e["hits"]) == n_hits
-    d2h = len(e["hits"]) * _native.HIT_DTYPE.itemsize + 2 * n_win * len(models) * 4 + 64
+    d2h = len(e["hits"]) * e["hits"].dtype.itemsize + 2 * n_win * len(models) * 4 + 64
+
+    # ---- what the host can feed: every rank copies a pinned buffer to its GPU at the same time ----------------
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty_like(probe_h, device="cuda")
+    probe_d.copy_(probe_h, non_blocking=True)
+    barrier()
+    t_c = time.perf_counter()
+    for _ in range(8):
+        probe_d.copy_(probe_h, non_blocking=True)
+    barrier()
+    h2d_probe_s = time.perf_counter() - t_c
+    del probe_h, probe_d
 
     # ---- second metric: calibration samples per second (BASELINE.json configs[3], throughput mode) ----
     # every rank scores its own CAL_SAMPLES device-drawn samples per model against the 165 GC classes
@@ -337,15 +354,16 @@ def run_ours(args):
     cal_loop_wall = time.perf_counter() - t3
 
     # ---- reduce over ranks: time = max, work = sum ---------------------------------------------------
-    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall, cal_loop_wall, cal_loop_kernel_ms],
-                     dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall, cal_loop_wall, cal_loop_kernel_ms,
+                      h2d_probe_s], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([n_hits, n_raw, tries[0], tries[1]], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(gathered, cnt)                      # the only collective: small per-rank hit counts
         cnt = torch.stack(gathered).sum(0)
-    wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall, cal_loop_wall, cal_loop_kernel_ms = t.tolist()
+    wall, e2e_wall, dev_ms, e2e_dev_ms, cal_wall, cal_kernel_ms, f64_wall, cal_loop_wall, cal_loop_kernel_ms, h2d_probe_s = t.tolist()
+    h2d_ceiling = 8 * (256 << 20) * world / h2d_probe_s / 1e9    # GB/s, all ranks together
     total_units = units * world
     value = total_units * args.steps / wall
     e2e_value = total_units * args.steps / e2e_wall
@@ -400,7 +418,12 @@ def run_ours(args):
                        "post_kernels_ms": post_ms / args.steps, "bpp_generation_ms": ms_gen},
             "e2e": {"value": e2e_value, "unit": "nt·model/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_wall / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
-                    "api": "rmd_scan (C ABI) on pinned host buffers, bpp lists in the 6-byte transport form (rmd_compact_bpp)",
+                    "api": "rmd_scan (C ABI) on pinned host buffers, bpp lists in the 6-byte transport form (rmd_compact_bpp), "
+                           "hits back as 32-byte records (rmd_set_hit_format)",
+                    "h2d_gbs": h2d * world * args.steps / e2e_wall / 1e9,
+                    "h2d_ceiling_gbs": h2d_ceiling,
+                    "h2d_ceiling_note": "all ranks copying 8 x 256 MB from pinned memory to their GPUs at the same time "
+                                        "(plain cudaMemcpyAsync): what the host can feed; h2d_gbs is what this step asks of it",
                     "fp64_transport": {"value": total_units * args.steps / f64_wall, "h2d_bytes_per_step": int(h2d_f64),
                                        "ms_per_step": 1e3 * f64_wall / args.steps}},
             "calibration": {"metric": "calibration samples scored/sec", "value": CAL_SAMPLES * len(models) * world / cal_wall,

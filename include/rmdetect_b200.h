@@ -125,9 +125,21 @@ typedef struct rmd_hit {
     double prob_model, prob_rand, score, evalue;
 } rmd_hit;
 
+/* The same hit in 32 bytes, for the download (rmd_set_hit_format): what the command line keeps of a hit.  start and
+   wlen follow from `window` and the job's geometry (lib/scanner.py:80-111); prob_model / prob_rand are not carried. */
+typedef struct rmd_hit32 {
+    uint32_t window;            /* index into the job's window list */
+    uint32_t seq;
+    uint16_t p0, p1;            /* window-relative chain pointers */
+    uint8_t model, keep;
+    uint16_t leaf;
+    double score, evalue;
+} rmd_hit32;
+
 typedef struct rmd_scan_result {
     int64_t n_hits;             /* after duplicate removal */
-    const rmd_hit *hits;        /* host memory owned by the context, valid until the next scan call */
+    const void *hits;           /* rmd_hit[n_hits], or rmd_hit32[n_hits] when hit_bytes == 32; host memory owned by the
+                                   context, valid until the next scan call */
     int64_t n_raw;              /* before duplicate removal */
     int64_t tries[2];           /* tests_all, tests_pairs */
     const uint32_t *gate_pass;  /* [n_win][n_models] tests_pairs per window and model */
@@ -137,6 +149,7 @@ typedef struct rmd_scan_result {
     float ms_h2d, ms_d2h;
     float ms_total;             /* device time of the whole call, first enqueue to last copy (CUDA events) */
     int32_t n_launches;         /* kernels launched by this call */
+    int32_t hit_bytes;          /* sizeof(rmd_hit) or sizeof(rmd_hit32) */
 } rmd_scan_result;
 
 int rmd_create(int device, rmd_ctx **out);
@@ -164,6 +177,8 @@ int rmd_set_return_dropped(rmd_ctx *ctx, int enable);
    command line's own filter (rmdetect.py:44 -> lib/candidates.py:78-97, --min-score, default 5.0) moved in front of
    the copy; the Scanner drop-in leaves it off because the reference's callbacks see unfiltered candidates. */
 int rmd_set_min_score(rmd_ctx *ctx, int enable, double min_score);
+/* compact != 0: scans return rmd_hit32 records (less than half the bytes on the way back); default 0 */
+int rmd_set_hit_format(rmd_ctx *ctx, int compact);
 /* Prefix screens (an optimisation with no effect on results): for sequences of at least min_windows windows the
    library tabulates, per sequence, which letter combinations let the first levels of each search tree survive
    (lib/node.py:176-248 evaluated for every combination with the sequence's GC table), and skips the tree walk of

@@ -46,16 +46,19 @@ class ScanResult(C.Structure):
     _fields_ = [("n_hits", C.c_int64), ("hits", C.c_void_p), ("n_raw", C.c_int64),
                 ("tries", C.c_int64 * 2), ("gate_pass", C.c_void_p), ("raw_count", C.c_void_p),
                 ("ms_scan", C.c_float), ("ms_post", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_total", C.c_float), ("n_launches", C.c_int32)]
+                ("ms_total", C.c_float), ("n_launches", C.c_int32), ("hit_bytes", C.c_int32)]
 
 
 HIT_DTYPE = np.dtype([("window", "<i8"), ("start", "<i8"), ("seq", "<i4"), ("wlen", "<i4"),
                       ("p0", "<i4"), ("p1", "<i4"), ("model", "<i2"), ("leaf", "<i2"), ("keep", "<i4"),
                       ("prob_model", "<f8"), ("prob_rand", "<f8"), ("score", "<f8"), ("evalue", "<f8")])
 assert HIT_DTYPE.itemsize == 72
+HIT32_DTYPE = np.dtype([("window", "<u4"), ("seq", "<u4"), ("p0", "<u2"), ("p1", "<u2"), ("model", "u1"), ("keep", "u1"),
+                        ("leaf", "<u2"), ("score", "<f8"), ("evalue", "<f8")])        # rmd_hit32: the download form
+assert HIT32_DTYPE.itemsize == 32
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
-           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
+           "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_hit_format", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
            "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
 
@@ -85,6 +88,7 @@ def load_library():
     L.rmd_set_gc.argtypes = [vp, vp, vp]
     L.rmd_set_return_dropped.argtypes = [vp, C.c_int]
     L.rmd_set_min_score.argtypes = [vp, C.c_int, f64]
+    L.rmd_set_hit_format.argtypes = [vp, C.c_int]
     L.rmd_set_screen_policy.argtypes = [vp, i64]
     L.rmd_scan_resident.argtypes = [vp, i64, i64, C.POINTER(ScanResult)]
     L.rmd_scan.argtypes = [vp, C.POINTER(ScanInput), C.POINTER(ScanResult)]
@@ -215,7 +219,7 @@ class Context:
             arr = np.frombuffer(buf, dtype=dtype, count=count)
             return arr.copy() if copy else arr
         ng = n_win * self.n_models
-        hits = view(res.hits, res.n_hits, HIT_DTYPE)
+        hits = view(res.hits, res.n_hits, HIT32_DTYPE if res.hit_bytes == 32 else HIT_DTYPE)
         gate = view(res.gate_pass, ng, np.uint32).reshape(n_win, self.n_models)
         raw = view(res.raw_count, ng, np.uint32).reshape(n_win, self.n_models)
         return dict(hits=hits, tries=[res.tries[0], res.tries[1]], gate_pass=gate, raw_count=raw, n_raw=res.n_raw,
@@ -322,6 +326,11 @@ class Context:
         callbacks see them (lib/scanner.py:99-109 runs before :53)."""
         self._check(self.lib.rmd_set_return_dropped(self.h, 1 if enable else 0), "rmd_set_return_dropped")
 
+    def set_hit_format(self, compact):
+        """compact=True: scans return HIT32_DTYPE records (window, seq, p0, p1, model, keep, leaf, score, evalue: 32
+        bytes instead of 72 on the way back); `expand_hits` rebuilds start / wlen from the job's geometry."""
+        self._check(self.lib.rmd_set_hit_format(self.h, 1 if compact else 0), "rmd_set_hit_format")
+
     def set_min_score(self, min_score):
         """Drop hits with score <= min_score on the device (reference rmdetect.py:44); None switches the filter off."""
         self._check(self.lib.rmd_set_min_score(self.h, 0 if min_score is None else 1, 0.0 if min_score is None else float(min_score)),
@@ -365,6 +374,33 @@ class Context:
         self._check(self.lib.rmd_download_job(self.h, off.ctypes.data, i.ctypes.data, j.ctypes.data, p.ctypes.data),
                     "rmd_download_job")
         return off, i, j, p
+
+
+def expand_hits(h32, seq_off, win_len, win_step):
+    """HIT_DTYPE records from the 32-byte download form: `start` and `wlen` follow from the window index and the job's
+    geometry (reference lib/scanner.py:80-111); prob_model / prob_rand are not carried (NaN)."""
+    seq_off = np.asarray(seq_off, dtype=np.int64)
+    lens = np.diff(seq_off)
+    if win_len == 0 or win_step == 0:
+        n_win = np.ones(len(lens), dtype=np.int64)
+    else:
+        n_win = np.where(lens <= win_len, 1, 1 + -(-(lens - win_len) // max(win_step, 1)))
+    base = np.concatenate([[0], np.cumsum(n_win)])
+    out = np.zeros(len(h32), dtype=HIT_DTYPE)
+    seq = h32["seq"].astype(np.int64)
+    k = h32["window"].astype(np.int64) - base[seq]
+    if win_len == 0 or win_step == 0:
+        start = np.zeros(len(h32), dtype=np.int64)
+        wlen = lens[seq]
+    else:
+        last = k == n_win[seq] - 1
+        start = np.where(last, np.maximum(lens[seq] - win_len, 0), k * win_step)
+        wlen = np.minimum(lens[seq] - start, win_len)
+    out["window"], out["start"], out["seq"], out["wlen"] = h32["window"], start, seq, wlen
+    for f in ("p0", "p1", "model", "leaf", "keep", "score", "evalue"):
+        out[f] = h32[f]
+    out["prob_model"] = out["prob_rand"] = np.nan
+    return out
 
 
 def compact_bpp(i, j, p, pinned=False):

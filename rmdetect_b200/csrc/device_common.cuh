@@ -54,6 +54,18 @@ __constant__ int c_n_prel;
 __constant__ unsigned char c_groups[RMD_MAX_MODELS + 1];   // candidate generation handles models [c_groups[g], c_groups[g + 1]) together
 __constant__ int c_n_groups;
 
+// The trie nodes of a group again, in the order candidate generation visits them: the group's root nodes (first pairs
+// of configurations: they need no parent test and go straight to the duplicate test), then the others.
+//   x    = (ro + 16) | (co + 16) << 12 | pbit << 24 | symmetric << 29     (see the node loop in scan_kernels.cuh)
+//   info = trie node | grandparent << 7 (0x7f: none) | model << 14 | (duplicate bitmap + 1) << 18 |
+//          second << 20 (a node other than the first of a trie that has no bitmap) | first node of the model's trie << 21
+struct CandNode { uint32_t x, info; };
+__constant__ CandNode c_cand[TRIE_CAP];
+__constant__ uint32_t c_ancw[TRIE_CAP];                    // per TRIE node: ro | co << 12 | parent << 24 (0x7f: none)
+__constant__ unsigned char c_cgrp[RMD_MAX_MODELS + 1][4];  // per group: first candidate index, end of its roots, end of the group
+#define NODE_SYM (1u << 29)
+#define NODE_GUARD 0x800800u
+
 // Search-tree node as the scoring engine reads it (32 bytes, built by rmd_set_models from
 // rmd_tree_node; all models concatenated, indices absolute).  The engine keeps the 16 letters from
 // p0 on and the 16 letters from p1 on as one 64-bit word, two bits per letter; a letter selector is the

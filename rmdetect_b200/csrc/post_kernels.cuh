@@ -155,6 +155,19 @@ __global__ void compact_hits_kernel(const rmd_hit *hits, long long n, const uint
     if (i < n && keep[i]) out[keep_off[i]] = hits[i];
 }
 
+// the download form of a hit list (rmd_set_hit_format)
+__global__ void pack_hits32_kernel(const rmd_hit *hits, long long n, rmd_hit32 *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const rmd_hit h = hits[i];
+    rmd_hit32 o;
+    o.window = (uint32_t)h.window; o.seq = (uint32_t)h.seq;
+    o.p0 = (uint16_t)h.p0; o.p1 = (uint16_t)h.p1;
+    o.model = (uint8_t)h.model; o.keep = (uint8_t)h.keep; o.leaf = (uint16_t)h.leaf;
+    o.score = h.score; o.evalue = h.evalue;
+    out[i] = o;
+}
+
 // ---- compact bpp transport -> the coordinate lists the scan reads (see rmd_compact_bpp) --------------
 // p = (q / 1e9)^2 moved by c - 1 ulps (c = top two bits): exactly the double the caller held.
 __global__ void expand_bpp_kernel(const uint16_t *ij, const uint32_t *q, long long n, uint16_t *oi, uint16_t *oj, double *op) {

@@ -46,6 +46,9 @@ struct SymbolTables {              // host copies of the __constant__ tables oth
     int n_groups;
     ScreenBuild build[SCREEN_CAP];
     ScreenDesc desc[SCREEN_CAP];
+    CandNode cand[TRIE_CAP];
+    uint32_t ancw[TRIE_CAP];
+    unsigned char cgrp[RMD_MAX_MODELS + 1][4];
 };
 
 struct DBuf {                      // grow-only device buffer
@@ -96,8 +99,10 @@ struct rmd_ctx {
     DBuf d_flag, d_counts, d_bpp_cnt, d_bpp_ij, d_bpp_q;      // d_bpp_ij / d_bpp_q: compact transport staging
     // scan outputs
     DBuf d_raw, d_counters, d_gate_pass, d_group_hits, d_group_off, d_scan_sums, d_final, d_keep, d_keep_off, d_compact;
-    rmd_hit *h_hits = nullptr;
+    rmd_hit *h_hits = nullptr;          // pinned; holds rmd_hit32 records when compact_hits
     size_t h_hits_cap = 0;
+    bool compact_hits = false;          // rmd_set_hit_format
+    DBuf d_pack;
     uint32_t *h_gate = nullptr, *h_group = nullptr;
     size_t h_gate_cap = 0;
     long long raw_cap = 0;
@@ -183,7 +188,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
     DBuf *bufs[] = {&ctx->d_seq_off, &ctx->d_win_base, &ctx->d_codes8, &ctx->d_codes2, &ctx->d_gc_log, &ctx->d_gc_class,
                     &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt, &ctx->d_bpp_ij, &ctx->d_bpp_q,
                     &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
-                    &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact,
+                    &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact, &ctx->d_pack,
                     &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
     for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
@@ -464,6 +469,29 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         groups[++n_groups] = (unsigned char)n_models;
         memcpy(sym.groups, groups, sizeof groups);
         sym.n_groups = n_groups;
+        // candidate order (device_common.cuh: CandNode): per group the root nodes, then the others, each in trie order
+        int k = 0;
+        for (int t = 0; t < trie_total; t++)
+            sym.ancw[t] = (uint32_t)(htrie[t].ro & 0xff) | ((uint32_t)(htrie[t].co & 0xff) << 12) | ((uint32_t)(htrie[t].parent < 0 ? 0x7f : htrie[t].parent) << 24);
+        for (int g = 0; g < n_groups; g++) {
+            const int t0 = hmodels[groups[g]].trie0, t1 = hmodels[groups[g + 1] - 1].trie0 + hmodels[groups[g + 1] - 1].n_trie;
+            sym.cgrp[g][0] = (unsigned char)k;
+            for (int pass = 0; pass < 2; pass++) {
+                for (int t = t0; t < t1; t++) {
+                    const TrieNode &tn = htrie[t];
+                    if ((tn.parent < 0) != (pass == 0)) continue;
+                    const CModel &c = hmodels[tn.model];
+                    if (tn.ro < 0 || tn.co < 0 || tn.ro > 100 || tn.co > 100) return fail(ctx, RMD_E_LIMIT, "model %d: gate pair offset out of range", (int)tn.model);
+                    const int gp = tn.parent < 0 ? 0x7f : (htrie[tn.parent].parent < 0 ? 0x7f : htrie[tn.parent].parent);
+                    CandNode &cn = sym.cand[k++];
+                    cn.x = (uint32_t)(tn.ro + 16) | ((uint32_t)(tn.co + 16) << 12) | ((uint32_t)(tn.pbit & 31) << 24) | (c.symmetric ? NODE_SYM : 0u);
+                    cn.info = (uint32_t)t | ((uint32_t)gp << 7) | ((uint32_t)tn.model << 14) | ((uint32_t)(c.cb_slot + 1) << 18) |
+                              ((c.cb_slot < 0 && t != c.trie0) ? 1u << 20 : 0u) | ((uint32_t)c.trie0 << 21);
+                }
+                if (pass == 0) sym.cgrp[g][1] = (unsigned char)k;
+            }
+            sym.cgrp[g][2] = (unsigned char)k;
+        }
     }
     sym.n_prel = n_prel;
     bool any_brute = prel_overflow;               // too many distinct pair geometries for the candidate filter: exact path
@@ -536,6 +564,9 @@ static int bind_tables(rmd_ctx *ctx) {
     CK(cudaMemcpyToSymbol(c_n_groups, &t.n_groups, sizeof t.n_groups));
     CK(cudaMemcpyToSymbol(c_screen_build, t.build, sizeof t.build));
     CK(cudaMemcpyToSymbol(c_screens, t.desc, sizeof t.desc));
+    CK(cudaMemcpyToSymbol(c_cand, t.cand, sizeof t.cand));
+    CK(cudaMemcpyToSymbol(c_ancw, t.ancw, sizeof t.ancw));
+    CK(cudaMemcpyToSymbol(c_cgrp, t.cgrp, sizeof t.cgrp));
     g_sym_owner[dev] = ctx; g_sym_gen[dev] = ctx->sym_gen;
     return RMD_OK;
 }
@@ -779,6 +810,12 @@ extern "C" int rmd_set_min_score(rmd_ctx *ctx, int enable, double min_score) {
     return RMD_OK;
 }
 
+extern "C" int rmd_set_hit_format(rmd_ctx *ctx, int compact) {
+    if (!ctx) return fail(ctx, RMD_E_INVALID, "rmd_set_hit_format: NULL context");
+    ctx->compact_hits = compact != 0;
+    return RMD_OK;
+}
+
 extern "C" int rmd_set_screen_policy(rmd_ctx *ctx, int64_t min_windows) {
     if (!ctx) return fail(ctx, RMD_E_INVALID, "rmd_set_screen_policy: NULL context");
     ctx->screen_min_windows = min_windows;
@@ -1001,7 +1038,16 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     const long long n_out = ctx->return_dropped ? n_raw : (long long)n_keep;
     if ((r = ensure_host(ctx, (size_t)n_out, (size_t)ngroups))) return r;
     CK(cudaEventRecord(ctx->ev[6], st));
-    if (n_out) CK(cudaMemcpyAsync(ctx->h_hits, ctx->return_dropped ? ctx->d_final.p : ctx->d_compact.p, sizeof(rmd_hit) * n_out, cudaMemcpyDeviceToHost, st));
+    const void *d_list = ctx->return_dropped ? ctx->d_final.p : ctx->d_compact.p;
+    size_t hit_bytes = sizeof(rmd_hit);
+    if (ctx->compact_hits && n_out) {
+        RESERVE(ctx->d_pack, sizeof(rmd_hit32) * (size_t)n_out);
+        pack_hits32_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>((const rmd_hit *)d_list, n_out, (rmd_hit32 *)ctx->d_pack.p);
+        launches++;
+        d_list = ctx->d_pack.p;
+    }
+    if (ctx->compact_hits) hit_bytes = sizeof(rmd_hit32);
+    if (n_out) CK(cudaMemcpyAsync(ctx->h_hits, d_list, hit_bytes * n_out, cudaMemcpyDeviceToHost, st));
     if (ngroups) {
         CK(cudaMemcpyAsync(ctx->h_gate, ctx->d_gate_pass.p, sizeof(uint32_t) * ngroups, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ctx->h_group, ctx->d_group_hits.p, sizeof(uint32_t) * ngroups, cudaMemcpyDeviceToHost, st));
@@ -1012,6 +1058,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     CK(cudaEventElapsedTime(&out->ms_total, ctx->ev[8], ctx->ev[9]));
     out->n_hits = n_out;
     out->hits = ctx->h_hits;
+    out->hit_bytes = (int32_t)hit_bytes;
     out->gate_pass = ctx->h_gate;
     out->raw_count = ctx->h_group;
     CK(cudaEventElapsedTime(&out->ms_scan, ctx->ev[0], ctx->ev[1]));

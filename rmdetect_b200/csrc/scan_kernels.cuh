@@ -64,9 +64,7 @@
 #define TAIL_ROW 8
 #endif
 #define STK_SLOTS 3                     // save slots of the scoring engine kept in shared memory (per lane)
-#define NODE_SYM (1u << 29)
-#define NODE_GUARD 0x800800u
-#define SCAN_CTA_FIXED (TRIE_CAP * 8)    // bytes of CTA-wide state in front of the teams' blocks: the gate tries
+#define SCAN_CTA_FIXED (TRIE_CAP * 16)   // bytes of CTA-wide state in front of the teams' blocks: gate tries (8 B per node), cinfo, ancw
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
@@ -91,7 +89,8 @@ struct __align__(16) FastSmem {
     int cur_seq;                          // sequence whose GC table is in gc
     uint32_t win_local;                   // window being generated (records are relative to w_base)
     double2 zero2;                       // (0, 0)
-    // per trie node, as the node loop of candidate generation reads it (one 8-byte broadcast load per node):
+    // per trie node in candidate order (device_common.cuh: c_cand), as candidate generation reads it (one 8-byte
+    // broadcast load per node):
     //   x = (ro + 16) | (co + 16) << 12 | pbit << 24 | symmetric << 29      (static)
     //   y = (n0 - 1 + 0x800) | (hi + 0x800) << 12 | need << 24               (the odometer's ranges in this window,
     //       lib/scanner.py:161-193; need: a generating value of at least need x min_bpp passes the gate for certain, 255: never)
@@ -116,6 +115,13 @@ struct __align__(16) FastSmem {
 __device__ __forceinline__ bool bpp_present(const FastSmem &sm, int wlen, int b1, int b2) {
     const int lo = min(b1, b2), hi = max(b1, b2);
     return lo >= 0 && hi < wlen && ((sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u);
+}
+
+// the same for a pair inside the window given as fields b1 | b2 << 12 (the diagonal is never stored)
+__device__ __forceinline__ bool bpp_present_f(const FastSmem &sm, uint32_t f) {
+    const uint32_t b1 = f & 0xfffu, b2 = f >> 12;
+    const uint32_t lo = min(b1, b2), hi = max(b1, b2);
+    return (sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u;
 }
 
 // bpp lookup by popcount rank: 0.0 unless the pair is stored
@@ -185,6 +191,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     // %tid and the kernel parameters in front of most shared-memory accesses (13 % of all instructions).
     // The gate tries (static, read by every team) sit once per CTA at the very start: a compile-time address.
     const TrieNode *const strie = reinterpret_cast<const TrieNode *>(dyn_smem);
+    const uint32_t *const cinfo = reinterpret_cast<const uint32_t *>(dyn_smem) + TRIE_CAP * 2;   // CandNode::info, candidate order
+    const uint32_t *const ancw = cinfo + TRIE_CAP;                                               // c_ancw, trie order
     uint32_t sm_off = (uint32_t)SCAN_CTA_FIXED + (uint32_t)team * (uint32_t)sizeof(FastSmem);
     asm volatile("mov.u32 %0, %0;" : "+r"(sm_off));
     FastSmem &sm = *reinterpret_cast<FastSmem *>(reinterpret_cast<char *>(dyn_smem) + sm_off);
@@ -217,12 +225,16 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         // need = ceil(slots / mult) passes for certain; the factor covers the roundings.  255: never.
         const int nt = c_models[n_models - 1].trie0 + c_models[n_models - 1].n_trie;
         for (int k = tid; k < nt; k += SCAN_THREADS) {
-            const TrieNode tn = c_trie[k];
-            if (team == 0) const_cast<TrieNode *>(strie)[k] = tn;
+            const CandNode cn = c_cand[k];
+            const TrieNode tn = c_trie[cn.info & 0x7fu];
+            if (team == 0) {
+                const_cast<TrieNode *>(strie)[k] = c_trie[k];
+                const_cast<uint32_t *>(cinfo)[k] = cn.info;
+                const_cast<uint32_t *>(ancw)[k] = c_ancw[k];
+            }
             const int slots = c_models[tn.model].cfg_begin[c_models[tn.model].n_cfg];
             const uint32_t need = (uint32_t)min((slots + tn.mult - 1) / max((int)tn.mult, 1), 255);
-            sm.nodew[k] = make_uint2((uint32_t)(tn.ro + 16) | ((uint32_t)(tn.co + 16) << 12) | ((uint32_t)(tn.pbit & 31) << 24) |
-                                     (c_models[tn.model].symmetric ? NODE_SYM : 0u), need << 24);
+            sm.nodew[k] = make_uint2(cn.x, need << 24);
         }
     }
     __syncthreads();
@@ -395,7 +407,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         }
         team_sync(team);
         for (int k = tid; k < sm.trie_end[n_models - 1]; k += SCAN_THREADS) {
-            const uint32_t bd = sm.bounds[strie[k].model];            // n0 | hi << 8 | symmetric << 16, n0 >= 1
+            const uint32_t bd = sm.bounds[(cinfo[k] >> 14) & 15u];    // n0 | hi << 8 | symmetric << 16, n0 >= 1
             sm.nodew[k].y = (sm.nodew[k].y & 0xff000000u) | ((bd & 0xffu) - 1u + 0x800u) | ((((bd >> 8) & 0xffu) + 0x800u) << 12);
         }
         if (tid < FAST_W / 16 + 2) {                          // two-bit letters for the scoring engine
@@ -593,14 +605,13 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             const int n_groups = c_n_groups;
             int nl = 0, ns = 0;                                  // warp-uniform fills of wl and s2
             for (int grp = 0; grp < n_groups; grp++) {
-                const int g0 = c_groups[grp], g1 = c_groups[grp + 1];
                 if (grp > 0) {                                   // bitmaps of the next group of models
                     team_sync(team);
                     for (int k = tid; k < CB_SLOTS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
                     if (tid == 0) sm.chunk_ctr[(grp + 1) & 1] = 0;
                     team_sync(team);
                 }
-                const int tg0 = sm.trie0[g0], tg1 = sm.trie_end[g1 - 1];   // the group's trie nodes are contiguous
+                const int kb = c_cgrp[grp][0], ke = c_cgrp[grp][2];      // the group's nodes in candidate order
                 const bool last_group = grp + 1 == n_groups;
                 for (bool more = true;;) {
                     // rows shrink towards the end of the list so that the four warps finish together
@@ -640,107 +651,101 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     __syncwarp();
                     const int er = (lane & 1) ? (int)((en >> 8) & 0xff) : (int)(en & 0xff);
                     const int ec = (lane & 1) ? (int)(en & 0xff) : (int)((en >> 8) & 0xff);
-                    uint32_t PM = 0x80000000u;                    // which parent-relative pairs are present (bit 31: no parent)
-                    if (!flush)
+                    uint32_t PM = valid ? 0x80000000u : 0u;       // which parent-relative pairs are present (bit 31: no parent; no item: none)
+                    if (!flush && valid)
                         for (int k = 0; k < n_prel; k++) {
                             const uint32_t d = sm.prel[k];
                             if (bpp_present(sm, wlen, er + (int)(int8_t)(d & 0xff), ec + (int)(int8_t)(d >> 8))) PM |= 1u << k;
                         }
-                    if (!valid) PM = 0;                           // a lane without an item never qualifies
                     // the item's pair as two guarded 12-bit fields, biased by 16 so that subtracting a node's offsets never borrows
                     const uint32_t ppg = (uint32_t)(er + 16 + 0x800) | ((uint32_t)(ec + 16 + 0x800) << 12);
                     const uint32_t level = (en >> 16) & 0xffu;
-                    int t = flush ? tg1 : tg0;
+                    // A node turns the item into the placement (p0, p1) = (er - ro, ec - co).  With guarded fields: ppg - x holds
+                    // 0x800 + p in each field (nothing borrows across fields), b = that without the guard bits (a negative p
+                    // leaves b >= 0x7f0), and c = y - b keeps both of ITS guard bits exactly when 0 <= p0 <= n0 - 1 and
+                    // 0 <= p1 <= hi.  The bits above the fields (parent index, flags, need) only see borrows that go upwards.
+                    auto in_range = [&](const uint2 nw, const uint32_t b) {
+                        const uint32_t c = nw.y - b;
+                        if (nw.x & NODE_SYM) {                    // SYMMETRIC (lib/scanner.py:183-188): p1 runs from p0 to max(hi, p0)
+                            const uint32_t q0 = b & 0xfffu, q1 = b >> 12, hi = (nw.y >> 12) & 0x7ffu;
+                            return (c & 0x800u) && q1 >= q0 && (q1 <= hi || q1 == q0);
+                        }
+                        return (~c & NODE_GUARD) == 0;
+                    };
+                    int k = flush ? ke : kb;
                     for (;;) {
-                        // Warp-uniform trie nodes, two per step (independent loads and tests).  A node turns the item into the
-                        // placement (p0, p1) = (er - ro, ec - co).  With guarded fields: a = ppg - x holds 0x800 + p in each field
-                        // (a guard bit drops when p < 0, nothing borrows across fields), b = a without the guards, and
-                        // c = y - b keeps both of ITS guard bits exactly when 0 <= p0 <= n0 - 1 and 0 <= p1 <= hi.  The bits
-                        // above the fields (parent index, flags, need) only see borrows that go upwards.
-                        while (t < tg1 && ns < 32) {
-                            const bool two = t + 1 < tg1;
-                            const uint2 na = sm.nodew[t], nb = sm.nodew[two ? t + 1 : t];
-                            const uint32_t aa = ppg - na.x, ab = ppg - nb.x;
-                            const uint32_t ba = aa & 0x7ff7ffu, bb = ab & 0x7ff7ffu;
-                            const uint32_t ca = na.y - ba, cb = nb.y - bb;
-                            bool oka = ((PM >> ((na.x >> 24) & 31u)) & 1u);       // (a field with p < 0 leaves b >= 0x7f0: c's guard drops too)
+                        // Warp-uniform nodes, two per step (independent loads and tests): a (item, node) pair is kept when the
+                        // node's parent pair is present (a root has none) and the placement lies in the odometer's range.  The
+                        // pairs of a row are compacted into s2 and go on in full batches of 32: a stage that took every root
+                        // node's placements straight from the row, skipping the queue, ran with 18 of 32 lanes and was 2 % slower.
+                        while (k < ke && ns < 32) {
+                            const bool two = k + 1 < ke;
+                            const uint2 na = sm.nodew[k], nb = sm.nodew[two ? k + 1 : k];
+                            const uint32_t ba = (ppg - na.x) & 0x7ff7ffu, bb = (ppg - nb.x) & 0x7ff7ffu;
+                            bool oka = ((PM >> ((na.x >> 24) & 31u)) & 1u);
                             bool okb = two && ((PM >> ((nb.x >> 24) & 31u)) & 1u);
-                            if ((na.x | nb.x) & NODE_SYM) {          // SYMMETRIC (lib/scanner.py:183-188): p1 runs from p0 to max(hi, p0)
-                                const uint32_t a0 = ba & 0xfffu, a1 = ba >> 12, b0p = bb & 0xfffu, b1p = bb >> 12;
-                                const uint32_t ha = ((na.y >> 12) & 0x7ffu), hb = ((nb.y >> 12) & 0x7ffu);
-                                oka = oka && (ca & 0x800u) && ((na.x & NODE_SYM) ? (a1 >= a0 && (a1 <= ha || a1 == a0)) : (ca & 0x800000u) != 0);
-                                okb = okb && (cb & 0x800u) && ((nb.x & NODE_SYM) ? (b1p >= b0p && (b1p <= hb || b1p == b0p)) : (cb & 0x800000u) != 0);
+                            if ((na.x | nb.x) & NODE_SYM) {       // rare: one test for the pair of nodes
+                                oka = oka && in_range(na, ba);
+                                okb = okb && in_range(nb, bb);
                             } else {
-                                oka = oka && (~ca & NODE_GUARD) == 0;
-                                okb = okb && (~cb & NODE_GUARD) == 0;
+                                oka = oka && (~(na.y - ba) & NODE_GUARD) == 0;
+                                okb = okb && (~(nb.y - bb) & NODE_GUARD) == 0;
                             }
                             const uint32_t oma = __ballot_sync(FULL_MASK, oka), omb = __ballot_sync(FULL_MASK, okb);
                             if (oma | omb) {
                                 const int na_cnt = __popc(oma);
-                                if (oka) s2[ns + __popc(oma & lt_mask)] = ba | ((uint32_t)t << 24) | (level >= (na.y >> 24) ? 0x80000000u : 0u);
-                                if (okb) s2[ns + na_cnt + __popc(omb & lt_mask)] = bb | ((uint32_t)(t + 1) << 24) | (level >= (nb.y >> 24) ? 0x80000000u : 0u);
+                                if (oka) s2[ns + __popc(oma & lt_mask)] = ba | ((uint32_t)k << 24) | (level >= (na.y >> 24) ? 0x80000000u : 0u);
+                                if (okb) s2[ns + na_cnt + __popc(omb & lt_mask)] = bb | ((uint32_t)(k + 1) << 24) | (level >= (nb.y >> 24) ? 0x80000000u : 0u);
                                 ns += na_cnt + __popc(omb);
                                 __syncwarp();
                             }
-                            t += 2;
+                            k += 2;
                         }
-                        const bool row_done = flush && t >= tg1;  // the closing pass of the group: whatever is left in s2
+                        const bool row_done = flush && k >= ke;   // the closing pass of the group: whatever is left in s2
                         if (ns < 32 && !row_done) break;          // every node has seen this row
-                        {
-                            // (placement, node) pairs whose parent pair is present: remaining ancestors, duplicates, queues
-                            const int n = min(ns, 32);
-                            const bool act = lane < n;
-                            const uint32_t it = act ? s2[ns - n + lane] : 0;
-                            ns -= n;
-                            __syncwarp();
-                            const int p0 = it & 0xff, p1 = (it >> 12) & 0xff;
-                            const TrieNode tn = strie[(it >> 24) & 0x7f];
-                            bool ok = act;
-#ifdef RMD_STATS
-                            if (lane == 0) atomicAdd(&O.stats[4], (unsigned long long)n);
-#endif
-                            int a = tn.parent >= 0 ? strie[tn.parent].parent : -1;
-                            while (__any_sync(FULL_MASK, ok && a >= 0)) {  // every pair before it must be non-zero
-                                if (ok && a >= 0) {
-                                    const TrieNode an = strie[a];
-                                    ok = bpp_present(sm, wlen, p0 + an.ro, p1 + an.co);
-                                    a = an.parent;
-                                }
+                        const int n = min(ns, 32);
+                        bool ok = lane < n;
+                        const uint32_t it = ok ? s2[ns - n + lane] : 0;
+                        ns -= n;
+                        __syncwarp();
+                        const uint32_t plc = it & 0xffffffu;      // placement p0 | p1 << 12
+                        bool sure = it >> 31;
+                        const uint32_t info = cinfo[(it >> 24) & 0x7fu];   // CandNode::info of the node that made it
+                        // every pair before the parent must be non-zero too (the reference's `break`)
+                        uint32_t a = (info >> 7) & 0x7fu;
+                        while (__any_sync(FULL_MASK, ok && a != 0x7fu)) {
+                            if (ok && a != 0x7fu) {
+                                const uint32_t w = ancw[a];
+                                ok = bpp_present_f(sm, plc + (w & 0xffffffu));
+                                a = w >> 24;
                             }
-#ifdef RMD_STATS
-                            { const uint32_t a1 = __ballot_sync(FULL_MASK, ok); if (lane == 0) atomicAdd(&O.stats[5], (unsigned long long)__popc(a1)); }
-#endif
-                            if (ok) {                                    // a placement is queued once
-                                const int slot = sm.cb_slot[tn.model];
-                                if (slot >= 0) {
-                                    const uint32_t bit = 1u << (p1 & 31);
-                                    ok = !(atomicOr(&sm.CB[slot][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);
-                                } else {
-                                    // a trie of two nodes: the first node produces the placement whenever its own pair is big,
-                                    // the second one only otherwise (one entry and one node give one placement)
-                                    const int t0 = sm.trie0[tn.model];
-                                    if ((int)((it >> 24) & 0x7f) != t0) {
-                                        const TrieNode fn = strie[t0];
-                                        ok = !(lookup(p0 + fn.ro, p1 + fn.co) >= big_min);
-                                    }
-                                }
-                            }
-                            const bool sure = ok && (it >> 31);
-                            const uint32_t om = __ballot_sync(FULL_MASK, ok);
-                            const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
-#ifdef RMD_STATS
-                            if (lane == 0) { atomicAdd(&O.stats[6], (unsigned long long)__popc(om)); atomicAdd(&O.stats[7], (unsigned long long)__popc(smask)); }
-#endif
-                            const uint32_t item = (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)tn.model << 16);
-                            if (sure) {
-                                qs[qns + __popc(smask & lt_mask)] = item;
-                                atomicAdd(&sm.gate_pass[tn.model], 1u);
-                            } else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
-                            qns += __popc(smask);
-                            qn1 += __popc(cmask);
-                            __syncwarp();
-                            consume(row_done && last_group, 0);
                         }
+                        const uint32_t p0 = plc & 0xfffu, p1 = plc >> 12;
+                        if (ok) {                                 // a placement is queued once
+                            const uint32_t slot1 = (info >> 18) & 3u;
+                            if (slot1) {
+                                const uint32_t bit = 1u << (p1 & 31);
+                                ok = !(atomicOr(&sm.CB[slot1 - 1][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);
+                            } else if (info & (1u << 20)) {
+                                // a trie without a bitmap (two nodes): its first node produces the placement whenever that node's
+                                // own pair is big, the other node only otherwise (one entry and one node give one placement)
+                                const uint32_t f = plc + (ancw[(info >> 21) & 0x7fu] & 0xffffffu);
+                                ok = !(lookup((int)(f & 0xfffu), (int)(f >> 12)) >= big_min);
+                            }
+                        }
+                        sure = sure && ok;
+                        const uint32_t om = __ballot_sync(FULL_MASK, ok);
+                        const uint32_t smask = __ballot_sync(FULL_MASK, sure), cmask = om & ~smask;
+                        const uint32_t model = (info >> 14) & 15u;
+                        const uint32_t item = p0 | (p1 << 8) | (model << 16);
+                        if (sure) {
+                            qs[qns + __popc(smask & lt_mask)] = item;
+                            atomicAdd(&sm.gate_pass[model], 1u);
+                        } else if (ok) q1[qn1 + __popc(cmask & lt_mask)] = item;
+                        qns += __popc(smask);
+                        qn1 += __popc(cmask);
+                        __syncwarp();
+                        consume(row_done && last_group, 0);
                         if (row_done) break;
                     }
                     if (flush) break;

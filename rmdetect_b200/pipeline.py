@@ -43,7 +43,7 @@ class ScanSession:
         cands = filter_candidates(cands, min_score=self.min_score)
         if self.fold is not None:
             by_key = {q.key: q.seq for q in self.seqs.sequence_list}
-            cands = compute_bpp(cands, by_key.__getitem__, self.fold)
+            cands = compute_bpp(cands, by_key.__getitem__, self.fold, constraint=self.scanner.config.constraint)
         else:
             for c in cands:
                 if c.bpp is None:

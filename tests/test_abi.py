@@ -41,14 +41,14 @@ def test_struct_layouts_match_the_header(tmp_path):
     import subprocess
     from rmdetect_b200.modelflat import PAIR_DTYPE, TREE_DTYPE
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "%s"\nint main(void) { printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(rmd_scan_result), '
-                   'sizeof(rmd_scan_input), sizeof(rmd_model_desc), sizeof(rmd_hit), sizeof(rmd_tree_node), sizeof(rmd_gate_pair)); return 0; }\n' % HEADER)
+    src.write_text('#include <stdio.h>\n#include "%s"\nint main(void) { printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(rmd_scan_result), '
+                   'sizeof(rmd_scan_input), sizeof(rmd_model_desc), sizeof(rmd_hit), sizeof(rmd_tree_node), sizeof(rmd_gate_pair), sizeof(rmd_hit32)); return 0; }\n' % HEADER)
     exe = tmp_path / "sizes"
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], env=env)
     sizes = [int(t) for t in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(_native.ScanResult), C.sizeof(_native.ScanInput), C.sizeof(_native.ModelDesc),
-                     _native.HIT_DTYPE.itemsize, TREE_DTYPE.itemsize, PAIR_DTYPE.itemsize]
+                     _native.HIT_DTYPE.itemsize, TREE_DTYPE.itemsize, PAIR_DTYPE.itemsize, _native.HIT32_DTYPE.itemsize]
 
 
 def test_version_and_error_text_without_a_context():

@@ -117,3 +117,25 @@ def test_calibration_loop_on_the_gpu_writes_the_reference_file(tmp_path):
         _, _, done = calibrate_model(load_model(name), str(out), samples=g["samples"], seed=g["seed"], log=None)
         assert done == min(g["samples"], 4 ** len(load_model(name).nodes))
         assert out.read_text() == g["text"]
+
+
+def test_compact_hit_records_carry_the_same_hits():
+    """rmd_set_hit_format(1): 32-byte records on the way back; expand_hits rebuilds start / wlen from the geometry."""
+    from rmdetect_b200._native import HIT32_DTYPE, expand_hits
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold, synth_sequence
+    eng = ScanEngine([load_model(m) for m in MODEL_ORDER], [load_evalues(m) for m in MODEL_ORDER], LN_UNKNOWN)
+    seqs = [("a", synth_sequence(2000, 3), None), ("b", synth_sequence(100, 4), None), ("c", synth_sequence(431, 5), None)]
+    for W, step in ((150, 75), (64, 17), (0, 0)):
+        job = eng.build_job(seqs, W, step, SynthFold(6), "", 0.001, LN_CUTOFF)
+        for dropped in (False, True):
+            eng.ctx.set_return_dropped(dropped)
+            eng.ctx.set_hit_format(False)
+            want = eng.scan_job(job)["hits"]
+            eng.ctx.set_hit_format(True)
+            got = eng.scan_job(job)["hits"]
+            assert got.dtype == HIT32_DTYPE and len(got) == len(want) > 0
+            full = expand_hits(got, job["seq_off"], W, step)
+            for f in ("window", "start", "seq", "wlen", "p0", "p1", "model", "leaf", "keep", "score", "evalue"):
+                assert np.array_equal(full[f], want[f]), f
+    eng.close()

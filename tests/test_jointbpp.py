@@ -34,6 +34,27 @@ def test_pairing_and_constraint_pattern_equal_the_reference():
         assert pattern_2d(cand) == rec["pattern"]
 
 
+def test_user_constraint_merged_into_the_pattern():
+    """lib/candidates.py:424-428,440-443: the window's slice of a user constraint joins the module's pairs through
+    merge_pairs; 509 of the 972 recorded cases merge, the others cut a helix in two and fail in the reference as here."""
+    from rmdetect_b200.jointbpp import merge_pairs, pattern_pairs
+    models = [load_model(n) for n in MODELS]
+    merged = failed = 0
+    for rec in golden("patterns_2d"):
+        cand = _hit(rec, models)
+        for con, want, pairs in rec["merged"]:
+            if want is None:
+                with pytest.raises(ValueError):
+                    pattern_2d(cand, con)
+                failed += 1
+            else:
+                assert pattern_2d(cand, con) == want
+                base, _ = pairing_of(cand)
+                assert [list(p) for p in merge_pairs(list(base) + pattern_pairs(con[cand.coords[0]:cand.coords[1]]))] == pairs
+                merged += 1
+    assert (merged, failed) == (509, 463)
+
+
 FAKE = textwrap.dedent('''\
     #!%(python)s
     # stand-in for `RNAfold --noPS -p [-C]`: free energy of the ensemble -10.00, raised by 0.25 per imposed pair and
