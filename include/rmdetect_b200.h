@@ -25,6 +25,7 @@
  *   rmd_eval            lib/node.py:176-277 called directly (rmcalibrate.py:279-281 style)
  *   rmd_calibrate       rmcalibrate.py:35-62,265-295 (sample scoring into weighted histograms)
  *   rmd_calib_*         the same as a session whose histograms stay on the device (rmcalibrate.py:235-298 loop)
+ *   rmd_cpt_counts      lib/bayes.py:69-150 (weighted counts behind rmbuild's conditional probability tables)
  *   rmd_parse_dot_ps    lib/rnatools.py:176-205 (parse_bpprobs: dot.ps text -> base-pair probabilities)
  *   rmd_compact_bpp     no reference counterpart: lossless 6-byte transport form of a bpp entry
  *   rmd_synth_strand    lib/sequences.py:138-143 (reverse complement), applied to the synthetic stream
@@ -218,6 +219,17 @@ int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *class_log, 
 int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n);
 int rmd_calib_device_hist(rmd_ctx *ctx, void **dptr, int64_t *n_doubles);
 int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t *overflow, float *ms_device);
+
+/* rmbuild's CPT estimation (lib/bayes.py:69-150 JointProb counting, driven by lib/model.py:100-137 from rmbuild.py:343-352):
+   rows of an alignment, one letter code (< K) per model node and row.  For every table t = (node column, parent column 0,
+   parent column 1; -1: none) and every row r: cell = l[a] + K * (l[b0] + K * l[b1]) (absent parents count as 0);
+   counts[run[r]][t][cell] += 1 and first_row[t][cell] = min(.., r).  `run` numbers the stretches of rows that share one
+   weight (rows of one alignment), so that the caller can replay the reference's row-by-row float sums exactly; first_row
+   gives the order in which the reference's dicts met their keys.  counts: [n_runs][n_tables][K*K*K] zeroed by the
+   library; first_row: [n_tables][K*K*K], INT32_MAX where a cell never occurs. */
+int rmd_cpt_counts(rmd_ctx *ctx, const uint8_t *letters, int64_t n_rows, int32_t n_cols, int32_t K,
+                   const int32_t *tables /* [n_tables][3] */, int32_t n_tables, const int32_t *run /* [n_rows] */, int32_t n_runs,
+                   uint32_t *counts, int32_t *first_row);
 
 /* synthetic job generated on the device: one sequence of n letters (positions first..first+n-1 of
    the stream keyed by seq_seed), windows per win_len/win_step, stand-in bpp keyed by bpp_seed */

@@ -59,7 +59,7 @@ assert HIT32_DTYPE.itemsize == 32
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
            "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_hit_format", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
-           "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
+           "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_cpt_counts", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
 
 _lib = None
@@ -101,6 +101,7 @@ def load_library():
     L.rmd_calib_add.argtypes = [vp, vp, C.c_uint64, i64, i64]
     L.rmd_calib_device_hist.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.rmd_calib_read.argtypes = [vp, vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.rmd_cpt_counts.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, i32, vp, vp]
     L.rmd_synth_job.argtypes = [vp, i64, i64, C.c_uint64, C.c_uint64, i32, i32, f64, f64, vp, vp,
                                 C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
     L.rmd_synth_strand.argtypes = [vp, i64, i32]
@@ -307,6 +308,18 @@ class Context:
         if ovf.value:
             raise NativeError("calibration score beyond the histogram range (%d bins)" % self._cal_shape[1])
         return hist, n_ok.value, ms.value
+
+    def cpt_counts(self, letters, K, tables, run, n_runs):
+        """(counts [n_runs][n_tables][K^3] uint32, first_row [n_tables][K^3] int32) — include/rmdetect_b200.h: rmd_cpt_counts."""
+        letters = np.ascontiguousarray(letters, dtype=np.uint8)
+        tables = np.ascontiguousarray(tables, dtype=np.int32).reshape(-1, 3)
+        run = np.ascontiguousarray(run, dtype=np.int32)
+        k3 = K ** 3
+        counts = np.zeros((n_runs, len(tables), k3), dtype=np.uint32)
+        first = np.zeros((len(tables), k3), dtype=np.int32)
+        self._check(self.lib.rmd_cpt_counts(self.h, letters.ctypes.data, letters.shape[0], letters.shape[1], K, tables.ctypes.data,
+                                            len(tables), run.ctypes.data, n_runs, counts.ctypes.data, first.ctypes.data), "rmd_cpt_counts")
+        return counts, first
 
     def synth_job(self, n, first, seq_seed, bpp_seed, win_len, win_step, min_bpp_mean, cutoff, gc_log, gc_class=None):
         gc_log = np.ascontiguousarray(gc_log, dtype=np.float64).reshape(1, N_CODES)

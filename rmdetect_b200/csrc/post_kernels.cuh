@@ -246,3 +246,20 @@ __global__ void eval_batch_kernel(int model, const uint8_t *codes, const long lo
     const EvalOut r = eval_placement(M, letter, gc, p0[i], p1[i], cutoff);
     leaf[i] = r.leaf; pm[i] = r.pm; pr[i] = r.pr;
 }
+
+// ---- rmbuild: counts behind the conditional probability tables (lib/bayes.py:109-127) --------------------------
+// one thread per (row, table); cells are counted per run of equally weighted rows, and the first row of every cell is
+// kept (the order in which the reference's dicts meet their keys)
+__global__ void cpt_count_kernel(const uint8_t *letters, long long n_rows, int n_cols, int K, const int *tables, int n_tables,
+                                 const int *run, unsigned int *counts, int *first_row) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * n_tables) return;
+    const long long r = i / n_tables;
+    const int t = (int)(i - r * n_tables);
+    const uint8_t *row = letters + r * n_cols;
+    const int a = tables[3 * t], b0 = tables[3 * t + 1], b1 = tables[3 * t + 2];
+    const int cell = row[a] + K * ((b0 >= 0 ? row[b0] : 0) + K * (b1 >= 0 ? row[b1] : 0));
+    const int k3 = K * K * K;
+    atomicAdd(&counts[((long long)run[r] * n_tables + t) * k3 + cell], 1u);
+    atomicMin(&first_row[(long long)t * k3 + cell], (int)r);
+}

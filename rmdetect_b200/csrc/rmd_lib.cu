@@ -1266,6 +1266,49 @@ extern "C" int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64
     return calibrate_once(ctx, model, nullptr, seed, first, n, L, class_log, n_class, cutoff, hist, n_bins, n_ok, overflow, ms_kernel);
 }
 
+extern "C" int rmd_cpt_counts(rmd_ctx *ctx, const uint8_t *letters, int64_t n_rows, int32_t n_cols, int32_t K,
+                              const int32_t *tables, int32_t n_tables, const int32_t *run, int32_t n_runs,
+                              uint32_t *counts, int32_t *first_row) {
+    if (!ctx || !letters || !tables || !run || !counts || !first_row) return fail(ctx, RMD_E_INVALID, "rmd_cpt_counts: NULL argument");
+    if (n_rows < 1 || n_rows > 0x7fffffff || n_cols < 1 || K < 2 || K > 16 || n_tables < 1 || n_runs < 1)
+        return fail(ctx, RMD_E_INVALID, "rmd_cpt_counts: sizes out of range");
+    const long long k3 = (long long)K * K * K, cells = k3 * n_tables;
+    if (cells * n_runs > (1LL << 24)) return fail(ctx, RMD_E_LIMIT, "rmd_cpt_counts: %lld runs x tables x cells exceed the limit", cells * n_runs);
+    for (int t = 0; t < n_tables; t++)
+        for (int c = 0; c < 3; c++) {
+            const int v = tables[3 * t + c];
+            if (v >= n_cols || (c == 0 && v < 0)) return fail(ctx, RMD_E_INVALID, "rmd_cpt_counts: table %d names column %d", t, v);
+        }
+    for (int64_t r = 0; r < n_rows; r++) {
+        if (run[r] < 0 || run[r] >= n_runs) return fail(ctx, RMD_E_INVALID, "rmd_cpt_counts: row %lld names run %d", (long long)r, run[r]);
+        for (int c = 0; c < n_cols; c++)
+            if (letters[r * n_cols + c] >= K) return fail(ctx, RMD_E_INVALID, "rmd_cpt_counts: letter code %d at row %lld is not below K", letters[r * n_cols + c], (long long)r);
+    }
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    CK(cudaSetDevice(ctx->device));
+    ctx->cal_open = false;                         // shares the scratch buffers
+    cudaStream_t st = ctx->stream;
+    RESERVE(ctx->d_e0, (size_t)n_rows * n_cols);
+    RESERVE(ctx->d_e1, sizeof(int) * 3 * (size_t)n_tables);
+    RESERVE(ctx->d_e2, sizeof(int) * (size_t)n_rows);
+    RESERVE(ctx->d_e3, sizeof(unsigned int) * (size_t)(cells * n_runs));
+    RESERVE(ctx->d_e4, sizeof(int) * (size_t)cells);
+    CK(cudaMemcpyAsync(ctx->d_e0.p, letters, (size_t)n_rows * n_cols, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e1.p, tables, sizeof(int) * 3 * (size_t)n_tables, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_e2.p, run, sizeof(int) * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_e3.p, 0, sizeof(unsigned int) * (size_t)(cells * n_runs), st));
+    CK(cudaMemsetAsync(ctx->d_e4.p, 0x7f, sizeof(int) * (size_t)cells, st));          // 0x7f7f7f7f: larger than any row
+    const long long work = (long long)n_rows * n_tables;
+    cpt_count_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>((const uint8_t *)ctx->d_e0.p, n_rows, n_cols, K, (const int *)ctx->d_e1.p,
+                                                                    n_tables, (const int *)ctx->d_e2.p, (unsigned int *)ctx->d_e3.p, (int *)ctx->d_e4.p);
+    CK(cudaMemcpyAsync(counts, ctx->d_e3.p, sizeof(unsigned int) * (size_t)(cells * n_runs), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(first_row, ctx->d_e4.p, sizeof(int) * (size_t)cells, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (long long c = 0; c < cells; c++) if (first_row[c] == 0x7f7f7f7f) first_row[c] = 0x7fffffff;
+    return RMD_OK;
+}
+
 extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t seq_seed, uint64_t bpp_seed,
                              int32_t win_len, int32_t win_step, double min_bpp_mean, double cutoff,
                              const double *gc_log, const int32_t *gc_class, int64_t *n_win, int64_t *n_bpp, float *ms_generate) {

@@ -439,6 +439,54 @@ def calibrate_checkpoints():
     dump("calibrate_ckpt.json.gz", out)
 
 
+# --------------------------------------------------------------------------- rmbuild's probability tables (round 2)
+def bayes_tables():
+    """lib/bayes.py + lib/model.py:100-147 as rmbuild.py:343-352 drives them, on the reference's own training rows
+    (examples/arich/*/ARICH_1.0.data with the node dependencies of the .def file next to it).  The rows are copied as
+    fixtures (gzip); recorded: every node's `probs` and the PROB block `ModelParser.write` prints for them."""
+    import lib.bayes as ref_bayes
+    from lib.model_parser import ModelParser
+    dst = os.path.join(HERE, "ref_data", "arich_build")
+    os.makedirs(dst, exist_ok=True)
+    out = {}
+    for name in ("two_alignments", "edit_network"):
+        src = REF + "/examples/arich/" + name
+        raw = open(src + "/ARICH_1.0.data", "rb").read()
+        with gzip.GzipFile(os.path.join(dst, name + ".data.gz"), "wb", mtime=0) as fh:
+            fh.write(raw)
+        lines = raw.decode().split("\n")
+        head = lines[0].split("\t")
+        data = []
+        for line in lines[1:]:
+            t = line.split("\t")
+            if len(t) == len(head):
+                row = dict(zip(head, t))
+                row["weight"] = float(row["weight"])
+                data.append(row)
+        os.chdir(src)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            def_model = ModelParser().parse(src + "/ARICH_1.0.def")
+            pmodel = ref_bayes.Model(data)
+            for i, node in enumerate(def_model.nodes):
+                if node.conds is None:
+                    node.probs = def_model.prob_joint(pmodel, "N%d" % i)
+                else:
+                    node.probs = def_model.prob_cond(pmodel, "N%d" % i, ["N%d" % c for c in node.conds])
+            def_model.data_sources = None
+            def_model.ref_seqs = None
+            tmp = "/tmp/golden_build_%s.model" % name
+            ModelParser().write(tmp, def_model)
+        text = open(tmp).read()
+        block = "".join(l + "\n" for l in text.split("\n") if l.startswith("PROB") or l == "")
+        out[name] = dict(rows=len(data), nodes=[[n.id, n.conds] for n in def_model.nodes],
+                         probs={str(n.id): n.probs for n in def_model.nodes},
+                         prob_lines=[l for l in text.split("\n") if l.startswith("PROB")],
+                         shipped_model=open(src + "/arich_1.0.model").read())
+        print("bayes", name, len(data), "rows", len(out[name]["prob_lines"]), "PROB lines")
+    os.system("chmod -R u+w %s" % dst)
+    dump("bayes_tables.json.gz", out)
+
+
 def main():
     only = set(sys.argv[1:])                      # e.g. `make_golden.py res ckpt` regenerates just those parts
     want = lambda part: not only or part in only
@@ -460,6 +508,8 @@ def main():
         res_files(sets)
     if want("ckpt"):
         calibrate_checkpoints()
+    if want("bayes"):
+        bayes_tables()
 
 
 if __name__ == "__main__":
