@@ -26,6 +26,9 @@
  *   rmd_calibrate       rmcalibrate.py:35-62,265-295 (sample scoring into weighted histograms)
  *   rmd_calib_*         the same as a session whose histograms stay on the device (rmcalibrate.py:235-298 loop)
  *   rmd_cpt_counts      lib/bayes.py:69-150 (weighted counts behind rmbuild's conditional probability tables)
+ *   rmd_table_*         lib/candidates.py:78-207 (Candidates.filter / top_model / top_seq / top_seq_model / get_model /
+ *                       nooverlap, Candidate.__cmp__ order) and lib/cluster.py:58-83,98-166,185-203 (first cluster list,
+ *                       the sums and counts of Cluster.calc_metrics) on a hit table that stays on the device
  *   rmd_parse_dot_ps    lib/rnatools.py:176-205 (parse_bpprobs: dot.ps text -> base-pair probabilities)
  *   rmd_compact_bpp     no reference counterpart: lossless 6-byte transport form of a bpp entry
  *   rmd_synth_strand    lib/sequences.py:138-143 (reverse complement), applied to the synthetic stream
@@ -230,6 +233,58 @@ int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t *overflow,
 int rmd_cpt_counts(rmd_ctx *ctx, const uint8_t *letters, int64_t n_rows, int32_t n_cols, int32_t K,
                    const int32_t *tables /* [n_tables][3] */, int32_t n_tables, const int32_t *run /* [n_rows] */, int32_t n_runs,
                    uint32_t *counts, int32_t *first_row);
+
+/* ---- Device-resident hit table: what rmfilter and rmcluster do to a result list, so that genome-scale
+   hit lists never become Python objects.  One table per context.  Rows keep their order unless a call says otherwise;
+   every call that removes rows keeps the survivors in order, as the reference's list comprehensions do. */
+typedef struct rmd_hit_row {    /* 64 bytes */
+    int64_t start;              /* coords[0]: window start within the sequence; coords[1] = start + wlen */
+    int32_t key;                /* caller's sequence id: equal ids <=> equal `key` strings */
+    uint16_t wlen;
+    uint16_t p0, p1;            /* window-relative chain pointers */
+    uint16_t leaf;              /* gap configuration */
+    uint8_t model, flags;
+    uint16_t pad_;
+    double score, evalue;
+    double bpp;                 /* NaN: not computed (the reference's None) */
+    uint32_t letters[3];        /* chain letters in node order (chain 0, then chain 1), 3 bits each: 0..3 ACGU, 4 '.', 5 other */
+    uint32_t id;                /* caller's row id, carried through every operation */
+} rmd_hit_row;
+
+int rmd_table_clear(rmd_ctx *ctx);
+int rmd_table_rows(rmd_ctx *ctx, int64_t *n_rows);
+/* append the hits the last rmd_scan / rmd_scan_resident kept (still on the device): key = key_base + seq,
+   start = start_base + window start (a piece of a longer sequence), letters read from the resident sequence,
+   id = rows appended so far */
+int rmd_table_append_scan(rmd_ctx *ctx, int32_t key_base, int64_t start_base, int64_t *n_rows);
+/* append rows from the host (hits loaded from a .res file) */
+int rmd_table_append_rows(rmd_ctx *ctx, const rmd_hit_row *rows, int64_t n, int64_t *n_rows);
+int rmd_table_download(rmd_ctx *ctx, rmd_hit_row *rows, int64_t first, int64_t n);
+/* lib/candidates.py:78-97 Candidates.filter without its closing sort (rmd_table_sort), and :156-169 get_model: a row stays when
+   score > *min_score, bpp > *min_bpp (a bpp that was never computed fails), evalue != 0 and evalue < *evalue_below — the
+   caller turns `-math.log(evalue) <= min_evalue` into that bound — and model == `model`; NULL / -1: no such test */
+int rmd_table_filter(rmd_ctx *ctx, const double *min_score, const double *min_bpp, const double *evalue_below, int32_t model, int64_t *n_rows);
+/* lib/candidates.py:380-394 Candidate.__cmp__ order, stable: key_rank[key] ascending (rank of the key string among all key
+   strings, equal strings equal ranks), E-value ascending, score descending */
+int rmd_table_sort(rmd_ctx *ctx, const int32_t *key_rank, int32_t n_keys);
+/* lib/candidates.py:99-154 top_model (group 0) / top_seq (1) / top_seq_model (2): sort, then the first top_n rows of every group */
+int rmd_table_top(rmd_ctx *ctx, int32_t group, int32_t top_n, const int32_t *key_rank, int32_t n_keys, int64_t *n_rows);
+/* lib/candidates.py:171-207 nooverlap, replayed in table order (the result depends on it, as the reference's does) */
+int rmd_table_nooverlap(rmd_ctx *ctx, int64_t *n_rows);
+/* lib/cluster.py:185-203: the first cluster list.  Cluster key of a row = (model, column of the first position of chain 0,
+   column of the first position of chain 1); column = cols[col_off[key] + position] (the alignment's column index,
+   lib/candidates.py:489-506) or the position itself when cols is NULL.  Clusters are numbered in the order the table meets
+   their keys; cluster_of[n_rows] receives every row's cluster. */
+int rmd_table_cluster_index(rmd_ctx *ctx, const int64_t *col_off, const int32_t *cols, int32_t n_keys, int32_t *cluster_of, int64_t *n_clusters);
+/* per cluster of the last rmd_table_cluster_index: its key (row, col, model), member count and first row; any pointer may be NULL */
+int rmd_table_cluster_info(rmd_ctx *ctx, int64_t *row, int64_t *col, int32_t *model, int32_t *count, int32_t *first);
+/* lib/cluster.py:58-83,98-166 Cluster.calc_metrics, the part that reads hits: for cluster c with member rows
+   members[off[c] .. off[c + 1]) (in the order of the reference's cluster.cands): sums[c] = (score, bpp) added in that order,
+   n_keys[c] = distinct sequences, counts[c][q][x * 4 + y] = members whose letters at the nodes of the model's q-th PAIRS line
+   (pair_ids[model][q] = (id1, id2), RMD_CL_MAX_PAIRS per model, n_pairs[model] used) are x and y in ACGU order */
+#define RMD_CL_MAX_PAIRS 16
+int rmd_table_cluster_metrics(rmd_ctx *ctx, const int32_t *members, const int64_t *off, int32_t n_clusters,
+                              const uint8_t *pair_ids, const int32_t *n_pairs, double *sums, uint32_t *counts, uint32_t *n_keys);
 
 /* synthetic job generated on the device: one sequence of n letters (positions first..first+n-1 of
    the stream keyed by seq_seed), windows per win_len/win_step, stand-in bpp keyed by bpp_seed */

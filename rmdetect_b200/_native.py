@@ -56,11 +56,19 @@ assert HIT_DTYPE.itemsize == 72
 HIT32_DTYPE = np.dtype([("window", "<u4"), ("seq", "<u4"), ("p0", "<u2"), ("p1", "<u2"), ("model", "u1"), ("keep", "u1"),
                         ("leaf", "<u2"), ("score", "<f8"), ("evalue", "<f8")])        # rmd_hit32: the download form
 assert HIT32_DTYPE.itemsize == 32
+ROW_DTYPE = np.dtype([("start", "<i8"), ("key", "<i4"), ("wlen", "<u2"), ("p0", "<u2"), ("p1", "<u2"), ("leaf", "<u2"),
+                      ("model", "u1"), ("flags", "u1"), ("pad_", "<u2"), ("score", "<f8"), ("evalue", "<f8"), ("bpp", "<f8"),
+                      ("letters", "<u4", (3,)), ("id", "<u4")])                        # rmd_hit_row: the device-resident hit table
+assert ROW_DTYPE.itemsize == 64
+CL_MAX_PAIRS = 16
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
            "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_hit_format", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
            "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_cpt_counts", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
-           "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free"]
+           "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free",
+           "rmd_table_clear", "rmd_table_rows", "rmd_table_append_scan", "rmd_table_append_rows", "rmd_table_download",
+           "rmd_table_filter", "rmd_table_sort", "rmd_table_top", "rmd_table_nooverlap", "rmd_table_cluster_index",
+           "rmd_table_cluster_info", "rmd_table_cluster_metrics"]
 
 _lib = None
 
@@ -111,6 +119,19 @@ def load_library():
     L.rmd_download_job.argtypes = [vp, vp, vp, vp, vp]
     L.rmd_compact_bpp.argtypes = [vp, vp, vp, i64, vp, vp, C.POINTER(i64)]
     L.rmd_parse_dot_ps.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, i64, C.POINTER(i64), C.c_char_p, i64]
+    pi64, pf64 = C.POINTER(i64), C.POINTER(f64)
+    L.rmd_table_clear.argtypes = [vp]
+    L.rmd_table_rows.argtypes = [vp, pi64]
+    L.rmd_table_append_scan.argtypes = [vp, i32, i64, pi64]
+    L.rmd_table_append_rows.argtypes = [vp, vp, i64, pi64]
+    L.rmd_table_download.argtypes = [vp, vp, i64, i64]
+    L.rmd_table_filter.argtypes = [vp, pf64, pf64, pf64, i32, pi64]
+    L.rmd_table_sort.argtypes = [vp, vp, i32]
+    L.rmd_table_top.argtypes = [vp, i32, i32, vp, i32, pi64]
+    L.rmd_table_nooverlap.argtypes = [vp, pi64]
+    L.rmd_table_cluster_index.argtypes = [vp, vp, vp, i32, vp, pi64]
+    L.rmd_table_cluster_info.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rmd_table_cluster_metrics.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.rmd_host_alloc.argtypes = [i64]
     L.rmd_host_alloc.restype = vp
     L.rmd_host_free.argtypes = [vp]

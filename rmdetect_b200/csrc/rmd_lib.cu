@@ -18,6 +18,7 @@
 #include "post_kernels.cuh"
 #include "calib_kernels.cuh"
 #include "synth_kernels.cuh"
+#include "table_kernels.cuh"
 
 static thread_local std::string g_error;
 
@@ -54,6 +55,15 @@ struct SymbolTables {              // host copies of the __constant__ tables oth
 struct DBuf {                      // grow-only device buffer
     void *p = nullptr;
     size_t cap = 0;
+};
+
+// device-resident hit table (rmd_table_*, rmd_table.cuh): rows plus the scratch of its sorts and selections
+struct HitTable {
+    DBuf rows, rows_alt, keys, keys_alt, idx, idx_alt, flag, off, aux32, aux64, hist, hist_off, totals, ranks, bmax;
+    DBuf col_off, cols, grp, cl_info, cl_of_row, members, sums, counts;
+    long long n = 0, n_clusters = 0;
+    uint32_t next_id = 0;
+    int min_key = 0x7fffffff, max_key = -1;        // sequence ids present
 };
 
 struct rmd_ctx {
@@ -114,6 +124,10 @@ struct rmd_ctx {
     // calibration session (rmd_calib_open .. rmd_calib_read): histogram in d_e3, counters in d_e4
     CalibArgs cal{};
     bool cal_open = false, cal_timed = false;
+    // the last scan's kept hits, still on the device (rmd_table_append_scan)
+    const rmd_hit *last_hits = nullptr;
+    long long last_n = 0;
+    HitTable table;
 };
 
 static int fail(rmd_ctx *ctx, int code, const char *fmt, ...) {
@@ -191,6 +205,10 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
                     &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact, &ctx->d_pack,
                     &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
     for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
+    HitTable &T = ctx->table;
+    DBuf *tbufs[] = {&T.rows, &T.rows_alt, &T.keys, &T.keys_alt, &T.idx, &T.idx_alt, &T.flag, &T.off, &T.aux32, &T.aux64, &T.hist, &T.hist_off, &T.totals,
+                     &T.ranks, &T.bmax, &T.col_off, &T.cols, &T.grp, &T.cl_info, &T.cl_of_row, &T.members, &T.sums, &T.counts};
+    for (DBuf *b : tbufs) if (b->p) cudaFree(b->p);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
@@ -1036,6 +1054,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     const long long n_out = ctx->return_dropped ? n_raw : (long long)n_keep;
+    ctx->last_hits = (const rmd_hit *)ctx->d_compact.p; ctx->last_n = (long long)n_keep;      // rmd_table_append_scan
     if ((r = ensure_host(ctx, (size_t)n_out, (size_t)ngroups))) return r;
     CK(cudaEventRecord(ctx->ev[6], st));
     const void *d_list = ctx->return_dropped ? ctx->d_final.p : ctx->d_compact.p;
@@ -1455,3 +1474,5 @@ extern "C" int rmd_download_job(rmd_ctx *ctx, int64_t *bpp_off, uint16_t *i, uin
     }
     return RMD_OK;
 }
+
+#include "rmd_table.cuh"
