@@ -4,7 +4,7 @@
   `Candidates.top_model / top_seq / top_seq_model / get_model / nooverlap` return (tests/golden/filters.json.gz);
 * rmcluster on the same hits for several column limits and list orders: clusters, members in order, metrics and the
   printed summary equal `lib/cluster.py`'s (tests/golden/clusters.json.gz, written by tests/golden/make_clusters.py);
-* a table of 10^6 synthetic rows (ties, dense overlaps) against the host restatement in rmdetect_b200/candidates.py,
+* tables of 3 000 and 200 000 synthetic rows (ties, dense overlaps) against the host restatement in rmdetect_b200/candidates.py,
   which test_filters.py pins on the reference;
 * rows appended straight from a scan equal the Python `Candidate` objects of the same scan.
 """
@@ -210,7 +210,7 @@ def test_rows_appended_from_a_scan_equal_its_candidates():
     from rmdetect_b200.hittable import HitTable
     from rmdetect_b200.scanner import Scanner
     from rmdetect_b200.synth import SynthFold
-    triples = golden("seqsets")["lys_stk"][:12]
+    triples = golden("seqsets")["lys.stk"][:12]
     models, evs = fresh_models(MODEL_ORDER)
     sc = Scanner(Cfg(models, evs))
     sc.rna_tools = SynthFold(5)
