@@ -164,6 +164,8 @@ struct ScanOut {
     long long raw_cap;
     uint32_t *gate_pass;             // [n_win_range][n_models]
     uint32_t *group_hits;            // [n_win_range][n_models]
+    const uint32_t *other_list;      // windows with a letter other than ACGU, relative to the range (scan_fast_kernel<..., OTHER>)
+    const uint32_t *other_count;
 };
 
 __device__ __forceinline__ int get_code(const DevJob &J, long long g) {

@@ -108,6 +108,7 @@ struct rmd_ctx {
     DBuf d_seq_off, d_win_base, d_codes8, d_codes2, d_gc_log, d_gc_class, d_bpp_off, d_bpp_i, d_bpp_j, d_bpp_p;
     DBuf d_flag, d_counts, d_bpp_cnt, d_bpp_ij, d_bpp_q;      // d_bpp_ij / d_bpp_q: compact transport staging
     // scan outputs
+    DBuf d_other;                       // work list of the OTHER launch: window numbers, then their count
     DBuf d_raw, d_counters, d_gate_pass, d_group_hits, d_group_off, d_scan_sums, d_final, d_keep, d_keep_off, d_compact;
     rmd_hit *h_hits = nullptr;          // pinned; holds rmd_hit32 records when compact_hits
     size_t h_hits_cap = 0;
@@ -203,7 +204,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
                     &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt, &ctx->d_bpp_ij, &ctx->d_bpp_q,
                     &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
                     &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact, &ctx->d_pack,
-                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
+                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_other, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
     for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
     HitTable &T = ctx->table;
     DBuf *tbufs[] = {&T.rows, &T.rows_alt, &T.keys, &T.keys_alt, &T.idx, &T.idx_alt, &T.flag, &T.off, &T.aux32, &T.aux64, &T.hist, &T.hist_off, &T.totals,
@@ -535,6 +536,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         if (scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", scan_smem, smem_max);
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -908,7 +910,11 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     // the shared-memory kernel takes windows longer than every chain and up to 160 letters
     const bool use_fast = ctx->max_chain <= 32 && ctx->motif_ok;
     const int min_fast_wlen = use_fast ? ctx->max_chain + 1 : 0x7fffffff;
-    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen || ctx->any_other;
+    // windows with a letter other than ACGU (N runs, IUPAC codes): a second launch of the shared-memory kernel takes them
+    // from a work list; the rare kernel shapes (exact gate, local-memory stack, tables in global memory) leave them to the generic kernel
+    const bool other_fast = use_fast && ctx->any_other && ctx->tables_in_smem && !ctx->local_stack && !(ctx->any_brute || !(J.min_bpp > 0.0));
+    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen || (ctx->any_other && !other_fast);
+    if (other_fast) RESERVE(ctx->d_other, sizeof(uint32_t) * (size_t)(nwin + 2));
     unsigned long long counters[16];
     int launches = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -921,7 +927,14 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         ScanOut O;
         O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.stats = O.raw_count + 8; O.raw_cap = ctx->raw_cap;
         O.gate_pass = (uint32_t *)ctx->d_gate_pass.p; O.group_hits = (uint32_t *)ctx->d_group_hits.p;
+        O.other_list = (const uint32_t *)ctx->d_other.p; O.other_count = O.other_list ? O.other_list + nwin : nullptr;
         CK(cudaEventRecord(ctx->ev[0], st));
+        if (other_fast && nwin > 0) {
+            CK(cudaMemsetAsync((uint32_t *)ctx->d_other.p + nwin, 0, sizeof(uint32_t), st));
+            other_windows_kernel<<<(unsigned)std::min<long long>((nwin + 7) / 8, (long long)ctx->sm_count * 8), 256, 0, st>>>(J, w_begin, w_end, min_fast_wlen, (uint32_t *)ctx->d_other.p,
+                                                                                                                            (uint32_t *)ctx->d_other.p + nwin);
+            launches++;
+        }
         // Chunks of windows whose lists are copied while earlier chunks are scanned.  Every chunk is one launch of
         // the persistent kernel and pays its tail (0.1 ms), and the first must be small so that the scan starts
         // early.  A chunk can start once its copy is complete: with the copy r times faster per window than the
@@ -937,7 +950,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             if (stream_in->bpp_q) {
                 n_chunks = 0;
                 // without expansion launches, and with the chunks' tails overlapping on two streams, a launch costs less
-                const bool will_fuse = use_fast && !need_generic && ctx->tables_in_smem && !ctx->local_stack &&
+                const bool will_fuse = use_fast && !need_generic && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
                                        !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");
                 const int gpct = will_fuse ? 45 : 60;
                 long long end = std::max<long long>(nwin / 128, 2048);
@@ -953,7 +966,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         // chunks then alternate between two compute streams: a launch does not wait for the previous one to end, its
         // CTAs start on the SMs whose persistent CTA has run out of windows.
         if (streaming) {
-            const bool fused = stream_in->bpp_q && use_fast && !need_generic && ctx->tables_in_smem && !ctx->local_stack &&
+            const bool fused = stream_in->bpp_q && use_fast && !need_generic && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
                                !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");     // = will_fuse above
             ctx->job.bpp_ij = fused ? (const uint16_t *)ctx->d_bpp_ij.p : nullptr;
             ctx->job.bpp_q = fused ? (const uint32_t *)ctx->d_bpp_q.p : nullptr;
@@ -995,13 +1008,18 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                 launches++;
             }
             if (need_generic) {
-                scan_generic_kernel<<<(unsigned)((c1 - c0) * J.n_models), GEN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen);
+                scan_generic_kernel<<<(unsigned)((c1 - c0) * J.n_models), GEN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, other_fast ? 1 : 0);
                 launches++;
             }
         }
         if (two_streams) {                                          // join
             CK(cudaEventRecord(ctx->ev[13], ctx->stream2));
             CK(cudaStreamWaitEvent(st, ctx->ev[13], 0));
+        }
+        if (other_fast && nwin > 0) {                               // the windows the launches above skipped; every list is on the device by now
+            scan_fast_kernel<false, true, false, false, true><<<(unsigned)ctx->sm_count * ctx->ctas_per_sm, (unsigned)ctx->teams * SCAN_THREADS, ctx->scan_smem, st>>>(
+                J, w_begin, w_end, w_begin, O, min_fast_wlen, (unsigned int *)ctx->d_next.p + STREAM_CHUNKS);
+            launches++;
         }
         CK(cudaEventRecord(ctx->ev[1], st));
         CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 128, cudaMemcpyDeviceToHost, st));

@@ -107,7 +107,8 @@ struct __align__(16) FastSmem {
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
     uint8_t letters[FAST_W + 16];
-    uint32_t l2[FAST_W / 16 + 2];        // the letters again, two bits each (meaningful when plain)
+    uint32_t l2[FAST_W / 16 + 2];        // the letters again, two bits each (a letter other than ACGU: its code's low bits)
+    uint32_t lo[FAST_W / 32 + 3];        // one bit per letter: it is not one of ACGU (OTHER variant)
     uint32_t plain;                      // every letter of the window is one of ACGU
 };
 
@@ -174,7 +175,12 @@ __device__ __forceinline__ void team_sync(const int team) {
 // LSTK: the model set branches deeper than STK_SLOTS, the engine's save slots go to local memory.
 // FUSED: the job's lists are on the device in the compact transport only (rmd_scan); every team rebuilds the values of
 // its own window while staging it and reads them back with coherent loads.
-template <bool BRUTE, bool TABLES, bool LSTK, bool FUSED = false>
+// OTHER: the launch takes the windows named by O.other_list — those that hold a letter other than ACGU (N runs, IUPAC
+// codes), which the plain launch skips.  Such a letter has its own log-frequency (lib/gcx.py:4-13) and no CPT entry
+// (lib/node.py:215-223: unknown_prob): the engine carries one more bit per letter, reads the letter's code from the
+// window when the bit is set, and finishes its walks before the team leaves the window; placements that touch such a
+// letter bypass the prefix screens, whose tables are indexed by ACGU.
+template <bool BRUTE, bool TABLES, bool LSTK, bool FUSED = false, bool OTHER = false>
 __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
@@ -260,6 +266,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     // so walks in flight carry over into the team's next window: the engine drains only when the sequence
     // changes and at the end of the kernel.
     uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
+    uint32_t e_o = 0;                                   // OTHER: bit k: letter k from p0 on is not ACGU, bit 16 + k: from p1 on
     unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
     int *const s_leaf = &sm.walk_leaf[tid];
     double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0;      // the best leaf's other sum and the walk's window wait in shared memory
@@ -288,6 +295,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     e_t = sm.xnode0[c >> 16];
                     e_m = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
                           ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
+                    if (OTHER) e_o = (__funnelshift_r(sm.lo[p0 >> 5], sm.lo[(p0 >> 5) + 1], p0 & 31u) & 0xffffu) |
+                                     (__funnelshift_r(sm.lo[p1 >> 5], sm.lo[(p1 >> 5) + 1], p1 & 31u) << 16);
                     *s_leaf = -1; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0;    // lib/node.py:250-251 (a hit always stores its own best_pr)
                 }
                 qn2 -= min(qn2, __popc(im));
@@ -302,10 +311,20 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             if (busy) {
                 const uint4 a = xn[2 * e_t];                      // sel, cpt, m0 | m1 << 16, skip | next << 16
                 const uint2 b = *reinterpret_cast<const uint2 *>(xn + 2 * e_t + 1);   // leaf | model << 16 | flags << 24 | bdepth << 28, dlo | dspan << 16
-                const int nt = (a.x & XSEL_OWN_GAP) ? 4 : (int)((uint32_t)(e_m >> (a.x & 63u)) & 3u);          // :199-213
-                const uint32_t c0 = (uint32_t)(e_m >> ((a.x >> 8) & 63u)) & 3u, c1 = (uint32_t)(e_m >> ((a.x >> 16) & 63u)) & 3u;
+                int nt = (a.x & XSEL_OWN_GAP) ? 4 : (int)((uint32_t)(e_m >> (a.x & 63u)) & 3u);          // :199-213
+                uint32_t c0 = (uint32_t)(e_m >> ((a.x >> 8) & 63u)) & 3u, c1 = (uint32_t)(e_m >> ((a.x >> 16) & 63u)) & 3u;
+                int gslot = nt;
+                if (OTHER && e_o) {                                // a letter other than ACGU: CPT column / row 5 (unknown_prob), its own GC slot
+                    if (!(a.x & XSEL_OWN_GAP) && ((e_o >> ((a.x & 63u) >> 1)) & 1u)) {
+                        const uint32_t p = (a.x & 32u) ? (e_c >> 16) : (e_c & 0xffffu);
+                        gslot = sm.letters[p + ((a.x & 31u) >> 1)];
+                        nt = 5;
+                    }
+                    if ((e_o >> (((a.x >> 8) & 63u) >> 1)) & 1u) c0 = 5;      // an absent parent has stride 0
+                    if ((e_o >> (((a.x >> 16) & 63u) >> 1)) & 1u) c1 = 5;
+                }
                 double v = xcpt[a.y + nt + c0 * (a.z & 0xffffu) + c1 * (a.z >> 16)];
-                const double g = sm.gc[nt];                       // :223 (slot 4 holds log 0.25)
+                const double g = sm.gc[gslot];                    // :223 (slot 4 holds log 0.25)
                 if (v == CUDART_INF) v = g;                       // GC-sentinel row (:217-218)
                 const uint32_t fl = b.x;
                 const int bdepth = fl >> 28;
@@ -360,8 +379,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     for (int turn = 0;; turn ^= 1) {
         if (tid == 0) sm.next[turn] = atomicAdd(next_window, 1u);
         team_sync(team);
-        const long long w = w_begin + sm.next[turn];
-        const bool last = w >= w_end;
+        const bool last = OTHER ? sm.next[turn] >= *O.other_count : w_begin + sm.next[turn] >= w_end;
+        const long long w = w_begin + (OTHER ? (last ? w_end - w_begin : (long long)O.other_list[sm.next[turn]]) : (long long)sm.next[turn]);
         const int cur_seq = sm.cur_seq;
         int seq = cur_seq, wlen = 0;
         long long start = 0;
@@ -421,6 +440,14 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             sm.l2[tid] = word;
             if (other) atomicAnd(&sm.plain, 0u);
         }
+        if (OTHER && tid >= 32 && tid < 32 + FAST_W / 32 + 3) {   // which letters are not ACGU, one bit each
+            uint32_t word = 0;
+            for (int k = 0; k < 32; k++) {
+                const int pos = (tid - 32) * 32 + k;
+                if (pos < FAST_W + 16 && sm.letters[pos] > 3) word |= 1u << k;
+            }
+            sm.lo[tid - 32] = word;
+        }
         // bits and ranks in one pass over the list: the entry that opens a word (its predecessor lies in another
         // word) is that word's rank; a list that is not strictly increasing in (i, j), or leaves the window's upper
         // triangle, is refused
@@ -455,7 +482,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             }
         }
         team_sync(team);
-        if (!sm.plain) continue;                              // a letter other than ACGU: the window is scan_generic_kernel's
+        if (!OTHER && !sm.plain) continue;                    // a letter other than ACGU: the window is the OTHER launch's (or scan_generic_kernel's)
 
 #ifdef RMD_STATS
         const long long ck1 = clock64();
@@ -476,7 +503,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 const uint32_t p0 = c & 0xffu, p1 = (c >> 8) & 0xffu, m = c >> 16;
                 int q = sm.screen0[m];
                 const int qe = sm.screen0[m + 1];
-                if (act && q < qe) {
+                bool screened = act && q < qe;
+                if (OTHER && screened)                            // the tables are indexed by ACGU letters
+                    screened = ((__funnelshift_r(sm.lo[p0 >> 5], sm.lo[(p0 >> 5) + 1], p0 & 31u) & 0xffffu) |
+                                (__funnelshift_r(sm.lo[p1 >> 5], sm.lo[(p1 >> 5) + 1], p1 & 31u) << 16)) == 0;
+                if (screened) {
                     const unsigned long long em = (unsigned long long)__funnelshift_r(sm.l2[p0 >> 4], sm.l2[(p0 >> 4) + 1], (p0 & 15u) * 2) |
                                                   ((unsigned long long)__funnelshift_r(sm.l2[p1 >> 4], sm.l2[(p1 >> 4) + 1], (p1 & 15u) * 2) << 32);
                     alive = false;
@@ -755,6 +786,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 #ifdef RMD_STATS
         const long long ck2 = clock64();
 #endif
+        if (OTHER) engine(true);                               // the walks read this window's letters: finish them here
 #ifdef RMD_STATS
         const long long ck3 = clock64();
 #endif
@@ -776,6 +808,24 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             atomicAdd(&O.stats[2], (unsigned long long)(ck3 - ck2)); atomicAdd(&O.stats[3], (unsigned long long)(ck4 - ck3));
         }
 #endif
+    }
+}
+
+// Windows of [w_begin, w_end) that the shared-memory kernel takes (length within [min_wlen, FAST_W]) and that hold a
+// letter other than ACGU: the OTHER launch's work list (window numbers relative to w_begin, any order).  One warp per window.
+__global__ void __launch_bounds__(256) other_windows_kernel(const DevJob J, const long long w_begin, const long long w_end, const int min_wlen,
+                                                            uint32_t *list, uint32_t *count) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = w_begin + warp; w < w_end; w += n_warps) {
+        int seq, wlen;
+        long long start;
+        window_geom(J, w, seq, start, wlen);
+        if (wlen < min_wlen || wlen > FAST_W) continue;
+        const uint8_t *c = J.codes8 + J.seq_off[seq] + start;
+        bool other = false;
+        for (int k = lane; k < wlen; k += 32) other |= c[k] > 3;
+        if (__any_sync(FULL_MASK, other) && lane == 0) list[atomicAdd(count, 1u)] = (uint32_t)(w - w_begin);
     }
 }
 
@@ -802,7 +852,7 @@ __device__ __forceinline__ double bpp_search(const DevJob &J, long long b0, int 
 
 __global__ void __launch_bounds__(GEN_THREADS)
 scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
-                    const ScanOut O, const int min_fast_wlen) {
+                    const ScanOut O, const int min_fast_wlen, const int fast_takes_other) {
     __shared__ uint32_t scan_tmp[GEN_THREADS / 32 + 1];
     __shared__ double gc[RMD_N_CODES];
     __shared__ unsigned long long s_base;
@@ -816,7 +866,8 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     long long start;
     window_geom(J, w, seq, start, wlen);
     if (wlen <= 0) return;
-    if (wlen >= min_fast_wlen && wlen <= FAST_W) {                         // scan_fast_kernel's, unless a letter is not ACGU
+    if (wlen >= min_fast_wlen && wlen <= FAST_W) {                         // scan_fast_kernel's, unless a letter is not ACGU and no OTHER launch follows
+        if (fast_takes_other) return;
         int other = 0;
         if (J.codes8) for (int k = tid; k < wlen; k += GEN_THREADS) other |= J.codes8[J.seq_off[seq] + start + k] > 3;
         if (!__syncthreads_or(other)) return;

@@ -591,3 +591,42 @@ def test_tuning_switches_in_the_environment_are_ignored(monkeypatch):
         monkeypatch.setenv(k, v)
     got = run()
     assert len(want["hits"]) > 0 and got["hits"].tobytes() == want["hits"].tobytes() and got["n_launches"] == want["n_launches"]
+
+
+@pytest.mark.parametrize("screens", [0, -1])
+def test_windows_with_other_letters_take_the_shared_memory_kernel(screens):
+    """N runs and scattered IUPAC codes in a 95 kb sequence (every such letter has its own log-frequency, lib/gcx.py:4-13,
+    and no CPT entry, lib/node.py:215-223): the OTHER launch of scan_fast_kernel scans those windows; hit for hit, bit for
+    bit the oracle's result, with the prefix screens on and off."""
+    from oracle import pyoracle
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold
+    rng = random.Random(77)
+    letters = [rng.choice("ACGU") for _ in range(95000)]
+    for _ in range(40):                                    # runs of N: 1 .. 200 letters
+        at, ln = rng.randrange(len(letters)), rng.choice([1, 2, 5, 30, 200])
+        letters[at:at + ln] = "N" * len(letters[at:at + ln])
+    for _ in range(150):                                   # single ambiguity codes
+        letters[rng.randrange(len(letters))] = rng.choice("RYKMSWN")
+    seqs = [("chr", "".join(letters), None), ("short", "ACGUNACGGGCAUNNNNACGAUCGAUCGGCUAGCUAGGCUA" * 5, None)]
+    names = MODEL_ORDER
+    fold = SynthFold(31)
+    eng = ScanEngine([load_model(n) for n in names], [load_evalues(n) for n in names], LN_UNKNOWN)
+    eng.ctx.set_screen_policy(screens)
+    job = eng.build_job(seqs, 150, 75, fold, "", 0.001, LN_CUTOFF)
+    r = eng.scan_job(job)
+    eng.close()
+    oms = [pyoracle.OracleModel(load_model(n)) for n in names]
+    oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+    hits = r["hits"]
+    at, tests = 0, [0, 0]
+    for si, (_, seq, _) in enumerate(seqs):
+        starts = pyoracle.windows(len(seq), 150, 75)
+        want, tries, _ = pyoracle.scan_sequence(oms, oes, si, seq, 150, 75, [fold.coo(seq[s:s + 150]) for s in starts],
+                                                0.001, LN_UNKNOWN, LN_CUTOFF)
+        tests[0] += tries[0]; tests[1] += tries[1]
+        for w in want:
+            g = hits[at]; at += 1
+            assert (g["seq"], g["model"], g["start"], g["p0"], g["p1"], g["leaf"]) == (si, w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"])
+            assert (g["prob_model"], g["prob_rand"], g["score"], g["evalue"]) == (w["prob_model"], w["prob_rand"], w["score"], w["evalue"])
+    assert at == len(hits) > 100 and r["tries"] == tests

@@ -23,6 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--models", default="")
+ap.add_argument("--n-frac", type=float, default=0.0, help="also scan the same job with this fraction of the letters replaced by runs of N")
 ap.add_argument("--e2e", action="store_true", help="also time rmd_scan from host buffers (compact transport) and print its parts")
 args = ap.parse_args()
 models, evs = load_models()
@@ -38,6 +39,25 @@ for k in range(args.steps):
 print("models %s windows %d bpp %d gen %.2f ms | scan %.3f ms post %.3f ms total %.3f ms | tries %s raw %d hits %d | %.1f M nt·model/s"
       % ([m.name for m in models], n_win, n_bpp, ms_gen, r["ms_scan"], r["ms_post"], r["ms_total"], r["tries"], r["n_raw"],
          len(r["hits"]), n * len(models) / r["ms_scan"] / 1e3))
+if args.n_frac > 0:
+    # the same chromosome with runs of N (real genomes: assembly gaps, masked repeats); lists unchanged
+    off, bi, bj, bp = eng.ctx.download_job(n_win, n_bpp)
+    codes = eng.ctx.download_codes(n).copy()
+    rng = np.random.default_rng(1)
+    run = 200
+    for at in rng.integers(0, n - run, int(args.n_frac * n / run)):
+        codes[at:at + run] = 5
+    counts = np.bincount(codes, minlength=16)
+    gcn = gc_table({"ACGUN"[min(c, 4)]: math.log(counts[c] / n) for c in (0, 1, 2, 3, 5) if counts[c]}, others="N")
+    job = dict(seq_off=np.array([0, n], dtype=np.int64), codes=codes, gc_log=gcn.reshape(1, -1),
+               gc_class=np.full((1, len(models)), -1, dtype=np.int32), win_len=WIN_LEN, win_step=WIN_STEP, n_win=n_win,
+               bpp_off=off, bpp_i=bi, bpp_j=bj, bpp_p=bp, bpp_ij=None, bpp_q=None, min_bpp_mean=MIN_BPP, cutoff=LN_CUTOFF)
+    eng.ctx.upload(job)
+    for k in range(args.steps):
+        r2 = eng.ctx.scan_resident(0, n_win)
+    n_other = int(sum(1 for w in range(n_win) if (codes[w * WIN_STEP:w * WIN_STEP + WIN_LEN] > 3).any())) if n_win < 200000 else -1
+    print("with %.2f %% N in runs of %d: %d of %d windows hold an N | scan %.3f ms post %.3f ms | tries %s raw %d | %.1f M nt·model/s"
+          % (100 * args.n_frac, run, n_other, n_win, r2["ms_scan"], r2["ms_post"], r2["tries"], r2["n_raw"], n * len(models) / r2["ms_scan"] / 1e3))
 if args.e2e:
     off, bi, bj, bp = eng.ctx.download_job(n_win, n_bpp, pinned=True)
     codes = _native.pinned_array(n, np.uint8)
