@@ -255,8 +255,9 @@ int rmd_table_clear(rmd_ctx *ctx);
 int rmd_table_rows(rmd_ctx *ctx, int64_t *n_rows);
 /* append the hits the last rmd_scan / rmd_scan_resident kept (still on the device): key = key_base + seq,
    start = start_base + window start (a piece of a longer sequence), letters read from the resident sequence,
-   id = rows appended so far */
-int rmd_table_append_scan(rmd_ctx *ctx, int32_t key_base, int64_t start_base, int64_t *n_rows);
+   id = rows appended so far.  first_n >= 0: only the first first_n hits (hits are in window order: a piece's halo
+   windows, scanned for the duplicate rule alone, come last) */
+int rmd_table_append_scan(rmd_ctx *ctx, int32_t key_base, int64_t start_base, int64_t first_n, int64_t *n_rows);
 /* append rows from the host (hits loaded from a .res file) */
 int rmd_table_append_rows(rmd_ctx *ctx, const rmd_hit_row *rows, int64_t n, int64_t *n_rows);
 int rmd_table_download(rmd_ctx *ctx, rmd_hit_row *rows, int64_t first, int64_t n);

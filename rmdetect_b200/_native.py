@@ -122,7 +122,7 @@ def load_library():
     pi64, pf64 = C.POINTER(i64), C.POINTER(f64)
     L.rmd_table_clear.argtypes = [vp]
     L.rmd_table_rows.argtypes = [vp, pi64]
-    L.rmd_table_append_scan.argtypes = [vp, i32, i64, pi64]
+    L.rmd_table_append_scan.argtypes = [vp, i32, i64, i64, pi64]
     L.rmd_table_append_rows.argtypes = [vp, vp, i64, pi64]
     L.rmd_table_download.argtypes = [vp, vp, i64, i64]
     L.rmd_table_filter.argtypes = [vp, pf64, pf64, pf64, i32, pi64]

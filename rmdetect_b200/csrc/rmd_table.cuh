@@ -147,11 +147,12 @@ extern "C" int rmd_table_rows(rmd_ctx *ctx, int64_t *n_rows) {
     return RMD_OK;
 }
 
-extern "C" int rmd_table_append_scan(rmd_ctx *ctx, int32_t key_base, int64_t start_base, int64_t *n_rows) {
+extern "C" int rmd_table_append_scan(rmd_ctx *ctx, int32_t key_base, int64_t start_base, int64_t first_n, int64_t *n_rows) {
     TABLE_ENTER("rmd_table_append_scan");
     if (!ctx->have_job || !ctx->last_hits) return fail(ctx, RMD_E_STATE, "rmd_table_append_scan: no scan result on the device");
     if (key_base < 0) return fail(ctx, RMD_E_INVALID, "rmd_table_append_scan: negative key_base");
-    const long long n = ctx->last_n;
+    if (first_n > ctx->last_n) return fail(ctx, RMD_E_INVALID, "rmd_table_append_scan: the scan kept %lld hits, %lld asked for", ctx->last_n, (long long)first_n);
+    const long long n = first_n < 0 ? ctx->last_n : first_n;
     if (T.n + n >= (1LL << 32)) return fail(ctx, RMD_E_LIMIT, "rmd_table_append_scan: a table holds fewer than 2^32 rows");
     int r;
     if ((r = bind_tables(ctx))) return r;

@@ -163,3 +163,99 @@ def scan_synthetic_genome(engine, total_nt, both_strands, seed, win_len, win_ste
                 windows=int(tot[4]), bpp_entries=int(tot[5]), checksum=checksum, counts=[int(c) for c in counts],
                 rank_wall_s=wall, rank_ms_generate=ms_gen, rank_ms_scan_kernel=ms_scan, rank_ms_device=ms_dev,
                 rank_pieces=n_pieces, rank_windows=n_windows)
+
+
+# ---- real input: FASTA chromosomes + a fold provider -------------------------------------------------------------
+def read_fasta(path):
+    """[(key, sequence)] of a FASTA file with the reference's rules (lib/file_io.py:5-24: key = first word after '>',
+    lines concatenated; lib/sequences.py:145-150: upper case, T -> U).  Vectorised: a chromosome is hundreds of megabytes."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    nl = np.flatnonzero(raw == 10)
+    line_starts = np.concatenate([[0], nl + 1])
+    line_starts = line_starts[line_starts < len(raw)]
+    heads = line_starts[raw[line_starts] == ord(">")]
+    # (a '>' preceded by blanks on its line is not recognised as a header; the reference strips every line first)
+    out = []
+    lut = np.arange(256, dtype=np.uint8)
+    for c in range(ord("a"), ord("z") + 1):
+        lut[c] = c - 32
+    lut[ord("T")] = lut[ord("t")] = ord("U")
+    for k, h in enumerate(heads):
+        end_head = nl[np.searchsorted(nl, h)] if np.searchsorted(nl, h) < len(nl) else len(raw)
+        words = raw[h + 1:end_head].tobytes().decode("latin-1").strip().split()
+        key = words[0] if words else ""
+        body = raw[end_head + 1:heads[k + 1] if k + 1 < len(heads) else len(raw)]
+        body = body[(body != 10) & (body != 13) & (body != 32) & (body != 9)]
+        out.append((key, lut[body].tobytes().decode("latin-1")))
+    return out
+
+
+def reverse_complement(seq):
+    """lib/sequences.py:138-143: reversed, A<->U and C<->G, every other letter unchanged."""
+    return seq[::-1].translate(str.maketrans("ACGU", "UGCA"))
+
+
+def scan_genome(engine, sequences, fold, both_strands=False, win_len=150, win_step=75, min_bpp_mean=0.001,
+                cutoff=math.log(0.1), constraint="", rank=0, world=1, dist=None, piece_windows=32768, min_score=None,
+                table=None, on_hits=None):
+    """Scan `rank`'s share of real sequences: [(key, sequence)] (e.g. `read_fasta`), bpp lists from `fold` (an object with
+    `coo_many(windows, constraint)` / `coo` / `bpprobs`: fold.RNAfold, the reference's RNATools, synth.SynthFold).
+
+    What `rmdetect.py` does with such an input (lib/sequences.py:103-111: with --both-strands every sequence is followed,
+    after all forward ones, by its reverse complement under key + "--"; lib/scanner.py:73-113: GC table of the whole
+    sequence, windows at k * step) is done piece by piece: every sequence is cut at window starts into contiguous ranges of
+    windows, one share per rank (`rank_pieces`), each piece is scanned as a sequence of its own with the parent's GC table
+    plus halo windows for the duplicate rule, and its own hits are kept in parent coordinates.  `table` (a `HitTable`)
+    collects them on the device; `on_hits(key, hits)` receives the records (start in parent coordinates).  Returns totals
+    over all ranks (after the closing all-reduce when `dist` is given)."""
+    from .gcx import GC
+    from ._native import HIT_DTYPE
+    strands = [(k, s) for k, s in sequences]
+    if both_strands:
+        strands += [(k + "--", reverse_complement(s)) for k, s in sequences]
+    engine.ctx.set_min_score(min_score)
+    tests_all = tests_pairs = n_hits = n_windows = checksum = 0
+    ms_dev = 0.0
+    t0 = time.perf_counter()
+    for si, (key, seq) in enumerate(strands):
+        if len(seq) == 0:
+            continue
+        gc = GC.compute(seq)                                   # over the whole sequence, before the first window
+        if table is not None:
+            table.key_id(key)                                  # ids in strand order on every rank
+        for a, b, bh, lo, hi in rank_pieces(len(seq), win_len, win_step, rank, world, piece_windows):
+            job = engine.build_job([(key, seq[lo:hi], None)], win_len, win_step, fold, constraint, min_bpp_mean, cutoff, gc=gc)
+            assert job["n_win"] == bh - a, (job["n_win"], a, bh)
+            r = engine.ctx.scan(job, copy=False)
+            own = b - a
+            h = r["hits"]
+            n_own = int(np.searchsorted(h["window"], own))     # hits are in window order; halo windows come last
+            h = h[:n_own]
+            tests_pairs += int(np.asarray(r["gate_pass"])[:own].sum())
+            starts = job["starts"][0][:own]
+            tests_all += sum(placements_in_window(m, min(win_len, hi - lo - int(s)) if win_len else hi - lo)
+                             for s in starts.tolist() for m in engine.models)
+            n_hits += n_own
+            n_windows += own
+            ms_dev += r["ms_total"]
+            if n_own:
+                checksum = (checksum + hit_checksum(si & 7, h["start"] + lo, h["p0"], h["p1"], h["model"], h["leaf"], h["score"])) & MASK64
+                if table is not None:
+                    table.append_scan([key], start_base=lo, first_n=n_own)
+                if on_hits is not None:
+                    hh = np.array(h, dtype=HIT_DTYPE, copy=True)
+                    hh["start"] += lo
+                    hh["window"] += a
+                    hh["seq"] = si
+                    on_hits(key, hh)
+    wall = time.perf_counter() - t0
+    engine.ctx.set_min_score(None)
+    tot = np.array([tests_all, tests_pairs, n_hits, n_windows, checksum >> 32, checksum & 0xffffffff], dtype=np.int64)
+    if dist is not None and world > 1:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(tot).to(dev)
+        dist.all_reduce(t)                                     # counters only: hit records stay with their rank
+        tot = t.cpu().numpy()
+    return dict(tests_all=int(tot[0]), tests_pairs=int(tot[1]), hits=int(tot[2]), windows=int(tot[3]),
+                checksum=((int(tot[4]) << 32) + int(tot[5])) & MASK64, strands=len(strands), rank_wall_s=wall, rank_ms_device=ms_dev)

@@ -85,14 +85,15 @@ class HitTable:
             self.keys.append(key)
         return self._key_id[key]
 
-    def append_scan(self, keys, start_base=0):
+    def append_scan(self, keys, start_base=0, first_n=-1):
         """The hits the engine's last scan kept become rows, on the device.  keys: the names of the scanned job's
-        sequences; start_base: position of the job's first letter in its sequence (a piece of a chromosome)."""
+        sequences; start_base: position of the job's first letter in its sequence (a piece of a chromosome);
+        first_n: only that many of the hits (a piece's halo windows come last and are not its own)."""
         ids = [self.key_id(k) for k in keys]
         if ids != list(range(ids[0], ids[0] + len(ids))):
             raise ValueError("append_scan: the job's sequences need consecutive ids (new names, or the same names in the same order)")
         n = C.c_int64(0)
-        self.ctx._check(self.lib.rmd_table_append_scan(self.ctx.h, ids[0], int(start_base), C.byref(n)), "rmd_table_append_scan")
+        self.ctx._check(self.lib.rmd_table_append_scan(self.ctx.h, ids[0], int(start_base), int(first_n), C.byref(n)), "rmd_table_append_scan")
         return n.value
 
     def row_of(self, cand, ident=0):

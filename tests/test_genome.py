@@ -217,3 +217,72 @@ def test_two_ranks_share_a_genome_over_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert two == one and one["hits"] > 0 and one["windows"] == 2 * 17 and sum(one["counts"]) == 1300
+
+
+@pytest.mark.gpu
+def test_fasta_genome_in_pieces_equals_the_scanner(tmp_path):
+    """Real input through the genome driver: a FASTA file (lower case, T, N runs, IUPAC codes), both strands, cut into
+    pieces of a few windows and shared by two ranks, gives the hits and tries of the drop-in `Scanner.scan` on the same
+    sequences (lib/sequences.py:103-111 order: forward sequences, then the reverse complements under key + "--"); the
+    device-resident table holds the same rows."""
+    import random
+    from helpers import Cfg, SeqList, fresh_models
+    from rmdetect_b200.genome import read_fasta, reverse_complement, scan_genome
+    from rmdetect_b200.hittable import HitTable
+    from rmdetect_b200.scanner import Scanner
+    from rmdetect_b200.synth import SynthFold
+    rng = random.Random(5)
+    chr1 = [rng.choice("ACGT") for _ in range(2600)]
+    chr1[700:760] = "N" * 60
+    for k in (50, 51, 1200, 2300):
+        chr1[k] = rng.choice("RYKM")
+    chr2 = "".join(rng.choice("acgu") for _ in range(420))
+    path = tmp_path / "g.fasta"
+    body = "".join(chr1)
+    path.write_text(">chr1 test sequence\n" + "\n".join(body[k:k + 70] for k in range(0, len(body), 70)) + "\n\n>chr2\n" + chr2 + "\n")
+    seqs = read_fasta(str(path))
+    assert [k for k, _ in seqs] == ["chr1", "chr2"] and seqs[0][1] == body.replace("T", "U") and seqs[1][1] == chr2.upper()
+    names = ["CL_1.0", "TGA_1.0", "GB_1.0", "KT_1.0"]
+    models, evs = fresh_models(names)
+    sc = Scanner(Cfg(models, evs))
+    sc.rna_tools = SynthFold(9)
+    both = [(k, s, None) for k, s in seqs] + [(k + "--", reverse_complement(s), None) for k, s in seqs]
+    cands, tries = sc.scan(SeqList(both))
+    want = sorted((c.key, c.coords[0], c.chains_pos[0][0], c.chains_pos[1][0], c.model.full_name(), c.score, c.evalue) for c in cands)
+    eng = sc._engine
+    eng.ctx.set_return_dropped(False)
+    T = HitTable(eng)
+    got, totals = [], []
+    for rank in range(2):
+        def on_hits(key, h, got=got):
+            for r in h:
+                got.append((key, int(r["start"]), int(r["start"] + r["p0"]), int(r["start"] + r["p1"]),
+                            models[int(r["model"])].full_name(), float(r["score"]), float(r["evalue"])))
+        totals.append(scan_genome(eng, seqs, SynthFold(9), both_strands=True, rank=rank, world=2, piece_windows=5, table=T, on_hits=on_hits))
+    assert sorted(got) == want and len(want) > 20
+    assert [totals[0][k] + totals[1][k] for k in ("tests_all", "tests_pairs")] == tries
+    assert totals[0]["hits"] + totals[1]["hits"] == len(want)
+    rows = T.rows()
+    assert sorted((T.keys[r["key"]], int(r["start"]), int(r["start"] + r["p0"]), int(r["start"] + r["p1"]), models[int(r["model"])].full_name(),
+                   float(r["score"]), float(r["evalue"])) for r in rows) == want
+    # letters of the rows are the sequence's (N and IUPAC codes as "other")
+    seq_of = {k: q for k, q, _ in both}
+    for c in T.candidates():
+        for letters, pos in zip(c.chains_seqs, c.chains_pos):
+            for ch, p in zip(letters, pos):
+                assert (ch == ".") == (p is None)
+                if p is not None:
+                    true = seq_of[c.key][p]
+                    assert ch == (true if true in "ACGU" else "N")
+    sc._engine.close()
+
+
+def test_fasta_reader_follows_the_reference(tmp_path):
+    """lib/file_io.py:5-24 + lib/sequences.py:103-111,138-150 on a small file (output of the reference's own Sequences
+    class for this text, recorded here)."""
+    from rmdetect_b200.genome import read_fasta, reverse_complement
+    path = tmp_path / "t.fasta"
+    path.write_text(">chr1 some text\nacgtnnACGU\nRYacg\n\n>chr2\nGGGTTT\n")
+    seqs = read_fasta(str(path))
+    assert seqs == [("chr1", "ACGUNNACGURYACG"), ("chr2", "GGGUUU")]
+    assert [(k + "--", reverse_complement(q)) for k, q in seqs] == [("chr1--", "CGUYRACGUNNACGU"), ("chr2--", "AAACCC")]
