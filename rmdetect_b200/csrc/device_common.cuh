@@ -54,15 +54,15 @@ __constant__ int c_n_prel;
 __constant__ unsigned char c_groups[RMD_MAX_MODELS + 1];   // candidate generation handles models [c_groups[g], c_groups[g + 1]) together
 __constant__ int c_n_groups;
 
-// The trie nodes of a group again, in the order candidate generation visits them: the group's root nodes (first pairs
-// of configurations: they need no parent test and go straight to the duplicate test), then the others.
+// The trie nodes of a group again, in the order candidate generation visits them: the nodes of models without SYMMETRIC,
+// then those of symmetric models; in each part the root nodes (first pairs of configurations), then the others.
 //   x    = (ro + 16) | (co + 16) << 12 | pbit << 24 | symmetric << 29     (see the node loop in scan_kernels.cuh)
 //   info = trie node | grandparent << 7 (0x7f: none) | model << 14 | (duplicate bitmap + 1) << 18 |
 //          second << 20 (a node other than the first of a trie that has no bitmap) | first node of the model's trie << 21
 struct CandNode { uint32_t x, info; };
 __constant__ CandNode c_cand[TRIE_CAP];
 __constant__ uint32_t c_ancw[TRIE_CAP];                    // per TRIE node: ro | co << 12 | parent << 24 (0x7f: none)
-__constant__ unsigned char c_cgrp[RMD_MAX_MODELS + 1][4];  // per group: first candidate index, end of its roots, end of the group
+__constant__ unsigned char c_cgrp[RMD_MAX_MODELS + 1][4];  // per group: first candidate index, first node of a SYMMETRIC model, end of the group
 #define NODE_SYM (1u << 29)
 #define NODE_GUARD 0x800800u
 
@@ -134,6 +134,7 @@ struct DevJob {
     int n_xnodes, n_xcpt;
     int motif_ok;                // every chain of every model fits the scoring engine's letter word
     int debug;                   // profiling experiments only (RMD_DEBUG): 1 skip scoring, 2 skip the exact gate
+    int no_score;                // the root's own prune test fails for this cutoff (lib/node.py:248): no placement can score
     const uint32_t *screen_bits; // prefix-screen tables of the sequences that have them
     const long long *screen_off; // [n_seq] first word of a sequence's block in screen_bits, -1: not tabulated (nullptr: no screens)
     int n_screens;               // screens of all models (c_screens); model m owns [screen0[m], screen0[m + 1])

@@ -495,11 +495,14 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         for (int g = 0; g < n_groups; g++) {
             const int t0 = hmodels[groups[g]].trie0, t1 = hmodels[groups[g + 1] - 1].trie0 + hmodels[groups[g + 1] - 1].n_trie;
             sym.cgrp[g][0] = (unsigned char)k;
-            for (int pass = 0; pass < 2; pass++) {
+            // models without SYMMETRIC first (their odometer range is one interval test per node), the symmetric ones after
+            // cgrp[g][1]; inside each part the root nodes (first pairs of configurations), then the others, each in trie order
+            for (int pass = 0; pass < 4; pass++) {
+                if (pass == 2) sym.cgrp[g][1] = (unsigned char)k;
                 for (int t = t0; t < t1; t++) {
                     const TrieNode &tn = htrie[t];
-                    if ((tn.parent < 0) != (pass == 0)) continue;
                     const CModel &c = hmodels[tn.model];
+                    if ((c.symmetric != 0) != (pass >= 2) || (tn.parent < 0) != ((pass & 1) == 0)) continue;
                     if (tn.ro < 0 || tn.co < 0 || tn.ro > 100 || tn.co > 100) return fail(ctx, RMD_E_LIMIT, "model %d: gate pair offset out of range", (int)tn.model);
                     const int gp = tn.parent < 0 ? 0x7f : (htrie[tn.parent].parent < 0 ? 0x7f : htrie[tn.parent].parent);
                     CandNode &cn = sym.cand[k++];
@@ -507,7 +510,6 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
                     cn.info = (uint32_t)t | ((uint32_t)gp << 7) | ((uint32_t)tn.model << 14) | ((uint32_t)(c.cb_slot + 1) << 18) |
                               ((c.cb_slot < 0 && t != c.trie0) ? 1u << 20 : 0u) | ((uint32_t)c.trie0 << 21);
                 }
-                if (pass == 0) sym.cgrp[g][1] = (unsigned char)k;
             }
             sym.cgrp[g][2] = (unsigned char)k;
         }
@@ -781,7 +783,7 @@ static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries)
     J.bpp_off = (const long long *)ctx->d_bpp_off.p;
     J.bpp_i = (const uint16_t *)ctx->d_bpp_i.p; J.bpp_j = (const uint16_t *)ctx->d_bpp_j.p; J.bpp_p = (const double *)ctx->d_bpp_p.p;
     J.bpp_ij = nullptr; J.bpp_q = nullptr;
-    J.min_bpp = in->min_bpp_mean; J.cutoff = in->cutoff;
+    J.min_bpp = in->min_bpp_mean; J.cutoff = in->cutoff; J.no_score = !(0.0 >= 0.0 + in->cutoff);
     ctx->have_job = true;
     return RMD_OK;
 }
@@ -1367,7 +1369,7 @@ extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t se
     RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(J.n_win + 1));
     RESERVE(ctx->d_bpp_off, sizeof(long long) * (size_t)(J.n_win + 1));
     J.codes2 = (const uint32_t *)ctx->d_codes2.p; J.codes8 = nullptr; ctx->any_other = false;
-    J.min_bpp = min_bpp_mean; J.cutoff = cutoff;
+    J.min_bpp = min_bpp_mean; J.cutoff = cutoff; J.no_score = !(0.0 >= 0.0 + cutoff);
     CK(cudaEventRecord(ctx->ev[0], st));
     const long long words = (n + 15) / 16;
     if (ctx->strand_total > 0 && (first < 0 || first + n > ctx->strand_total))

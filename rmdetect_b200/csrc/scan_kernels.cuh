@@ -64,7 +64,7 @@
 #define TAIL_ROW 8
 #endif
 #define STK_SLOTS 3                     // save slots of the scoring engine kept in shared memory (per lane)
-#define SCAN_CTA_FIXED (TRIE_CAP * 16)   // bytes of CTA-wide state in front of the teams' blocks: gate tries (8 B per node), cinfo, ancw
+#define SCAN_CTA_FIXED (TRIE_CAP * 32)   // bytes of CTA-wide state in front of the teams' blocks: gate tries (8 B per node), cinfo, ancw, cnw (16 B per node)
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
 
@@ -89,14 +89,9 @@ struct __align__(16) FastSmem {
     int cur_seq;                          // sequence whose GC table is in gc
     uint32_t win_local;                   // window being generated (records are relative to w_base)
     double2 zero2;                       // (0, 0)
-    // per trie node in candidate order (device_common.cuh: c_cand), as candidate generation reads it (one 8-byte
-    // broadcast load per node):
-    //   x = (ro + 16) | (co + 16) << 12 | pbit << 24 | symmetric << 29      (static)
-    //   y = (n0 - 1 + 0x800) | (hi + 0x800) << 12 | need << 24               (the odometer's ranges in this window,
-    //       lib/scanner.py:161-193; need: a generating value of at least need x min_bpp passes the gate for certain, 255: never)
-    // Two 12-bit fields with a guard bit each (0x800) let one subtraction turn an item into a placement and a second
-    // one test both ranges, see the node loop.
-    uint2 nodew[TRIE_CAP];
+    // per trie node in candidate order: the odometer's ranges in this window (lib/scanner.py:161-193) as
+    // (n0 - 1 + 0x800) | (hi + 0x800) << 12, next to the static words of the node in cnw (see the node loop)
+    uint32_t nodey[TRIE_CAP];
     double gc[RMD_N_CODES];
     uint32_t bounds[RMD_MAX_MODELS];     // n0 | p1 upper bound << 8 | symmetric << 16
     uint32_t gate_pass[RMD_MAX_MODELS];
@@ -199,6 +194,11 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const TrieNode *const strie = reinterpret_cast<const TrieNode *>(dyn_smem);
     const uint32_t *const cinfo = reinterpret_cast<const uint32_t *>(dyn_smem) + TRIE_CAP * 2;   // CandNode::info, candidate order
     const uint32_t *const ancw = cinfo + TRIE_CAP;                                               // c_ancw, trie order
+    // static words of a node in candidate order, as the node loop reads them (one 16-byte broadcast load per node):
+    //   x = (ro + 16) | (co + 16) << 12, y = 1 << (index of the parent-relative pair; 31: no parent),
+    //   z = node << 24 (its place in a queued pair), w = need: a generating value of at least need x min_bpp passes the
+    //   gate for certain (255: never)
+    const uint4 *const cnw = reinterpret_cast<const uint4 *>(dyn_smem) + TRIE_CAP;
     uint32_t sm_off = (uint32_t)SCAN_CTA_FIXED + (uint32_t)team * (uint32_t)sizeof(FastSmem);
     asm volatile("mov.u32 %0, %0;" : "+r"(sm_off));
     FastSmem &sm = *reinterpret_cast<FastSmem *>(reinterpret_cast<char *>(dyn_smem) + sm_off);
@@ -240,17 +240,17 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             }
             const int slots = c_models[tn.model].cfg_begin[c_models[tn.model].n_cfg];
             const uint32_t need = (uint32_t)min((slots + tn.mult - 1) / max((int)tn.mult, 1), 255);
-            sm.nodew[k] = make_uint2(cn.x, need << 24);
+            if (team == 0) const_cast<uint4 *>(cnw)[k] = make_uint4(cn.x & 0xffffffu, 1u << ((cn.x >> 24) & 31u), (uint32_t)k << 24, need);
         }
     }
     __syncthreads();
     const uint4 *xn = TABLES ? sx : reinterpret_cast<const uint4 *>(J.xnodes);
     const double *xcpt = TABLES ? scpt : J.xcpt;
-    const bool root_ok = 0.0 >= __dadd_rn(0.0, J.cutoff);   // the root's own test (lib/node.py:248)
+    // the root's own test (lib/node.py:248: 0.0 >= 0.0 + cutoff) is taken on the host, once per job: when it fails nothing can score
 #ifdef RMD_TUNING
-    const bool no_score = !root_ok || (J.debug & 1);      // profiling experiment: gate only
+    const bool no_score = J.no_score || (J.debug & 1);     // profiling experiment: gate only
 #else
-    const bool no_score = !root_ok;
+    const bool no_score = J.no_score != 0;
 #endif
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
     uint32_t wq_off = sm_off + (uint32_t)offsetof(FastSmem, wq) + (uint32_t)wid * (uint32_t)sizeof(WarpQueues);
@@ -427,7 +427,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         team_sync(team);
         for (int k = tid; k < sm.trie_end[n_models - 1]; k += SCAN_THREADS) {
             const uint32_t bd = sm.bounds[(cinfo[k] >> 14) & 15u];    // n0 | hi << 8 | symmetric << 16, n0 >= 1
-            sm.nodew[k].y = (sm.nodew[k].y & 0xff000000u) | ((bd & 0xffu) - 1u + 0x800u) | ((((bd >> 8) & 0xffu) + 0x800u) << 12);
+            sm.nodey[k] = ((bd & 0xffu) - 1u + 0x800u) | ((((bd >> 8) & 0xffu) + 0x800u) << 12);
         }
         if (tid < FAST_W / 16 + 2) {                          // two-bit letters for the scoring engine
             uint32_t word = 0, other = 0;
@@ -642,7 +642,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     if (tid == 0) sm.chunk_ctr[(grp + 1) & 1] = 0;
                     team_sync(team);
                 }
-                const int kb = c_cgrp[grp][0], ke = c_cgrp[grp][2];      // the group's nodes in candidate order
+                const int kb = c_cgrp[grp][0], ks = c_cgrp[grp][1], ke = c_cgrp[grp][2];      // the group's nodes in candidate order; [ks, ke): SYMMETRIC models
                 const bool last_group = grp + 1 == n_groups;
                 for (bool more = true;;) {
                     // rows shrink towards the end of the list so that the four warps finish together
@@ -695,47 +695,45 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     // 0x800 + p in each field (nothing borrows across fields), b = that without the guard bits (a negative p
                     // leaves b >= 0x7f0), and c = y - b keeps both of ITS guard bits exactly when 0 <= p0 <= n0 - 1 and
                     // 0 <= p1 <= hi.  The bits above the fields (parent index, flags, need) only see borrows that go upwards.
-                    auto in_range = [&](const uint2 nw, const uint32_t b) {
-                        const uint32_t c = nw.y - b;
-                        if (nw.x & NODE_SYM) {                    // SYMMETRIC (lib/scanner.py:183-188): p1 runs from p0 to max(hi, p0)
-                            const uint32_t q0 = b & 0xfffu, q1 = b >> 12, hi = (nw.y >> 12) & 0x7ffu;
-                            return (c & 0x800u) && q1 >= q0 && (q1 <= hi || q1 == q0);
-                        }
-                        return (~c & NODE_GUARD) == 0;
-                    };
                     int k = flush ? ke : kb;
                     for (;;) {
                         // Warp-uniform nodes, two per step (independent loads and tests): a (item, node) pair is kept when the
                         // node's parent pair is present (a root has none) and the placement lies in the odometer's range.  The
                         // pairs of a row are compacted into s2 and go on in full batches of 32: a stage that took every root
                         // node's placements straight from the row, skipping the queue, ran with 18 of 32 lanes and was 2 % slower.
-                        while (k < ke && ns < 32) {
-                            const bool two = k + 1 < ke;
-                            const uint2 na = sm.nodew[k], nb = sm.nodew[two ? k + 1 : k];
-                            const uint32_t ba = (ppg - na.x) & 0x7ff7ffu, bb = (ppg - nb.x) & 0x7ff7ffu;
-                            bool oka = ((PM >> ((na.x >> 24) & 31u)) & 1u);
-                            bool okb = two && ((PM >> ((nb.x >> 24) & 31u)) & 1u);
-                            if ((na.x | nb.x) & NODE_SYM) {       // rare: one test for the pair of nodes
-                                oka = oka && in_range(na, ba);
-                                okb = okb && in_range(nb, bb);
-                            } else {
-                                oka = oka && (~(na.y - ba) & NODE_GUARD) == 0;
-                                okb = okb && (~(nb.y - bb) & NODE_GUARD) == 0;
-                            }
+                        auto push2 = [&](const bool oka, const bool okb, const uint32_t ba, const uint32_t bb, const uint4 &na, const uint4 &nb) {
                             const uint32_t oma = __ballot_sync(FULL_MASK, oka), omb = __ballot_sync(FULL_MASK, okb);
                             if (oma | omb) {
                                 const int na_cnt = __popc(oma);
-                                if (oka) s2[ns + __popc(oma & lt_mask)] = ba | ((uint32_t)k << 24) | (level >= (na.y >> 24) ? 0x80000000u : 0u);
-                                if (okb) s2[ns + na_cnt + __popc(omb & lt_mask)] = bb | ((uint32_t)(k + 1) << 24) | (level >= (nb.y >> 24) ? 0x80000000u : 0u);
+                                if (oka) s2[ns + __popc(oma & lt_mask)] = ba | na.z | (level >= na.w ? 0x80000000u : 0u);
+                                if (okb) s2[ns + na_cnt + __popc(omb & lt_mask)] = bb | nb.z | (level >= nb.w ? 0x80000000u : 0u);
                                 ns += na_cnt + __popc(omb);
-                                __syncwarp();
                             }
-                            k += 2;
+                        };
+                        while (k < ks && ns < 32) {               // models without SYMMETRIC: both ranges in one test
+                            const bool two = k + 1 < ks;
+                            const uint4 na = cnw[k], nb = cnw[two ? k + 1 : k];
+                            const uint32_t ya = sm.nodey[k], yb = sm.nodey[two ? k + 1 : k];
+                            const uint32_t ba = (ppg - na.x) & 0x7ff7ffu, bb = (ppg - nb.x) & 0x7ff7ffu;
+                            const bool oka = (PM & na.y) && (~(ya - ba) & NODE_GUARD) == 0;
+                            const bool okb = two && (PM & nb.y) && (~(yb - bb) & NODE_GUARD) == 0;
+                            push2(oka, okb, ba, bb, na, nb);
+                            k += two ? 2 : 1;
+                        }
+                        while (k >= ks && k < ke && ns < 32) {    // SYMMETRIC (lib/scanner.py:183-188): p1 runs from p0 to max(hi, p0)
+                            const uint4 na = cnw[k];
+                            const uint32_t ya = sm.nodey[k];
+                            const uint32_t ba = (ppg - na.x) & 0x7ff7ffu;
+                            const uint32_t q0 = ba & 0xfffu, q1 = ba >> 12, hi = (ya >> 12) & 0x7ffu;
+                            const bool oka = (PM & na.y) && ((ya - ba) & 0x800u) && q1 >= q0 && (q1 <= hi || q1 == q0);
+                            push2(oka, false, ba, ba, na, na);
+                            k++;
                         }
                         const bool row_done = flush && k >= ke;   // the closing pass of the group: whatever is left in s2
                         if (ns < 32 && !row_done) break;          // every node has seen this row
                         const int n = min(ns, 32);
                         bool ok = lane < n;
+                        __syncwarp();                             // the pairs pushed above are visible to the lanes that take them
                         const uint32_t it = ok ? s2[ns - n + lane] : 0;
                         ns -= n;
                         __syncwarp();
