@@ -57,7 +57,15 @@ def ncu_summary(kernel="scan_fast"):
                 pass
     if "dram__bytes_read.sum" not in vals:
         return None
-    return {"file": os.path.relpath(files[-1], ROOT),
+    pct = {}
+    for line in open(files[-1]):
+        t = line.strip().split(",")
+        if len(t) == 3 and t[1] == "%":
+            try:
+                pct[t[0]] = float(t[2])
+            except ValueError:
+                pass
+    return {"file": os.path.relpath(files[-1], ROOT), "pct": pct,
             "dram_bytes": vals["dram__bytes_read.sum"] + vals.get("dram__bytes_write.sum", 0.0),
             "warp_instructions": vals.get("smsp__inst_executed.sum"), "ms": vals.get("gpu__time_duration.sum")}
 
@@ -98,6 +106,21 @@ class ClockSampler(threading.Thread):
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(self.rows)}
+
+
+def cal_roofline(kernel_ms, samples, n_class):
+    """calibrate_kernel against the fp64 pipe: one exp (the class weight) and the score's bucket per (sample, class).  The
+    algorithmic work is counted in (sample, class) pairs; the pipe figures come from the committed ncu capture of one launch
+    of 2^20 samples (profiles/r*_calibrate_ncu_full.csv), the rate is measured live."""
+    ncu = ncu_summary("calibrate")
+    out = {"bound": "fp64 pipe / issue", "achieved": samples * n_class / (kernel_ms * 1e-3), "unit": "(sample, class) pairs/s"}
+    if ncu:
+        p = ncu["pct"]
+        out.update({"source": ncu["file"],
+                    "fp64_pipe_pct_of_peak": p.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                    "issue_active_pct": p.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "ncu_launch_ms": ncu.get("ms"), "dram_bytes": ncu.get("dram_bytes")})
+    return out
 
 
 def chromosome_counts(n, first=0):
@@ -439,7 +462,8 @@ def run_ours(args):
                                         "histograms all-reduced over the GPUs after every block, the reference's convergence "
                                         "rule on the reduced table, min(samples, 4^L) samples per model"},
                             "cpu_baseline": cal_cpu,
-                            "python_reference": pyref.get("calibrate_1core") if isinstance(pyref, dict) else None},
+                            "python_reference": pyref.get("calibrate_1core") if isinstance(pyref, dict) else None,
+                            "roofline": cal_roofline(cal_kernel_ms, CAL_SAMPLES * len(models), len(cl))},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -496,12 +520,36 @@ def run_genome(args):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    from rmdetect_b200.hittable import HitTable
+    table = HitTable(eng)                                         # every rank's hits stay on its GPU, as rows of a table
     r = scan_synthetic_genome(eng, total, True, SEED, WIN_LEN, WIN_STEP, MIN_BPP, LN_CUTOFF, rank=rank, world=world,
-                              dist=dist, piece_windows=piece, min_score=args.min_score)
+                              dist=dist, piece_windows=piece, min_score=args.min_score, table=table)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    # rmfilter's work on the device-resident list (lib/candidates.py:99-207): order, overlaps, best hits per model
+    rows0 = len(table)
+    t1 = time.perf_counter()
+    table.sort()
+    t_sort = time.perf_counter() - t1
+    t1 = time.perf_counter()
+    rows1 = table.nooverlap()
+    t_noov = time.perf_counter() - t1
+    t1 = time.perf_counter()
+    rows2 = table.top_model(1000)
+    t_top = time.perf_counter() - t1
+    best = table.rows(0, min(rows2, 4))
+    tt = torch.tensor([rows0, rows1, rows2], dtype=torch.int64, device="cuda")
+    ts = torch.tensor([t_sort, t_noov, t_top], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    table_line = {"rows": int(tt[0]), "sort_s": float(ts[0]), "rows_after_nooverlap": int(tt[1]), "nooverlap_s": float(ts[1]),
+                  "rows_after_top_model_1000": int(tt[2]), "top_model_s": float(ts[2]),
+                  "best_scores_rank0": [float(x) for x in best["score"]],
+                  "note": "hits with score > min_score kept as 64-byte rows on each rank's GPU (rmd_table_*): sorted in the "
+                          "reference's Candidate order, nooverlap replayed, 1000 best per model kept; seconds are the max over ranks"}
     t = torch.tensor([wall, r["rank_ms_generate"], r["rank_ms_scan_kernel"], r["rank_ms_device"]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -524,7 +572,8 @@ def run_genome(args):
                                  "place), which is not part of the metric",
                        "wall_s": wall, "scan_device_s": ms_dev * 1e-3, "scan_kernel_s": ms_kernel * 1e-3,
                        "generation_s": ms_gen * 1e-3,
-                       "value_incl_generation": units / wall},
+                       "value_incl_generation": units / wall,
+                       "hit_table": table_line},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -83,7 +83,7 @@ def strand_gc(counts_fwd, reverse):
 
 def scan_synthetic_genome(engine, total_nt, both_strands, seed, win_len, win_step, min_bpp_mean, cutoff,
                           rank=0, world=1, dist=None, piece_windows=266_667, on_hits=None, min_score=None,
-                          forward_counts=None):
+                          forward_counts=None, table=None):
     """Scan `rank`'s share of a synthetic genome of `total_nt` letters per strand.
 
     Returns a dict with whole-job totals (after the closing all-reduce when `dist` is given): tests_all,
@@ -91,6 +91,8 @@ def scan_synthetic_genome(engine, total_nt, both_strands, seed, win_len, win_ste
     own hits (window starts relative to `lo`) when the caller wants the records themselves.  `min_score` moves
     the command line's score filter (reference rmdetect.py:44, default 5.0 there) in front of the download.
     `forward_counts` (A, C, G, U of the whole forward strand) replaces the counting pass and its all-reduce.
+    `table` (a `hittable.HitTable`) collects every piece's own hits on the device, in strand coordinates, under the keys
+    "genome" and "genome--" (lib/sequences.py:138-143): the list rmfilter / rmcluster would work on never leaves the GPU.
     """
     import torch
     ctx = engine.ctx
@@ -129,6 +131,8 @@ def scan_synthetic_genome(engine, total_nt, both_strands, seed, win_len, win_ste
                 ev.select_gc(gc)
                 cls.append(-1 if ev.selected is None else ev.selected)
         tab = gc_table(gc)
+        if table is not None:
+            table.key_id("genome--" if strand else "genome")
         ctx.synth_strand(total_nt, strand == 1)
         for a, b, bh, plo, phi in rank_pieces(total_nt, win_len, win_step, rank, world, piece_windows):
             n_win, n_bpp, ms = ctx.synth_job(phi - plo, plo, seed, seed, win_len, win_step, min_bpp_mean, cutoff, tab, cls)
@@ -136,7 +140,10 @@ def scan_synthetic_genome(engine, total_nt, both_strands, seed, win_len, win_ste
             r = ctx.scan_resident(0, n_win, copy=False)
             own = b - a
             h = r["hits"]
-            h = h[h["window"] < own]                  # halo windows only served the duplicate rule
+            n_own = int(np.searchsorted(h["window"], own))   # hits are in window order
+            h = h[:n_own]                             # halo windows only served the duplicate rule
+            if table is not None and n_own:
+                table.append_scan(["genome--" if strand else "genome"], start_base=plo, first_n=n_own)
             n_hits += len(h)
             n_raw += int(np.asarray(r["raw_count"])[:own].sum())
             tests_pairs += int(np.asarray(r["gate_pass"])[:own].sum())
