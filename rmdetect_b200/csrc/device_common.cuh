@@ -167,6 +167,8 @@ struct ScanOut {
     uint32_t *group_hits;            // [n_win_range][n_models]
     const uint32_t *other_list;      // windows with a letter other than ACGU, relative to the range (scan_fast_kernel<..., OTHER>)
     const uint32_t *other_count;
+    const unsigned int *ready;       // streamed scan in one launch: windows (relative to the range) whose lists have arrived, advanced by the
+                                     // copy stream while the kernel runs; nullptr: everything is resident
 };
 
 __device__ __forceinline__ int get_code(const DevJob &J, long long g) {

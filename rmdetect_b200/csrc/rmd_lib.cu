@@ -115,6 +115,7 @@ struct rmd_ctx {
     bool compact_hits = false;          // rmd_set_hit_format
     DBuf d_pack;
     uint32_t *h_gate = nullptr, *h_group = nullptr;
+    unsigned int *h_ready = nullptr;    // pinned: progress marks of a streamed scan (windows whose lists have been copied)
     size_t h_gate_cap = 0;
     long long raw_cap = 0;
     bool return_dropped = false;
@@ -213,6 +214,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
+    if (ctx->h_ready) cudaFreeHost(ctx->h_ready);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -888,6 +890,10 @@ static int ensure_host(rmd_ctx *ctx, size_t hits, size_t groups) {
 // are not on the device yet: they are copied in window chunks on the copy stream while the compute
 // stream scans the chunks already there.
 #define STREAM_CHUNKS 16
+#define STREAM_PIECES 40                  // copies of a streamed scan that runs as ONE launch (compact transport)
+#ifndef STREAM_GROWTH_FUSED
+#define STREAM_GROWTH_FUSED 45             // per cent by which a chunk's end grows over the previous one's (compact transport)
+#endif
 static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out, const rmd_scan_input *stream_in) {
     if (!ctx || !out) return fail(ctx, RMD_E_INVALID, "rmd_scan_resident: NULL argument");
     if (!ctx->have_job) return fail(ctx, RMD_E_STATE, "rmd_scan_resident: no resident job");
@@ -904,7 +910,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     CK(cudaEventRecord(ctx->ev[8], st));
     if (ctx->screens_dirty) { int rs = build_screens(ctx); if (rs) return rs; }
     RESERVE(ctx->d_counters, 128);
-    RESERVE(ctx->d_next, sizeof(unsigned int) * (STREAM_CHUNKS + 1));
+    RESERVE(ctx->d_next, sizeof(unsigned int) * (STREAM_CHUNKS + 2));
     RESERVE(ctx->d_gate_pass, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_hits, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(ngroups + 1));
@@ -923,13 +929,14 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         RESERVE(ctx->d_raw, sizeof(RawHit) * (size_t)ctx->raw_cap);
         launches = 0;
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, 128, st));
-        CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(unsigned int) * (STREAM_CHUNKS + 1), st));
+        CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(unsigned int) * (STREAM_CHUNKS + 2), st));
         CK(cudaMemsetAsync(ctx->d_gate_pass.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         CK(cudaMemsetAsync(ctx->d_group_hits.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         ScanOut O;
         O.raw = (RawHit *)ctx->d_raw.p; O.raw_count = (unsigned long long *)ctx->d_counters.p; O.stats = O.raw_count + 8; O.raw_cap = ctx->raw_cap;
         O.gate_pass = (uint32_t *)ctx->d_gate_pass.p; O.group_hits = (uint32_t *)ctx->d_group_hits.p;
         O.other_list = (const uint32_t *)ctx->d_other.p; O.other_count = O.other_list ? O.other_list + nwin : nullptr;
+        O.ready = nullptr;
         CK(cudaEventRecord(ctx->ev[0], st));
         if (other_fast && nwin > 0) {
             CK(cudaMemsetAsync((uint32_t *)ctx->d_other.p + nwin, 0, sizeof(uint32_t), st));
@@ -954,7 +961,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                 // without expansion launches, and with the chunks' tails overlapping on two streams, a launch costs less
                 const bool will_fuse = use_fast && !need_generic && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
                                        !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");
-                const int gpct = will_fuse ? 45 : 60;
+                const int gpct = will_fuse ? STREAM_GROWTH_FUSED : 60;
                 long long end = std::max<long long>(nwin / 128, 2048);
                 while (end < nwin && n_chunks < STREAM_CHUNKS - 1) { bounds[++n_chunks] = w_begin + end; end = end + end * gpct / 100 + 1024; }
                 bounds[++n_chunks] = w_end;
@@ -974,13 +981,48 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             ctx->job.bpp_q = fused ? (const uint32_t *)ctx->d_bpp_q.p : nullptr;
         }
         const bool fused_expand = ctx->job.bpp_q != nullptr;
-        const bool two_streams = streaming && fused_expand && n_chunks > 1;
+        const bool two_streams = false;                            // (chunk launches of the compact transport alternated between two streams before the one-launch scan)
         if (two_streams) {                                          // the second compute stream starts after the resets above
             CK(cudaEventRecord(ctx->ev[12], st));
             CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[12], 0));
         }
         const cudaStream_t first_stream = st;
-        for (int ch = 0; ch < n_chunks && nwin > 0; ch++) {
+        // Compact transport, every window the shared-memory kernel's: ONE launch scans the whole range while the copy
+        // stream is still delivering it.  After every piece of the lists the copy stream writes a progress mark (the
+        // number of windows that are complete); a team that draws a window beyond the mark waits for it.  No launch
+        // tails between chunks, no chunk schedule to tune: the scan ends when the slower of copy and kernel ends.
+        const bool one_launch = streaming && fused_expand && nwin > 0 && n_chunks > 1;
+        if (one_launch) {
+            if (!ctx->h_ready) CK(cudaMallocHost((void **)&ctx->h_ready, sizeof(unsigned int) * (STREAM_PIECES + 2)));
+            unsigned int *d_ready = (unsigned int *)ctx->d_next.p + STREAM_CHUNKS + 1;
+            O.ready = d_ready;
+            CK(cudaEventRecord(ctx->ev[12], st));                   // the mark was zeroed on `st`: marks come after that
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[12], 0));
+            const unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * ctx->ctas_per_sm, (nwin + ctx->teams - 1) / ctx->teams);
+            scan_fast_kernel<false, true, false, true><<<grid, (unsigned)ctx->teams * SCAN_THREADS, ctx->scan_smem, st>>>(
+                J, w_begin, w_end, w_begin, O, min_fast_wlen, (unsigned int *)ctx->d_next.p);
+            launches++;
+            // a small first piece (the kernel starts on it), equal pieces after it
+            const long long first = std::min<long long>(nwin, std::max<long long>(nwin / 128, 1024));
+            const long long rest = (nwin - first + STREAM_PIECES - 2) / (STREAM_PIECES - 1);
+            int rc = RMD_OK, k = 0;
+            for (long long c0 = 0; c0 < nwin && rc == RMD_OK; k++) {
+                const long long c1 = k == 0 ? first : std::min(nwin, c0 + std::max<long long>(rest, 1));
+                rc = stage_entries(ctx, stream_in, stream_in->bpp_off[w_begin + c0], stream_in->bpp_off[w_begin + c1], ctx->copy_stream, false);
+                ctx->h_ready[k] = (unsigned int)c1;
+                if (rc == RMD_OK && cudaMemcpyAsync(d_ready, ctx->h_ready + k, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
+                    rc = fail(ctx, RMD_E_CUDA, "progress mark of a streamed scan could not be enqueued: %s", cudaGetErrorString(cudaGetLastError()));
+                c0 = c1;
+            }
+            if (rc != RMD_OK) {                                     // never leave the kernel waiting for lists that will not come
+                ctx->h_ready[STREAM_PIECES + 1] = 0xffffffffu;
+                cudaMemcpyAsync(d_ready, ctx->h_ready + STREAM_PIECES + 1, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copy_stream);
+                cudaStreamSynchronize(ctx->copy_stream);
+                cudaStreamSynchronize(st);
+                return rc;
+            }
+        }
+        for (int ch = 0; ch < n_chunks && nwin > 0 && !one_launch; ch++) {
             const long long c0 = bounds[ch], c1 = bounds[ch + 1];
             const cudaStream_t st = two_streams && (ch & 1) ? ctx->stream2 : first_stream;
             if (streaming) {                                        // entries of windows [c0, c1): copy stream, then let the scan wait for them
@@ -1029,6 +1071,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         CK(cudaGetLastError());
         if (counters[7] & ERR_BAD_LIST) return fail(ctx, RMD_E_INVALID, "a window's bpp list is not a sorted, duplicate-free upper triangle (i < j < window length)");
         if (counters[7] & ERR_BAD_VALUE) return fail(ctx, RMD_E_INVALID, "a bpp value is negative or not a number");
+        if (counters[7] & ERR_TIMEOUT) return fail(ctx, RMD_E_CUDA, "streamed scan: the lists of some windows did not arrive within ten seconds");
         if ((long long)counters[0] <= ctx->raw_cap) break;
         if (attempt == 1) return fail(ctx, RMD_E_NOMEM, "hit buffer overflow persisted (%llu records)", counters[0]);
         ctx->raw_cap = (long long)counters[0] + (long long)counters[0] / 8 + 1024;   // rerun with room for every record

@@ -67,6 +67,7 @@
 #define SCAN_CTA_FIXED (TRIE_CAP * 32)   // bytes of CTA-wide state in front of the teams' blocks: gate tries (8 B per node), cinfo, ancw, cnw (16 B per node)
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
+#define ERR_TIMEOUT 4ull                // a streamed scan waited ten seconds for lists that never arrived
 
 struct WarpQueues {                      // one warp's work lists (one base address per warp)
     uint32_t wl[WL_CAP];                 // big entries waiting for a full row, i | j << 8 | sure-mask << 16
@@ -377,7 +378,26 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     };
 
     for (int turn = 0;; turn ^= 1) {
-        if (tid == 0) sm.next[turn] = atomicAdd(next_window, 1u);
+        if (tid == 0) {
+            unsigned int nx = atomicAdd(next_window, 1u);
+            if (FUSED && O.ready != nullptr && w_begin + nx < w_end) {
+                // the lists of this window may still be on their way (rmd_scan copies them while this one launch runs):
+                // wait for the copy stream's progress mark, which it writes after the data
+                unsigned int have;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(O.ready) : "memory");
+                if (have <= nx) {
+                    unsigned long long t0, t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    do {
+                        __nanosleep(400);
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(O.ready) : "memory");
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 10000000000ull) { atomicOr(&O.raw_count[7], ERR_TIMEOUT); nx = 0xffffffffu; break; }
+                    } while (have <= nx);
+                }
+            }
+            sm.next[turn] = nx;
+        }
         team_sync(team);
         const bool last = OTHER ? sm.next[turn] >= *O.other_count : w_begin + sm.next[turn] >= w_end;
         const long long w = w_begin + (OTHER ? (last ? w_end - w_begin : (long long)O.other_list[sm.next[turn]]) : (long long)sm.next[turn]);
@@ -459,12 +479,12 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 ei[k] = ej[k] = 0; pi[k] = pj[k] = -1;
                 if (FUSED) {                                  // compact transport: i | j << 8, and the value is rebuilt here
                     if (e < nnz) {
-                        const uint32_t w16 = J.bpp_ij[b0 + e], v = J.bpp_q[b0 + e];
+                        const uint32_t w16 = __ldcg(J.bpp_ij + b0 + e), v = __ldcg(J.bpp_q + b0 + e);   // L2: the copy engine may have just written them
                         ei[k] = w16 & 0xffu; ej[k] = w16 >> 8;
                         const double x = __ddiv_rn((double)(v & 0x3fffffffu), 1e9);       // as expand_bpp_kernel (post_kernels.cuh)
                         const_cast<double *>(vals)[e] = __longlong_as_double(__double_as_longlong(__dmul_rn(x, x)) + (long long)(v >> 30) - 1);
                     }
-                    if (e < nnz && e > 0) { const uint32_t w16 = J.bpp_ij[b0 + e - 1]; pi[k] = w16 & 0xffu; pj[k] = w16 >> 8; }
+                    if (e < nnz && e > 0) { const uint32_t w16 = __ldcg(J.bpp_ij + b0 + e - 1); pi[k] = w16 & 0xffu; pj[k] = w16 >> 8; }
                 } else {
                     if (e < nnz) { ei[k] = J.bpp_i[b0 + e]; ej[k] = J.bpp_j[b0 + e]; }
                     if (e < nnz && e > 0) { pi[k] = J.bpp_i[b0 + e - 1]; pj[k] = J.bpp_j[b0 + e - 1]; }
@@ -658,7 +678,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                         if (e < nnz) {
                             const double p = FUSED ? vals[e] : __ldg(vals + e);   // independent loads: one memory latency per chunk
                             uint32_t ei, ej;
-                            if (FUSED) { const uint32_t w16 = J.bpp_ij[b0 + e]; ei = w16 & 0xffu; ej = w16 >> 8; }
+                            if (FUSED) { const uint32_t w16 = __ldcg(J.bpp_ij + b0 + e); ei = w16 & 0xffu; ej = w16 >> 8; }
                             else { ei = J.bpp_i[b0 + e]; ej = J.bpp_j[b0 + e]; }
                             if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
                             if (p >= big_min) {

@@ -70,4 +70,7 @@ if args.e2e:
         e = eng.ctx.scan(job, copy=False)
     print("e2e: total %.3f ms | h2d(first stage) %.3f  scan %.3f  post %.3f  d2h %.3f | launches %d"
           % (e["ms_total"], e["ms_h2d"], e["ms_scan"], e["ms_post"], e["ms_d2h"], e["n_launches"]))
+    for k in range(args.steps):                     # the job stays resident in the compact form: the FUSED kernel without any copy
+        r3 = eng.ctx.scan_resident(0, n_win)
+    print("resident after rmd_scan (values rebuilt per window, FUSED): scan %.3f ms" % r3["ms_scan"])
 eng.close()
