@@ -961,3 +961,19 @@ int64_t orc_calibrate(void *h, const char *samples, int64_t n, int L, const doub
     }
     return nok;
 }
+
+/* Test support for the device's expansion of the compact bpp transport (rmdetect_b200/csrc/device_common.cuh:
+   transport_root): q * 1e-9 corrected by its exact residual equals the IEEE quotient q / 1e9 for EVERY q below 2^30.
+   The three operations are correctly rounded IEEE operations on the host and on the GPU alike, so the exhaustive check
+   here settles it for both.  Returns the number of mismatches (0). */
+__attribute__((target("fma"))) int64_t orc_check_div1e9(void) {
+    int64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+    for (int64_t q = 0; q < ((int64_t)1 << 30); q++) {
+        const double x = (double)q, want = x / 1e9;
+        const double y = x * 1e-9;
+        const double got = fma(fma(-y, 1e9, x), 1e-9, y);
+        if (got != want) bad++;
+    }
+    return bad;
+}

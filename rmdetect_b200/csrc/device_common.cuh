@@ -217,6 +217,15 @@ __device__ __forceinline__ unsigned long long odometer_count(const CModel &M, in
     return (unsigned long long)n0 * (unsigned long long)(p1_last(wlen, L1, 0) + 1);
 }
 
+// q / 1e9 for a transport word q < 2^30 (rmd_compact_bpp), correctly rounded, without the division subroutine: a product
+// with the rounded reciprocal, its exact residual, one correction.  Equal to the IEEE quotient for every q below 2^30 —
+// checked exhaustively on the host with the same three IEEE operations (oracle/rmd_oracle.c: orc_check_div1e9,
+// tests/test_ingest.py).
+__device__ __forceinline__ double transport_root(uint32_t q) {
+    const double x = (double)q, y = __dmul_rn(x, 1e-9);
+    return __fma_rn(__fma_rn(-y, 1e9, x), 1e-9, y);
+}
+
 struct EvalOut { int leaf; double pm, pr; };
 
 // NodeSearch.eval + the winner of get_solution (lib/node.py:153-277) on the flattened tree.

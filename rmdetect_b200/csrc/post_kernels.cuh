@@ -174,7 +174,7 @@ __global__ void expand_bpp_kernel(const uint16_t *ij, const uint32_t *q, long lo
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t w = ij[k], v = q[k];
-    const double x = __ddiv_rn((double)(v & 0x3fffffffu), 1e9);
+    const double x = transport_root(v & 0x3fffffffu);
     const long long bits = __double_as_longlong(__dmul_rn(x, x)) + (long long)(v >> 30) - 1;
     oi[k] = (uint16_t)(w & 0xffu);
     oj[k] = (uint16_t)(w >> 8);

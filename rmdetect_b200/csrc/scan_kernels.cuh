@@ -481,7 +481,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     if (e < nnz) {
                         const uint32_t w16 = __ldcg(J.bpp_ij + b0 + e), v = __ldcg(J.bpp_q + b0 + e);   // L2: the copy engine may have just written them
                         ei[k] = w16 & 0xffu; ej[k] = w16 >> 8;
-                        const double x = __ddiv_rn((double)(v & 0x3fffffffu), 1e9);       // as expand_bpp_kernel (post_kernels.cuh)
+                        const double x = transport_root(v & 0x3fffffffu);                 // as expand_bpp_kernel (post_kernels.cuh)
                         const_cast<double *>(vals)[e] = __longlong_as_double(__double_as_longlong(__dmul_rn(x, x)) + (long long)(v >> 30) - 1);
                     }
                     if (e < nnz && e > 0) { const uint32_t w16 = __ldcg(J.bpp_ij + b0 + e - 1); pi[k] = w16 & 0xffu; pj[k] = w16 >> 8; }

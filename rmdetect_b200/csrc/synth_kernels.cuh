@@ -124,7 +124,7 @@ synth_bpp_kernel(const DevJob J, unsigned long long seed, uint32_t *bpp_cnt, con
             for (int j = i + 4; j < n; j++) {
                 const long long v = synth_cell(lt, n, key, i, j);
                 if (v > 0) {
-                    const double root = __ddiv_rn((double)v, 1e9);
+                    const double root = transport_root((uint32_t)v);
                     oi[dst] = (uint16_t)i; oj[dst] = (uint16_t)j; op[dst] = __dmul_rn(root, root);
                     dst++;
                 }

@@ -55,3 +55,13 @@ def test_compact_round_trip_and_rejects():
     assert compact_bpp(i[:3], j[:3], np.array([0.1234567891234, 0.5, 0.5])) is None          # not a squared 9-decimal
     assert compact_bpp(np.array([300], dtype=np.uint16), np.array([301], dtype=np.uint16), p[:1]) is None
     assert compact_bpp(i[:1], j[:1], np.array([-0.25])) is None
+
+
+def test_transport_root_is_the_ieee_quotient_for_every_word():
+    """The device expands a transport word q as q * 1e-9 plus one residual correction (csrc/device_common.cuh:
+    transport_root) instead of dividing by 1e9; the same three IEEE operations on the host give q / 1e9 for all 2^30 words."""
+    import ctypes as C
+    from oracle import pyoracle
+    L = pyoracle.lib()
+    L.orc_check_div1e9.restype = C.c_int64
+    assert L.orc_check_div1e9() == 0
