@@ -273,6 +273,7 @@ def run_ours(args):
     units = n * len(models)
 
     # ---- device-resident scan ------------------------------------------------------------------
+    ctx.set_hit_format(True)                                    # hits come back as 32-byte records (rmd_hit32), as in the e2e arm
     for _ in range(args.warmup):
         ctx.scan_resident(0, n_win, copy=False)
     sampler = ClockSampler(local)
@@ -287,6 +288,7 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t0
     n_hits, n_raw, tries = len(r["hits"]), r["n_raw"], r["tries"]
+    ctx.set_hit_format(False)
     # one untimed scan that also returns the hits the duplicate rule removed: what the CPU baseline's sample is checked against
     ctx.set_return_dropped(True)
     full = ctx.scan_resident(0, n_win, copy=True)
