@@ -286,3 +286,92 @@ def test_fasta_reader_follows_the_reference(tmp_path):
     seqs = read_fasta(str(path))
     assert seqs == [("chr1", "ACGUNNACGURYACG"), ("chr2", "GGGUUU")]
     assert [(k + "--", reverse_complement(q)) for k, q in seqs] == [("chr1--", "CGUYRACGUNNACGU"), ("chr2--", "AAACCC")]
+
+
+# ---- world size 2 on CPU (gloo) for the real-input driver: pieces, strands, the closing all-reduce ----------------------
+class _OracleJobEngine:
+    """Plays `ScanEngine` for `scan_genome`: `build_job` keeps the piece, `ctx.scan` scans it with the CPU oracle (the
+    host-side plumbing of the N > 1 path; the CUDA path is covered by test_fasta_genome_in_pieces_equals_the_scanner)."""
+
+    def __init__(self, names):
+        from oracle import pyoracle
+        self.py = pyoracle
+        self.models = [load_model(n) for n in names]
+        self.evalues = [load_evalues(n) for n in names]
+        self.oms = [pyoracle.OracleModel(m) for m in self.models]
+        self.oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+        self.ctx = self
+        self.min_score = None
+
+    def set_min_score(self, v):
+        self.min_score = v
+
+    def build_job(self, seqs, win_len, win_step, fold, constraint, min_bpp, cutoff, gc=None):
+        (key, seq, _), = seqs
+        starts = window_starts(len(seq), win_len, win_step)
+        return dict(seq=seq, gc=gc, fold=fold, n_win=len(starts), starts=[starts], win=(win_len, win_step), min_bpp=min_bpp, cutoff=cutoff)
+
+    def scan(self, job, copy=False):
+        from rmdetect_b200._native import HIT_DTYPE
+        W, step = job["win"]
+        seq, starts = job["seq"], job["starts"][0]
+        for oe, ev in zip(self.oes, self.evalues):
+            ev.select_gc(job["gc"])
+            oe.selected = ev.selected
+        bpp = [job["fold"].coo(seq[s:s + W]) for s in starts.tolist()]
+        hits, tries, tpw = self.py.scan_sequence(self.oms, self.oes, 0, seq, W, step, bpp, job["min_bpp"], LN_UNKNOWN, job["cutoff"], gc=job["gc"])
+        if self.min_score is not None:
+            hits = [h for h in hits if h["score"] > self.min_score]
+        out = np.zeros(len(hits), dtype=HIT_DTYPE)
+        for k, h in enumerate(hits):
+            out[k] = (int(np.searchsorted(starts, h["coords"][0])), h["coords"][0], 0, h["coords"][1] - h["coords"][0], h["p"][0], h["p"][1],
+                      h["model"], h["cfg"], 1, h["prob_model"], h["prob_rand"], h["score"], h["evalue"])
+        gate = np.zeros((len(starts), len(self.oms)), dtype=np.uint32)
+        gate[:, 0] = tpw[:len(starts), 1]
+        return dict(hits=out, gate_pass=gate, raw_count=np.zeros_like(gate), ms_scan=0.0, ms_total=0.0)
+
+
+def _fasta_worker(rank, world, port, q):
+    import os
+    import random
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from rmdetect_b200.genome import scan_genome
+    from rmdetect_b200.synth import SynthFold
+    rng = random.Random(3)
+    seqs = [("chrA", "".join(rng.choice("ACGU") for _ in range(1100))), ("chrB", "".join(rng.choice("ACGUN") for _ in range(400)))]
+    names = ["TGA_1.0", "KT_1.0"]
+    got = []
+    r = scan_genome(_OracleJobEngine(names), seqs, SynthFold(4), both_strands=True, rank=rank, world=world, dist=dist, piece_windows=3,
+                    min_score=2.0, on_hits=lambda key, h: got.extend((key, int(x["start"]), int(x["p0"]), int(x["p1"]), int(x["model"])) for x in h))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, got)
+    if rank == 0:
+        one_hits = []
+        one = scan_genome(_OracleJobEngine(names), seqs, SynthFold(4), both_strands=True, piece_windows=1000, min_score=2.0,
+                          on_hits=lambda key, h: one_hits.extend((key, int(x["start"]), int(x["p0"]), int(x["p1"]), int(x["model"])) for x in h))
+        keys = ("tests_all", "tests_pairs", "hits", "windows", "checksum", "strands")
+        q.put(({k: r[k] for k in keys}, {k: one[k] for k in keys}, sorted(sum(gathered, [])), sorted(one_hits)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_share_fasta_sequences_over_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fasta_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    two, one, hits2, hits1 = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert two == one and hits2 == hits1 and one["hits"] > 0 and one["strands"] == 4
