@@ -39,6 +39,13 @@ def to_coo(bpp, win_len):
     """
     if hasattr(bpp, "coo"):
         i, j, p = bpp.coo()
+        if (isinstance(i, np.ndarray) and i.dtype == np.uint16 and isinstance(j, np.ndarray) and j.dtype == np.uint16
+                and isinstance(p, np.ndarray) and p.dtype == np.float64 and len(i) == len(j) == len(p)):
+            # a provider that already hands over the kernel's form (fold.RNAfold's parser, synth.SynthFold): one check
+            # that the list is a strictly increasing upper triangle inside the window with no zeros
+            key = i.astype(np.int32) * 65536 + j
+            if len(i) == 0 or ((i < j).all() and int(j.max()) < win_len and (p != 0.0).all() and (len(i) == 1 or (key[1:] > key[:-1]).all())):
+                return i, j, p
         i = np.asarray(i, dtype=np.int64)
         j = np.asarray(j, dtype=np.int64)
         p = np.asarray(p, dtype=np.float64)

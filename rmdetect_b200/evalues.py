@@ -29,17 +29,38 @@ class EValues:
 
     def select_gc(self, gc):
         # reference lib/evalues.py:12-23: Euclidean distance over the class's own letters,
-        # a letter absent from `gc` counts as e**0 = 1; strict '<' so the first minimum wins
+        # a letter absent from `gc` counts as e**0 = 1; strict '<' so the first minimum wins.
+        # Same floating-point operations in the same order as the reference; only the four `e ** gc[k]` are taken
+        # once per call instead of once per class (same function, same argument: same bits).
+        items = self._class_items()
+        last = getattr(self, "_last_gc", None)
+        key = tuple(gc.items())
+        if last is not None and last[0] == key and last[1] is items:
+            self.selected = last[2]
+            return self.selected
+        power = {}
         min_d = None
-        for i, gc_class in enumerate(self.gc_classes):
+        for i, pairs in enumerate(items):
             x = 0.0
-            for k, v in gc_class.items():
-                x += (v - math.e ** gc.get(k, 0)) ** 2
+            for k, v in pairs:
+                e = power.get(k)
+                if e is None:
+                    e = power[k] = math.e ** gc.get(k, 0)
+                x += (v - e) ** 2
             d = math.sqrt(x)
             if min_d is None or d < min_d:
                 min_d = d
                 self.selected = i
+        self._last_gc = (key, items, self.selected)
         return self.selected
+
+    def _class_items(self):
+        """gc_classes as a tuple of ((letter, value), ...) in dict order, rebuilt when the list changes."""
+        cached = getattr(self, "_items", None)
+        if cached is None or cached[0] is not self.gc_classes or cached[1] != len(self.gc_classes):
+            cached = (self.gc_classes, len(self.gc_classes), tuple(tuple(c.items()) for c in self.gc_classes))
+            self._items = cached
+        return cached[2]
 
     def compute(self, score):
         # reference lib/evalues.py:25-36 (host restatement, used by the drop-in API and tests)

@@ -46,14 +46,17 @@ def window_starts(seq_len, win_len, win_step):
 
 
 def placements_in_window(model, wlen):
-    """How many pointer settings the odometer tries in a window of `wlen` letters (tests_all)."""
+    """How many pointer settings the odometer tries in a window of `wlen` letters (tests_all): closed form of the loop
+    (reference lib/scanner.py:137-157,161-193; same formula as the device's odometer_count)."""
     if wlen <= 0:
         return 0
     L0, L1 = model.chains_length[0], model.chains_length[1]
     n0 = max(1, wlen - L0)
     if not model.symmetric:
         return n0 * max(1, wlen - L1)
-    return sum(max(1, wlen - L1 - p0) for p0 in range(n0))
+    a = wlen - L1                                  # sum over p0 < n0 of max(1, a - p0)
+    k = min(max(a, 0), n0)
+    return k * a - k * (k - 1) // 2 + (n0 - k)
 
 
 def gc_of_codes(codes, others):
@@ -107,12 +110,19 @@ class ScanEngine:
             off.append(off[-1] + len(codes))
             gcs.append(g)
             gc_tabs.append(gc_table(g, others))
-            cls = []
+            cls, same = [], {}
             for ev in self.evalues:
                 if ev is None or not ev.gc_classes:
                     cls.append(-1)
                 else:
-                    ev.select_gc(g)
+                    # models calibrated on the same GC classes (the shipped ones all are) select the same class
+                    items = ev._class_items() if hasattr(ev, "_class_items") else None
+                    if items is not None and items in same:
+                        ev.selected = same[items]
+                    else:
+                        ev.select_gc(g)
+                        if items is not None:
+                            same[items] = ev.selected
                     cls.append(-1 if ev.selected is None else ev.selected)
             gc_cls.append(cls)
             starts = window_starts(len(seq), win_len, win_step)
