@@ -535,9 +535,13 @@ def run_genome(args):
     t1 = time.perf_counter()
     table.sort()
     t_sort = time.perf_counter() - t1
+    if table.first_unsorted() != -1:
+        raise SystemExit("bench.py: the hit table is not in Candidate order after rmd_table_sort")
     t1 = time.perf_counter()
     rows1 = table.nooverlap()
     t_noov = time.perf_counter() - t1
+    if table.nooverlap() != rows1:                                # no two survivors are duplicates: a second pass removes nothing
+        raise SystemExit("bench.py: rmd_table_nooverlap is not idempotent")
     t1 = time.perf_counter()
     rows2 = table.top_model(1000)
     t_top = time.perf_counter() - t1
@@ -551,7 +555,8 @@ def run_genome(args):
                   "rows_after_top_model_1000": int(tt[2]), "top_model_s": float(ts[2]),
                   "best_scores_rank0": [float(x) for x in best["score"]],
                   "note": "hits with score > min_score kept as 64-byte rows on each rank's GPU (rmd_table_*): sorted in the "
-                          "reference's Candidate order, nooverlap replayed, 1000 best per model kept; seconds are the max over ranks"}
+                          "reference's Candidate order (checked row against row on the device), nooverlap replayed (a second pass removes nothing), "
+                          "1000 best per model kept; seconds are the max over ranks"}
     t = torch.tensor([wall, r["rank_ms_generate"], r["rank_ms_scan_kernel"], r["rank_ms_device"]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

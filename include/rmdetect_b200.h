@@ -268,6 +268,8 @@ int rmd_table_filter(rmd_ctx *ctx, const double *min_score, const double *min_bp
 /* lib/candidates.py:380-394 Candidate.__cmp__ order, stable: key_rank[key] ascending (rank of the key string among all key
    strings, equal strings equal ranks), E-value ascending, score descending */
 int rmd_table_sort(rmd_ctx *ctx, const int32_t *key_rank, int32_t n_keys);
+/* *first_bad = the first row that compares smaller than its predecessor in that order, -1 when the table is sorted */
+int rmd_table_is_sorted(rmd_ctx *ctx, const int32_t *key_rank, int32_t n_keys, int64_t *first_bad);
 /* lib/candidates.py:99-154 top_model (group 0) / top_seq (1) / top_seq_model (2): sort, then the first top_n rows of every group */
 int rmd_table_top(rmd_ctx *ctx, int32_t group, int32_t top_n, const int32_t *key_rank, int32_t n_keys, int64_t *n_rows);
 /* lib/candidates.py:171-207 nooverlap, replayed in table order (the result depends on it, as the reference's does) */

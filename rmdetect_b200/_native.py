@@ -67,7 +67,7 @@ EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_se
            "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_cpt_counts", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free",
            "rmd_table_clear", "rmd_table_rows", "rmd_table_append_scan", "rmd_table_append_rows", "rmd_table_download",
-           "rmd_table_filter", "rmd_table_sort", "rmd_table_top", "rmd_table_nooverlap", "rmd_table_cluster_index",
+           "rmd_table_filter", "rmd_table_sort", "rmd_table_is_sorted", "rmd_table_top", "rmd_table_nooverlap", "rmd_table_cluster_index",
            "rmd_table_cluster_info", "rmd_table_cluster_metrics"]
 
 _lib = None
@@ -127,6 +127,7 @@ def load_library():
     L.rmd_table_download.argtypes = [vp, vp, i64, i64]
     L.rmd_table_filter.argtypes = [vp, pf64, pf64, pf64, i32, pi64]
     L.rmd_table_sort.argtypes = [vp, vp, i32]
+    L.rmd_table_is_sorted.argtypes = [vp, vp, i32, pi64]
     L.rmd_table_top.argtypes = [vp, i32, i32, vp, i32, pi64]
     L.rmd_table_nooverlap.argtypes = [vp, pi64]
     L.rmd_table_cluster_index.argtypes = [vp, vp, vp, i32, vp, pi64]

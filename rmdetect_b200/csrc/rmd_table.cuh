@@ -221,6 +221,24 @@ extern "C" int rmd_table_sort(rmd_ctx *ctx, const int32_t *key_rank, int32_t n_k
     return table_sort_cmp(ctx);
 }
 
+extern "C" int rmd_table_is_sorted(rmd_ctx *ctx, const int32_t *key_rank, int32_t n_keys, int64_t *first_bad) {
+    TABLE_ENTER("rmd_table_is_sorted");
+    if (!first_bad) return fail(ctx, RMD_E_INVALID, "rmd_table_is_sorted: NULL argument");
+    int r;
+    if ((r = table_key_ranks(ctx, key_rank, n_keys, "rmd_table_is_sorted"))) return r;
+    *first_bad = -1;
+    if (T.n < 2) return RMD_OK;
+    RESERVE(T.totals, sizeof(uint32_t) * 8 * 256);
+    unsigned long long bad = (unsigned long long)T.n;
+    CK(cudaMemcpyAsync(T.totals.p, &bad, sizeof bad, cudaMemcpyHostToDevice, ctx->stream));
+    table_sorted_kernel<<<TBL_BLOCKS(T.n), 256, 0, ctx->stream>>>((const rmd_hit_row *)T.rows.p, T.n, (const int *)T.ranks.p, (unsigned long long *)T.totals.p);
+    CK(cudaMemcpyAsync(&bad, T.totals.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if ((long long)bad < T.n) *first_bad = (int64_t)bad;
+    return RMD_OK;
+}
+
 extern "C" int rmd_table_top(rmd_ctx *ctx, int32_t group, int32_t top_n, const int32_t *key_rank, int32_t n_keys, int64_t *n_rows) {
     TABLE_ENTER("rmd_table_top");
     if (group < 0 || group > 2 || top_n < 0) return fail(ctx, RMD_E_INVALID, "rmd_table_top: group %d, n %d", group, top_n);

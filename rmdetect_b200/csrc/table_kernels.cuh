@@ -167,6 +167,20 @@ __global__ void table_compact_kernel(const rmd_hit_row *rows, long long n, const
     for (int k = 0; k < 4; k++) dst[k] = src[k];
 }
 
+// is the table in Candidate.__cmp__ order?  first_bad = smallest row whose predecessor compares greater (n: none)
+__global__ void table_sorted_kernel(const rmd_hit_row *rows, long long n, const int *key_rank, unsigned long long *first_bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1 || i >= n) return;
+    const rmd_hit_row &a = rows[i - 1], &b = rows[i];
+    const unsigned long long ka = (unsigned long long)(uint32_t)key_rank[a.key], kb = (unsigned long long)(uint32_t)key_rank[b.key];
+    bool greater = ka > kb;
+    if (ka == kb) {
+        const unsigned long long ea = order_bits(a.evalue), eb = order_bits(b.evalue);
+        greater = ea > eb || (ea == eb && order_bits(-a.score) > order_bits(-b.score));
+    }
+    if (greater) atomicMin(first_bad, (unsigned long long)i);
+}
+
 // ---- the last scan's hits become table rows ------------------------------------------------------------------
 // letters of the winning gap configuration in node order (chain 0, then chain 1), 3 bits each: 0..3 ACGU, 4 '.', 5 other
 __global__ void table_append_scan_kernel(const DevJob J, const rmd_hit *hits, long long n, int key_base, long long start_base,

@@ -180,6 +180,13 @@ class HitTable:
         r = self._ranks()
         self.ctx._check(self.lib.rmd_table_sort(self.ctx.h, _ptr(r), len(r)), "rmd_table_sort")
 
+    def first_unsorted(self):
+        """The first row that compares smaller than its predecessor (`Candidate.__cmp__`), or -1: the table is sorted."""
+        r = self._ranks()
+        bad = C.c_int64(-1)
+        self.ctx._check(self.lib.rmd_table_is_sorted(self.ctx.h, _ptr(r), len(r), C.byref(bad)), "rmd_table_is_sorted")
+        return bad.value
+
     def _top(self, group, n_top):
         r = self._ranks()
         n = C.c_int64(0)

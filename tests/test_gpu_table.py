@@ -160,8 +160,10 @@ def test_synthetic_table_against_the_host_restatement(n, span):
         T.ctx._check(T.lib.rmd_table_append_rows(T.ctx.h, _ptr(rows), len(rows), C.byref(cnt)), "rmd_table_append_rows")
 
     ids = lambda lst: [o.id for o in lst]
-    load(); T.sort()
-    assert T.rows()["id"].tolist() == ids(sorted(objs))
+    load()
+    assert T.first_unsorted() == next(k for k in range(1, n) if objs[k] < objs[k - 1])
+    T.sort()
+    assert T.rows()["id"].tolist() == ids(sorted(objs)) and T.first_unsorted() == -1
     load(); T.top_model(50)
     assert T.rows()["id"].tolist() == ids(host.top_model(objs, 50))
     load(); T.top_seq(17)
@@ -177,6 +179,8 @@ def test_synthetic_table_against_the_host_restatement(n, span):
         assert T.rows()["id"].tolist() == ids(host.nooverlap(objs))
         load(); T.sort(); T.nooverlap()
         assert T.rows()["id"].tolist() == ids(host.nooverlap(sorted(objs)))
+        left = len(T)
+        assert T.nooverlap() == left                                # idempotent: no two survivors are duplicates
     else:                                                           # sparse positions: the same answer group by group
         load(); T.nooverlap()
         left = set(T.rows()["id"].tolist())
