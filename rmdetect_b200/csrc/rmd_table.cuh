@@ -316,7 +316,14 @@ extern "C" int rmd_table_cluster_index(rmd_ctx *ctx, const int64_t *col_off, con
     }
     const rmd_hit_row *rows = (const rmd_hit_row *)T.rows.p;
     const unsigned long long *rc = (const unsigned long long *)T.aux64.p;
-    cluster_cols_kernel<<<TBL_BLOCKS(n), 256, 0, st>>>(rows, n, d_off, d_cols, (unsigned long long *)T.aux64.p);
+    CK(cudaMemsetAsync(T.totals.p, 0, sizeof(uint32_t), st));
+    cluster_cols_kernel<<<TBL_BLOCKS(n), 256, 0, st>>>(rows, n, d_off, d_cols, (unsigned long long *)T.aux64.p, (unsigned int *)T.totals.p);
+    {
+        unsigned int bad = 0;
+        CK(cudaMemcpyAsync(&bad, T.totals.p, sizeof bad, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (bad) return fail(ctx, RMD_E_INVALID, "rmd_table_cluster_index: a hit lies beyond its sequence's column index");
+    }
     table_iota(ctx, n);
     if ((r = table_sort_by(ctx, n, TF_CL_COL, nullptr, nullptr, rc))) return r;
     if ((r = table_sort_by(ctx, n, TF_CL_MODEL_ROW, nullptr, nullptr, rc))) return r;

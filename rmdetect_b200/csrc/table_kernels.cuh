@@ -368,12 +368,17 @@ __global__ void __launch_bounds__(256) nooverlap_replay_kernel(const rmd_hit_row
 // ---- rmcluster: the first cluster list (lib/cluster.py:185-203) ----------------------------------------------------
 // cluster key of a hit = (model, column of the first position of chain 0, of chain 1); columns come from the alignment's
 // column index when the sequences were read from one (lib/candidates.py:489-506), else they are the positions themselves
-__global__ void cluster_cols_kernel(const rmd_hit_row *rows, long long n, const long long *col_off, const int *cols, unsigned long long *rc /* [n][2] */) {
+__global__ void cluster_cols_kernel(const rmd_hit_row *rows, long long n, const long long *col_off, const int *cols, unsigned long long *rc /* [n][2] */,
+                                    unsigned int *bad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const rmd_hit_row r = rows[i];
     long long a = r.start + r.p0, b = r.start + r.p1;
-    if (cols) { const long long o = col_off[r.key]; a = cols[o + a]; b = cols[o + b]; }
+    if (cols) {
+        const long long o = col_off[r.key], len = col_off[r.key + 1] - o;
+        if (a >= len || b >= len) { atomicOr(bad, 1u); a = b = 0; }       // a position beyond the sequence's column index
+        else { a = cols[o + a]; b = cols[o + b]; }
+    }
     rc[2 * i] = (unsigned long long)a; rc[2 * i + 1] = (unsigned long long)b;
 }
 
