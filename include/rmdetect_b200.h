@@ -59,6 +59,7 @@ extern "C" {
 #define RMD_MAX_FIRST_PAIRS 16
 #define RMD_MAX_BRANCH_DEPTH 8
 #define RMD_FAST_WINDOW 160  /* windows up to this length take the shared-memory kernel */
+#define RMD_BIG_WINDOW 256   /* windows of 161..256 letters take the same kernel staged with a larger bit matrix (fewer teams per SM) */
 
 typedef struct rmd_ctx rmd_ctx;
 

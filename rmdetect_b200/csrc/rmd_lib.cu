@@ -87,6 +87,8 @@ struct rmd_ctx {
     DBuf d_xnodes, d_xcpt, d_next;
     int teams = 8, ctas_per_sm = 1;      // shape of the persistent scan kernel (rmd_set_models)
     size_t scan_smem = 0;
+    int teams_big = 0;                   // the same kernel staged for windows of 161..256 letters (FastSmemT<256>): teams per CTA, 0: not available
+    size_t scan_smem_big = 0;
     bool tables_in_smem = true;
     // prefix screens (device_common.cuh: ScreenDesc): per model [screen0[m], screen0[m + 1]), words of one sequence's tables
     int n_screens = 0;
@@ -520,8 +522,8 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     bool any_brute = prel_overflow;               // too many distinct pair geometries for the candidate filter: exact path
     for (const CModel &c : hmodels) if (c.brute) any_brute = true;
     for (int m = n_models; m <= RMD_MAX_MODELS; m++) screen0[m] = (unsigned char)n_screens;
-    int teams_new = 8, ctas_new = 1, sm_count = 0;
-    size_t scan_smem = 0;
+    int teams_new = 8, ctas_new = 1, sm_count = 0, teams_big_new = 0;
+    size_t scan_smem = 0, scan_smem_big = 0;
     bool tables_in_smem = true;
     {   // shape of the persistent scan kernel: tables + one FastSmem per team within the SM's shared memory
         int smem_max = 0;
@@ -541,6 +543,16 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, false, RMD_BIG_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, true, RMD_BIG_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        // windows of 161..256 letters: the same kernel with a larger bit matrix per team, as many teams as still fit
+        teams_big_new = 0;
+        if (tables_in_smem) {
+            int tb = SCAN_MAX_THREADS / SCAN_THREADS;
+            while (tb > 0 && fixed + tb * sizeof(FastSmemT<RMD_BIG_WINDOW>) > (size_t)smem_max / ctas_new) tb--;
+            teams_big_new = tb;
+            scan_smem_big = fixed + tb * sizeof(FastSmemT<RMD_BIG_WINDOW>);
+        }
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -568,6 +580,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
     ctx->n_screens = n_screens; ctx->screen_words = screen_words; ctx->screens_dirty = true;
     ctx->teams = teams_new; ctx->ctas_per_sm = ctas_new; ctx->sm_count = sm_count;
     ctx->scan_smem = scan_smem; ctx->tables_in_smem = tables_in_smem;
+    ctx->teams_big = teams_big_new; ctx->scan_smem_big = scan_smem_big;
     return RMD_OK;
 }
 
@@ -910,7 +923,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     CK(cudaEventRecord(ctx->ev[8], st));
     if (ctx->screens_dirty) { int rs = build_screens(ctx); if (rs) return rs; }
     RESERVE(ctx->d_counters, 128);
-    RESERVE(ctx->d_next, sizeof(unsigned int) * (STREAM_CHUNKS + 2));
+    RESERVE(ctx->d_next, sizeof(unsigned int) * (2 * STREAM_CHUNKS + 4));    // per chunk launch, OTHER launch, progress mark; the same for the big-window launches
     RESERVE(ctx->d_gate_pass, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_hits, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1));
     RESERVE(ctx->d_group_off, sizeof(uint32_t) * (size_t)(ngroups + 1));
@@ -921,7 +934,11 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     // windows with a letter other than ACGU (N runs, IUPAC codes): a second launch of the shared-memory kernel takes them
     // from a work list; the rare kernel shapes (exact gate, local-memory stack, tables in global memory) leave them to the generic kernel
     const bool other_fast = use_fast && ctx->any_other && ctx->tables_in_smem && !ctx->local_stack && !(ctx->any_brute || !(J.min_bpp > 0.0));
-    const bool need_generic = !use_fast || ctx->max_wlen > RMD_FAST_WINDOW || ctx->min_wlen < min_fast_wlen || (ctx->any_other && !other_fast);
+    // windows of 161..256 letters (a larger --win-len, whole-sequence mode on short sequences): a second launch of the kernel staged for them
+    const bool big_fast = use_fast && ctx->max_wlen > RMD_FAST_WINDOW && ctx->teams_big > 0 && ctx->tables_in_smem && !ctx->local_stack &&
+                          !(ctx->any_brute || !(J.min_bpp > 0.0));
+    const int max_fast_wlen = big_fast ? RMD_BIG_WINDOW : RMD_FAST_WINDOW;
+    const bool need_generic = !use_fast || ctx->max_wlen > max_fast_wlen || ctx->min_wlen < min_fast_wlen || (ctx->any_other && !other_fast);
     if (other_fast) RESERVE(ctx->d_other, sizeof(uint32_t) * (size_t)(nwin + 2));
     unsigned long long counters[16];
     int launches = 0;
@@ -929,7 +946,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         RESERVE(ctx->d_raw, sizeof(RawHit) * (size_t)ctx->raw_cap);
         launches = 0;
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, 128, st));
-        CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(unsigned int) * (STREAM_CHUNKS + 2), st));
+        CK(cudaMemsetAsync(ctx->d_next.p, 0, sizeof(unsigned int) * (2 * STREAM_CHUNKS + 4), st));
         CK(cudaMemsetAsync(ctx->d_gate_pass.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         CK(cudaMemsetAsync(ctx->d_group_hits.p, 0, sizeof(uint32_t) * (size_t)std::max<long long>(ngroups, 1), st));
         ScanOut O;
@@ -940,7 +957,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         CK(cudaEventRecord(ctx->ev[0], st));
         if (other_fast && nwin > 0) {
             CK(cudaMemsetAsync((uint32_t *)ctx->d_other.p + nwin, 0, sizeof(uint32_t), st));
-            other_windows_kernel<<<(unsigned)std::min<long long>((nwin + 7) / 8, (long long)ctx->sm_count * 8), 256, 0, st>>>(J, w_begin, w_end, min_fast_wlen, (uint32_t *)ctx->d_other.p,
+            other_windows_kernel<<<(unsigned)std::min<long long>((nwin + 7) / 8, (long long)ctx->sm_count * 8), 256, 0, st>>>(J, w_begin, w_end, min_fast_wlen, max_fast_wlen, (uint32_t *)ctx->d_other.p,
                                                                                                                             (uint32_t *)ctx->d_other.p + nwin);
             launches++;
         }
@@ -959,7 +976,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             if (stream_in->bpp_q) {
                 n_chunks = 0;
                 // without expansion launches, and with the chunks' tails overlapping on two streams, a launch costs less
-                const bool will_fuse = use_fast && !need_generic && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
+                const bool will_fuse = use_fast && !need_generic && !big_fast && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
                                        !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");
                 const int gpct = will_fuse ? STREAM_GROWTH_FUSED : 60;
                 long long end = std::max<long long>(nwin / 128, 2048);
@@ -975,7 +992,7 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         // chunks then alternate between two compute streams: a launch does not wait for the previous one to end, its
         // CTAs start on the SMs whose persistent CTA has run out of windows.
         if (streaming) {
-            const bool fused = stream_in->bpp_q && use_fast && !need_generic && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
+            const bool fused = stream_in->bpp_q && use_fast && !need_generic && !big_fast && !ctx->any_other && ctx->tables_in_smem && !ctx->local_stack &&
                                !(ctx->any_brute || !(J.min_bpp > 0.0)) && !tune_env("RMD_NO_FUSED_EXPAND");     // = will_fuse above
             ctx->job.bpp_ij = fused ? (const uint16_t *)ctx->d_bpp_ij.p : nullptr;
             ctx->job.bpp_q = fused ? (const uint32_t *)ctx->d_bpp_q.p : nullptr;
@@ -1051,8 +1068,14 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
                 }
                 launches++;
             }
+            if (big_fast) {                                         // windows of 161..256 letters of this chunk
+                const unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * ctx->ctas_per_sm, (c1 - c0 + ctx->teams_big - 1) / ctx->teams_big);
+                scan_fast_kernel<false, true, false, false, false, RMD_BIG_WINDOW><<<grid, (unsigned)ctx->teams_big * SCAN_THREADS, ctx->scan_smem_big, st>>>(
+                    J, c0, c1, w_begin, O, RMD_FAST_WINDOW + 1, (unsigned int *)ctx->d_next.p + STREAM_CHUNKS + 2 + ch);
+                launches++;
+            }
             if (need_generic) {
-                scan_generic_kernel<<<(unsigned)((c1 - c0) * J.n_models), GEN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, other_fast ? 1 : 0);
+                scan_generic_kernel<<<(unsigned)((c1 - c0) * J.n_models), GEN_THREADS, 0, st>>>(J, c0, c1, w_begin, O, min_fast_wlen, max_fast_wlen, other_fast ? 1 : 0);
                 launches++;
             }
         }
@@ -1064,6 +1087,11 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
             scan_fast_kernel<false, true, false, false, true><<<(unsigned)ctx->sm_count * ctx->ctas_per_sm, (unsigned)ctx->teams * SCAN_THREADS, ctx->scan_smem, st>>>(
                 J, w_begin, w_end, w_begin, O, min_fast_wlen, (unsigned int *)ctx->d_next.p + STREAM_CHUNKS);
             launches++;
+            if (big_fast) {
+                scan_fast_kernel<false, true, false, false, true, RMD_BIG_WINDOW><<<(unsigned)ctx->sm_count * ctx->ctas_per_sm, (unsigned)ctx->teams_big * SCAN_THREADS, ctx->scan_smem_big, st>>>(
+                    J, w_begin, w_end, w_begin, O, RMD_FAST_WINDOW + 1, (unsigned int *)ctx->d_next.p + 2 * STREAM_CHUNKS + 3);
+                launches++;
+            }
         }
         CK(cudaEventRecord(ctx->ev[1], st));
         CK(cudaMemcpyAsync(counters, ctx->d_counters.p, 128, cudaMemcpyDeviceToHost, st));

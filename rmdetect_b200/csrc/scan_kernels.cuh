@@ -77,10 +77,12 @@ struct WarpQueues {                      // one warp's work lists (one base addr
     uint32_t q2[Q2_CAP];                 // survivors some screen calls alive: the scoring engine's queue
 };
 
-struct __align__(16) FastSmem {
-    uint32_t Ub[UWORDS];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
-    uint16_t Ur[UWORDS];                 // entries before this word in list order
-    uint32_t CB[CB_SLOTS][UWORDS];       // placements already queued, per bitmap-using model of the current group
+template <int WCAP>
+struct __align__(16) FastSmemT {
+    static constexpr int WORDS = WCAP / 32, UW = WCAP * (WCAP / 32);
+    uint32_t Ub[UW];                 // bit j of word (i, j >> 5): pair (i, j), i < j, is stored
+    uint16_t Ur[UW];                 // entries before this word in list order
+    uint32_t CB[CB_SLOTS][UW];       // placements already queued, per bitmap-using model of the current group
     WarpQueues wq[SCAN_WARPS];
     double2 stk[STK_SLOTS][SCAN_THREADS]; // running sums saved at gap branches, [slot][thread]: conflict-free 16-byte accesses
     double best_pr[SCAN_THREADS];         // per lane: random-model sum of the walk's best leaf so far (read when the walk ends)
@@ -102,31 +104,34 @@ struct __align__(16) FastSmem {
     uint32_t chunk_ctr[2];               // next entry chunk of the window, per model group (alternating)
     uint32_t next[2];                    // window taken from the global counter (alternating slots)
     uint16_t prel[32];                   // distinct parent-relative offsets of the tries: (dr & 0xff) | dc << 8
-    uint8_t letters[FAST_W + 16];
-    uint32_t l2[FAST_W / 16 + 2];        // the letters again, two bits each (a letter other than ACGU: its code's low bits)
-    uint32_t lo[FAST_W / 32 + 3];        // one bit per letter: it is not one of ACGU (OTHER variant)
+    uint8_t letters[WCAP + 16];
+    uint32_t l2[WCAP / 16 + 2];        // the letters again, two bits each (a letter other than ACGU: its code's low bits)
+    uint32_t lo[WCAP / 32 + 3];        // one bit per letter: it is not one of ACGU (OTHER variant)
     uint32_t plain;                      // every letter of the window is one of ACGU
 };
+typedef FastSmemT<FAST_W> FastSmem;       // the common case: windows up to 160 letters (FastSmemT<256>: up to 256, five teams per CTA)
 
 // is pair (b1, b2) stored?  (lib/bpprobs.py:17-18; the diagonal is never stored)
-__device__ __forceinline__ bool bpp_present(const FastSmem &sm, int wlen, int b1, int b2) {
+template <class SM>
+__device__ __forceinline__ bool bpp_present(const SM &sm, int wlen, int b1, int b2) {
     const int lo = min(b1, b2), hi = max(b1, b2);
-    return lo >= 0 && hi < wlen && ((sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u);
+    return lo >= 0 && hi < wlen && ((sm.Ub[lo * SM::WORDS + (hi >> 5)] >> (hi & 31)) & 1u);
 }
 
 // the same for a pair inside the window given as fields b1 | b2 << 12 (the diagonal is never stored)
-__device__ __forceinline__ bool bpp_present_f(const FastSmem &sm, uint32_t f) {
+template <class SM>
+__device__ __forceinline__ bool bpp_present_f(const SM &sm, uint32_t f) {
     const uint32_t b1 = f & 0xfffu, b2 = f >> 12;
     const uint32_t lo = min(b1, b2), hi = max(b1, b2);
-    return (sm.Ub[lo * FAST_WORDS + (hi >> 5)] >> (hi & 31)) & 1u;
+    return (sm.Ub[lo * SM::WORDS + (hi >> 5)] >> (hi & 31)) & 1u;
 }
 
 // bpp lookup by popcount rank: 0.0 unless the pair is stored
-template <bool COHERENT = false>
-__device__ __forceinline__ double bpp_fast(const FastSmem &sm, const double *vals, int wlen, int b1, int b2) {
+template <bool COHERENT = false, class SM>
+__device__ __forceinline__ double bpp_fast(const SM &sm, const double *vals, int wlen, int b1, int b2) {
     const int lo = min(b1, b2), hi = max(b1, b2);
     if (hi >= wlen) return 0.0;
-    const int k = lo * FAST_WORDS + (hi >> 5);
+    const int k = lo * SM::WORDS + (hi >> 5);
     const uint32_t w = sm.Ub[k], bit = 1u << (hi & 31);
     if (!(w & bit)) return 0.0;
     const double *at = vals + sm.Ur[k] + __popc(w & (bit - 1));
@@ -176,10 +181,11 @@ __device__ __forceinline__ void team_sync(const int team) {
 // (lib/node.py:215-223: unknown_prob): the engine carries one more bit per letter, reads the letter's code from the
 // window when the bit is set, and finishes its walks before the team leaves the window; placements that touch such a
 // letter bypass the prefix screens, whose tables are indexed by ACGU.
-template <bool BRUTE, bool TABLES, bool LSTK, bool FUSED = false, bool OTHER = false>
+template <bool BRUTE, bool TABLES, bool LSTK, bool FUSED = false, bool OTHER = false, int WCAP = FAST_W>
 __global__ void __launch_bounds__(SCAN_MAX_THREADS, 1)
 scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
+    typedef FastSmemT<WCAP> Smem;                            // WCAP: the longest window this instantiation stages (160 or 256)
     extern __shared__ uint4 dyn_smem[];
     int tid = threadIdx.x & (SCAN_THREADS - 1), lane = tid & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(tid));          // opaque like the team offset below: no re-derivation from %tid
@@ -188,7 +194,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     uint32_t lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     const int n_models = J.n_models;
-    // ---- shared memory: the teams' state first (a team's base is team * sizeof(FastSmem)), then the CTA-wide tables.
+    // ---- shared memory: the teams' state first (a team's base is team * sizeof(Smem)), then the CTA-wide tables.
     // The team's byte offset goes through an opaque move: left to itself the compiler re-derives it from
     // %tid and the kernel parameters in front of most shared-memory accesses (13 % of all instructions).
     // The gate tries (static, read by every team) sit once per CTA at the very start: a compile-time address.
@@ -200,10 +206,10 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     //   z = node << 24 (its place in a queued pair), w = need: a generating value of at least need x min_bpp passes the
     //   gate for certain (255: never)
     const uint4 *const cnw = reinterpret_cast<const uint4 *>(dyn_smem) + TRIE_CAP;
-    uint32_t sm_off = (uint32_t)SCAN_CTA_FIXED + (uint32_t)team * (uint32_t)sizeof(FastSmem);
+    uint32_t sm_off = (uint32_t)SCAN_CTA_FIXED + (uint32_t)team * (uint32_t)sizeof(Smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(sm_off));
-    FastSmem &sm = *reinterpret_cast<FastSmem *>(reinterpret_cast<char *>(dyn_smem) + sm_off);
-    const int t_words = SCAN_CTA_FIXED / 16 + (int)(blockDim.x / SCAN_THREADS) * (int)(sizeof(FastSmem) / 16);   // in uint4
+    Smem &sm = *reinterpret_cast<Smem *>(reinterpret_cast<char *>(dyn_smem) + sm_off);
+    const int t_words = SCAN_CTA_FIXED / 16 + (int)(blockDim.x / SCAN_THREADS) * (int)(sizeof(Smem) / 16);   // in uint4
     const int x_words = TABLES ? 2 * J.n_xnodes : 0, c_words = TABLES ? (J.n_xcpt + 1) / 2 : 0;
     const int s_words = 2 * J.n_screens;
     uint4 *sx = dyn_smem + t_words;
@@ -254,7 +260,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     const bool no_score = J.no_score != 0;
 #endif
     const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
-    uint32_t wq_off = sm_off + (uint32_t)offsetof(FastSmem, wq) + (uint32_t)wid * (uint32_t)sizeof(WarpQueues);
+    uint32_t wq_off = sm_off + (uint32_t)offsetof(Smem, wq) + (uint32_t)wid * (uint32_t)sizeof(WarpQueues);
     asm volatile("mov.u32 %0, %0;" : "+r"(wq_off));
     WarpQueues &wq = *reinterpret_cast<WarpQueues *>(reinterpret_cast<char *>(dyn_smem) + wq_off);
     uint32_t *const q1 = wq.q1, *const q2 = wq.q2, *const qs = wq.qs;
@@ -417,7 +423,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 sm.tbl = so >= 0 ? J.screen_bits + so : nullptr;
             }
         }
-        if (wlen < min_wlen || wlen > FAST_W) continue;       // long or degenerate windows: scan_generic_kernel
+        if (wlen < min_wlen || wlen > WCAP) continue;       // long or degenerate windows: scan_generic_kernel
 #ifdef RMD_STATS
         const long long ck0 = clock64();
 #endif
@@ -431,9 +437,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         if (!FUSED) for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
 
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
-        for (int k = tid; k < UWORDS; k += SCAN_THREADS) sm.Ub[k] = 0;
-        for (int k = tid; k < CB_SLOTS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
-        for (int k = tid; k < FAST_W + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
+        for (int k = tid; k < Smem::UW; k += SCAN_THREADS) sm.Ub[k] = 0;
+        for (int k = tid; k < CB_SLOTS * Smem::UW; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+        for (int k = tid; k < WCAP + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
         if (tid == 0) sm.plain = 1;
         if (tid < 2) sm.chunk_ctr[tid] = 0;
         if (new_seq && tid < RMD_N_CODES) sm.gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
@@ -449,22 +455,22 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             const uint32_t bd = sm.bounds[(cinfo[k] >> 14) & 15u];    // n0 | hi << 8 | symmetric << 16, n0 >= 1
             sm.nodey[k] = ((bd & 0xffu) - 1u + 0x800u) | ((((bd >> 8) & 0xffu) + 0x800u) << 12);
         }
-        if (tid < FAST_W / 16 + 2) {                          // two-bit letters for the scoring engine
+        if (tid < WCAP / 16 + 2) {                          // two-bit letters for the scoring engine
             uint32_t word = 0, other = 0;
             for (int k = 0; k < 16; k++) {
                 const int pos = tid * 16 + k;
-                const uint32_t c = pos < FAST_W + 16 ? sm.letters[pos] : 0;
+                const uint32_t c = pos < WCAP + 16 ? sm.letters[pos] : 0;
                 word |= (c & 3u) << (2 * k);
                 other |= c >> 2;
             }
             sm.l2[tid] = word;
             if (other) atomicAnd(&sm.plain, 0u);
         }
-        if (OTHER && tid >= 32 && tid < 32 + FAST_W / 32 + 3) {   // which letters are not ACGU, one bit each
+        if (OTHER && tid >= 32 && tid < 32 + WCAP / 32 + 3) {   // which letters are not ACGU, one bit each
             uint32_t word = 0;
             for (int k = 0; k < 32; k++) {
                 const int pos = (tid - 32) * 32 + k;
-                if (pos < FAST_W + 16 && sm.letters[pos] > 3) word |= 1u << k;
+                if (pos < WCAP + 16 && sm.letters[pos] > 3) word |= 1u << k;
             }
             sm.lo[tid - 32] = word;
         }
@@ -496,9 +502,9 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 if (e >= nnz) continue;
                 const bool inside = i < j && j < wlen, rising = (pi[k] << 16 | pj[k]) < (i << 16 | j) || e == 0;
                 if (!inside || !rising) { atomicOr(&O.raw_count[7], ERR_BAD_LIST); continue; }
-                const int word = i * FAST_WORDS + (j >> 5);
+                const int word = i * Smem::WORDS + (j >> 5);
                 atomicOr(&sm.Ub[word], 1u << (j & 31));
-                if (e == 0 || pi[k] * FAST_WORDS + (pj[k] >> 5) != word) sm.Ur[word] = (uint16_t)e;
+                if (e == 0 || pi[k] * Smem::WORDS + (pj[k] >> 5) != word) sm.Ur[word] = (uint16_t)e;
             }
         }
         team_sync(team);
@@ -658,7 +664,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             for (int grp = 0; grp < n_groups; grp++) {
                 if (grp > 0) {                                   // bitmaps of the next group of models
                     team_sync(team);
-                    for (int k = tid; k < CB_SLOTS * UWORDS; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+                    for (int k = tid; k < CB_SLOTS * Smem::UW; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
                     if (tid == 0) sm.chunk_ctr[(grp + 1) & 1] = 0;
                     team_sync(team);
                 }
@@ -774,7 +780,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                             const uint32_t slot1 = (info >> 18) & 3u;
                             if (slot1) {
                                 const uint32_t bit = 1u << (p1 & 31);
-                                ok = !(atomicOr(&sm.CB[slot1 - 1][p0 * FAST_WORDS + (p1 >> 5)], bit) & bit);
+                                ok = !(atomicOr(&sm.CB[slot1 - 1][p0 * Smem::WORDS + (p1 >> 5)], bit) & bit);
                             } else if (info & (1u << 20)) {
                                 // a trie without a bitmap (two nodes): its first node produces the placement whenever that node's
                                 // own pair is big, the other node only otherwise (one entry and one node give one placement)
@@ -829,17 +835,17 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     }
 }
 
-// Windows of [w_begin, w_end) that the shared-memory kernel takes (length within [min_wlen, FAST_W]) and that hold a
+// Windows of [w_begin, w_end) that the shared-memory kernel takes (length within [min_wlen, max_wlen]) and that hold a
 // letter other than ACGU: the OTHER launch's work list (window numbers relative to w_begin, any order).  One warp per window.
 __global__ void __launch_bounds__(256) other_windows_kernel(const DevJob J, const long long w_begin, const long long w_end, const int min_wlen,
-                                                            uint32_t *list, uint32_t *count) {
+                                                            const int max_wlen, uint32_t *list, uint32_t *count) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long w = w_begin + warp; w < w_end; w += n_warps) {
         int seq, wlen;
         long long start;
         window_geom(J, w, seq, start, wlen);
-        if (wlen < min_wlen || wlen > FAST_W) continue;
+        if (wlen < min_wlen || wlen > max_wlen) continue;
         const uint8_t *c = J.codes8 + J.seq_off[seq] + start;
         bool other = false;
         for (int k = lane; k < wlen; k += 32) other |= c[k] > 3;
@@ -870,7 +876,7 @@ __device__ __forceinline__ double bpp_search(const DevJob &J, long long b0, int 
 
 __global__ void __launch_bounds__(GEN_THREADS)
 scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_end, const long long w_base,
-                    const ScanOut O, const int min_fast_wlen, const int fast_takes_other) {
+                    const ScanOut O, const int min_fast_wlen, const int max_fast_wlen, const int fast_takes_other) {
     __shared__ uint32_t scan_tmp[GEN_THREADS / 32 + 1];
     __shared__ double gc[RMD_N_CODES];
     __shared__ unsigned long long s_base;
@@ -884,7 +890,7 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     long long start;
     window_geom(J, w, seq, start, wlen);
     if (wlen <= 0) return;
-    if (wlen >= min_fast_wlen && wlen <= FAST_W) {                         // scan_fast_kernel's, unless a letter is not ACGU and no OTHER launch follows
+    if (wlen >= min_fast_wlen && wlen <= max_fast_wlen) {                         // scan_fast_kernel's, unless a letter is not ACGU and no OTHER launch follows
         if (fast_takes_other) return;
         int other = 0;
         if (J.codes8) for (int k = tid; k < wlen; k += GEN_THREADS) other |= J.codes8[J.seq_off[seq] + start + k] > 3;

@@ -630,3 +630,37 @@ def test_windows_with_other_letters_take_the_shared_memory_kernel(screens):
             assert (g["seq"], g["model"], g["start"], g["p0"], g["p1"], g["leaf"]) == (si, w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"])
             assert (g["prob_model"], g["prob_rand"], g["score"], g["evalue"]) == (w["prob_model"], w["prob_rand"], w["score"], w["evalue"])
     assert at == len(hits) > 100 and r["tries"] == tests
+
+
+def test_windows_of_161_to_256_letters_take_the_shared_memory_kernel():
+    """A larger --win-len and whole-sequence mode: windows up to 160 letters go to the common launch, 161..256 to the
+    launch staged with a larger bit matrix, longer ones to the generic kernel, with and without letters other than
+    ACGU; every hit equals the oracle's, bit for bit."""
+    from oracle import pyoracle
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import SynthFold
+    rng = random.Random(19)
+    mk = lambda n, letters="ACGU": "".join(rng.choice(letters) for _ in range(n))
+    names = MODEL_ORDER + ["ARICH_1.0"]
+    fold = SynthFold(41)
+    eng = ScanEngine([load_model(n) for n in names], [load_evalues(n) for n in names], LN_UNKNOWN)
+    oms = [pyoracle.OracleModel(load_model(n)) for n in names]
+    oes = [pyoracle.OracleEValues(evalues_path(n)) for n in names]
+    for W, step, seqs in ((230, 90, [("a", mk(2000), None), ("b", mk(140), None), ("c", mk(700, "ACGUN"), None), ("d", mk(256), None)]),
+                          (0, 0, [("w%d" % n, mk(n, "ACGU" if n % 2 else "ACGUR"), None) for n in (120, 160, 161, 200, 255, 256, 257, 300)])):
+        job = eng.build_job(seqs, W, step, fold, "", 0.001, LN_CUTOFF)
+        r = eng.scan_job(job)
+        hits = r["hits"]
+        at, tests = 0, [0, 0]
+        for si, (_, seq, _) in enumerate(seqs):
+            starts = pyoracle.windows(len(seq), W, step)
+            wl = W if W else len(seq)
+            want, tries, _ = pyoracle.scan_sequence(oms, oes, si, seq, W, step, [fold.coo(seq[s:s + wl]) for s in starts],
+                                                    0.001, LN_UNKNOWN, LN_CUTOFF)
+            tests[0] += tries[0]; tests[1] += tries[1]
+            for w in want:
+                g = hits[at]; at += 1
+                assert (g["seq"], g["model"], g["start"], g["p0"], g["p1"], g["leaf"]) == (si, w["model"], w["coords"][0], w["p"][0], w["p"][1], w["cfg"])
+                assert (g["prob_model"], g["prob_rand"], g["score"], g["evalue"]) == (w["prob_model"], w["prob_rand"], w["score"], w["evalue"])
+        assert at == len(hits) > 20 and r["tries"] == tests
+    eng.close()
