@@ -653,9 +653,9 @@ def test_windows_of_161_to_256_letters_take_the_shared_memory_kernel():
         hits = r["hits"]
         at, tests = 0, [0, 0]
         for si, (_, seq, _) in enumerate(seqs):
-            starts = pyoracle.windows(len(seq), W, step)
-            wl = W if W else len(seq)
-            want, tries, _ = pyoracle.scan_sequence(oms, oes, si, seq, W, step, [fold.coo(seq[s:s + wl]) for s in starts],
+            Wo, so = (W, step) if W else (len(seq), len(seq))      # whole-sequence mode = one window that is the sequence
+            starts = pyoracle.windows(len(seq), Wo, so)
+            want, tries, _ = pyoracle.scan_sequence(oms, oes, si, seq, Wo, so, [fold.coo(seq[s:s + Wo]) for s in starts],
                                                     0.001, LN_UNKNOWN, LN_CUTOFF)
             tests[0] += tries[0]; tests[1] += tries[1]
             for w in want:
