@@ -542,6 +542,10 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         if (scan_smem > (size_t)smem_max) return fail(ctx, RMD_E_LIMIT, "scan kernel needs %zu bytes of shared memory, the device offers %d", scan_smem, smem_max);
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        if (tune_env("RMD_CARVEOUT")) {                // L1 / shared memory split of the main kernel, per cent of shared memory
+            CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(tune_env("RMD_CARVEOUT"))));
+            CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(tune_env("RMD_CARVEOUT"))));
+        }
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, false, RMD_BIG_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         CK(cudaFuncSetAttribute(scan_fast_kernel<false, true, false, false, true, RMD_BIG_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));

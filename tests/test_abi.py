@@ -85,8 +85,8 @@ def test_host_only_entry_points_work_without_a_device():
 
 
 def test_release_library_reads_no_tuning_switch():
-    """RMD_DEBUG, RMD_TEAMS, RMD_CTAS_PER_SM, RMD_LOCAL_STACK, RMD_NO_SCREEN and RMD_NO_FUSED_EXPAND exist only in
+    """RMD_DEBUG, RMD_TEAMS, RMD_CTAS_PER_SM, RMD_CARVEOUT, RMD_LOCAL_STACK, RMD_NO_SCREEN and RMD_NO_FUSED_EXPAND exist only in
     -DRMD_TUNING builds: the shipped library must not even contain their names (nor import getenv for them)."""
     blob = open(_native.LIB_PATH, "rb").read()
-    for name in (b"RMD_DEBUG", b"RMD_TEAMS", b"RMD_CTAS_PER_SM", b"RMD_LOCAL_STACK", b"RMD_NO_SCREEN", b"RMD_NO_FUSED_EXPAND"):
+    for name in (b"RMD_DEBUG", b"RMD_TEAMS", b"RMD_CTAS_PER_SM", b"RMD_CARVEOUT", b"RMD_LOCAL_STACK", b"RMD_NO_SCREEN", b"RMD_NO_FUSED_EXPAND"):
         assert name not in blob, name
