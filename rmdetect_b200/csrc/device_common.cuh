@@ -129,6 +129,10 @@ struct DevJob {
     const uint16_t *bpp_ij;      // compact transport kept on the device (rmd_scan): i | j << 8 per entry, values as bpp_q;
     const uint32_t *bpp_q;       // scan_fast_kernel<..., FUSED> then rebuilds bpp_p window by window (nullptr: bpp_i/j/p are complete)
     double min_bpp, cutoff;
+    // derived from min_bpp on the host (job_thresholds): as kernel parameters they cost scan_fast_kernel no registers
+    double thr_hi, thr_lo;       // min_bpp -+ 1e-12 relative: a fast gate mean outside is decided, inside it is re-summed exactly
+    double big_min;              // a mean of values all below this stays below min_bpp
+    double inv_sure_unit;        // 1 / (min_bpp (1 + 1e-12)): a value in units of the threshold
     const XNode *xnodes;         // all models' search trees (scoring engine format)
     const double *xcpt;          // all models' CPTs, concatenated
     int n_xnodes, n_xcpt;
@@ -140,6 +144,13 @@ struct DevJob {
     int n_screens;               // screens of all models (c_screens); model m owns [screen0[m], screen0[m + 1])
     unsigned char screen0[RMD_MAX_MODELS + 1];
 };
+
+static inline void job_thresholds(DevJob &J) {
+    J.thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12;
+    J.thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
+    J.big_min = J.min_bpp - J.min_bpp * 1e-12;
+    J.inv_sure_unit = 1.0 / (J.min_bpp * (1.0 + 1e-12));
+}
 
 // Unordered hit record written by the scan kernels; `rank` is its position inside its
 // (window, model) group in odometer order, so the ordering pass is a plain scatter.

@@ -803,6 +803,7 @@ static int upload_job(rmd_ctx *ctx, const rmd_scan_input *in, bool with_entries)
     J.bpp_i = (const uint16_t *)ctx->d_bpp_i.p; J.bpp_j = (const uint16_t *)ctx->d_bpp_j.p; J.bpp_p = (const double *)ctx->d_bpp_p.p;
     J.bpp_ij = nullptr; J.bpp_q = nullptr;
     J.min_bpp = in->min_bpp_mean; J.cutoff = in->cutoff; J.no_score = !(0.0 >= 0.0 + in->cutoff);
+    job_thresholds(J);
     ctx->have_job = true;
     return RMD_OK;
 }
@@ -1445,6 +1446,7 @@ extern "C" int rmd_synth_job(rmd_ctx *ctx, int64_t n, int64_t first, uint64_t se
     RESERVE(ctx->d_bpp_off, sizeof(long long) * (size_t)(J.n_win + 1));
     J.codes2 = (const uint32_t *)ctx->d_codes2.p; J.codes8 = nullptr; ctx->any_other = false;
     J.min_bpp = min_bpp_mean; J.cutoff = cutoff; J.no_score = !(0.0 >= 0.0 + cutoff);
+    job_thresholds(J);
     CK(cudaEventRecord(ctx->ev[0], st));
     const long long words = (n + 15) / 16;
     if (ctx->strand_total > 0 && (first < 0 || first + n > ctx->strand_total))

@@ -40,6 +40,7 @@
 #include <math_constants.h>
 #include "device_common.cuh"
 
+#define UNROLL_SMALL _Pragma("unroll 1")   // code that runs once per window stays small: 32 warps in different phases share the instruction caches
 #define FAST_W RMD_FAST_WINDOW          // 160
 #define FAST_WORDS (FAST_W / 32)        // 5
 #define UWORDS (FAST_W * FAST_WORDS)    // 800
@@ -85,12 +86,14 @@ struct __align__(16) FastSmemT {
     uint32_t CB[CB_SLOTS][UW];       // placements already queued, per bitmap-using model of the current group
     WarpQueues wq[SCAN_WARPS];
     double2 stk[STK_SLOTS][SCAN_THREADS]; // running sums saved at gap branches, [slot][thread]: conflict-free 16-byte accesses
-    double best_pr[SCAN_THREADS];         // per lane: random-model sum of the walk's best leaf so far (read when the walk ends)
-    uint32_t walk_win[SCAN_THREADS];      // per lane: window of the walk in flight
-    int walk_leaf[SCAN_THREADS];          // per lane: best leaf | model << 16 of the walk in flight, -1: none yet
+    // per lane, right behind the save slots and with their stride, so that one address register serves both: random-model sum
+    // of the walk's best leaf so far (read when the walk ends), window of the walk in flight, its best leaf | model << 16
+    // (-1: none yet)
+    struct LaneRec { double best_pr; uint32_t walk_win; int walk_leaf; } rec[SCAN_THREADS];
     const uint32_t *tbl;                  // prefix-screen tables of the current sequence (nullptr: every survivor is walked)
     int cur_seq;                          // sequence whose GC table is in gc
     uint32_t win_local;                   // window being generated (records are relative to w_base)
+    int nnz_s;                            // entries of its list (read where a register would be live across the whole window)
     double2 zero2;                       // (0, 0)
     // per trie node in candidate order: the odometer's ranges in this window (lib/scanner.py:161-193) as
     // (n0 - 1 + 0x800) | (hi + 0x800) << 12, next to the static words of the node in cnw (see the node loop)
@@ -164,6 +167,14 @@ __device__ __forceinline__ bool gate_pass(const CModel &M, Lookup lookup, bool a
 }
 // With no pair summed the reference's mean is 0.0 and is still compared with min_bpp_mean, so a
 // non-positive threshold lets every placement through; every placement is then a candidate.
+
+// tests_all of one window over all models; out of line: one thread per window calls it, and the scan kernel's loop body has
+// to stay small (instruction caches)
+__device__ __noinline__ unsigned long long odometer_count_all(const int n_models, const int wlen) {
+    unsigned long long tests_all = 0;
+    for (int m = 0; m < n_models; m++) tests_all += odometer_count(c_models[m], wlen);
+    return tests_all;
+}
 
 // barrier of one team (4 warps); barrier 0 stays with __syncthreads()
 __device__ __forceinline__ void team_sync(const int team) {
@@ -259,7 +270,6 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
 #else
     const bool no_score = J.no_score != 0;
 #endif
-    const double thr_hi = J.min_bpp + fabs(J.min_bpp) * 1e-12, thr_lo = J.min_bpp - fabs(J.min_bpp) * 1e-12;
     uint32_t wq_off = sm_off + (uint32_t)offsetof(Smem, wq) + (uint32_t)wid * (uint32_t)sizeof(WarpQueues);
     asm volatile("mov.u32 %0, %0;" : "+r"(wq_off));
     WarpQueues &wq = *reinterpret_cast<WarpQueues *>(reinterpret_cast<char *>(dyn_smem) + wq_off);
@@ -275,15 +285,18 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
     uint32_t e_c = 0, e_t = XNODE_END;                  // placement p0 | p1 << 16; node (XNODE_END: lane idle)
     uint32_t e_o = 0;                                   // OTHER: bit k: letter k from p0 on is not ACGU, bit 16 + k: from p1 on
     unsigned long long e_m = 0;                         // 16 letters from p0 on | 16 letters from p1 on << 32, two bits each
-    int *const s_leaf = &sm.walk_leaf[tid];
     double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0;      // the best leaf's other sum and the walk's window wait in shared memory
-    double *const s_bpr = &sm.best_pr[tid];
-    uint32_t *const s_win = &sm.walk_win[tid];
     // sums saved at gap branches: slot k - 1 holds the sums of the branch node at (renumbered) depth k; a node that
     // restores at depth 0 is a child of the implicit root and restarts from zero
     double2 e_stk[LSTK ? RMD_MAX_BRANCH_DEPTH + 2 : 1];
     e_stk[0] = make_double2(0.0, 0.0);
     double2 *const s_stk = &sm.stk[0][tid];
+    typename Smem::LaneRec *const s_rec = reinterpret_cast<typename Smem::LaneRec *>(s_stk + STK_SLOTS * SCAN_THREADS);   // = &sm.rec[tid]
+    static_assert(sizeof(typename Smem::LaneRec) == sizeof(double2) && offsetof(Smem, rec) == offsetof(Smem, stk) + sizeof(double2) * STK_SLOTS * SCAN_THREADS,
+                  "the per-lane records follow the save slots");
+    int *const s_leaf = &s_rec->walk_leaf;
+    double *const s_bpr = &s_rec->best_pr;
+    uint32_t *const s_win = &s_rec->walk_win;
 #ifdef RMD_STATS
     unsigned long long dbg_iter = 0, dbg_visits = 0;    // engine statistics
 #endif
@@ -432,13 +445,20 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         const int nnz = (int)(b1 - b0);
         const double *vals = J.bpp_p + b0;                    // values stay in global memory (L1)
         const uint32_t win_local = (uint32_t)(w - w_base);
-        if (tid == 0) sm.win_local = win_local;
+        if (tid == 0) { sm.win_local = win_local; sm.nnz_s = nnz; }
         // the values are first needed after the staging pass: have their lines on the way (one 128-byte line per thread)
-        if (!FUSED) for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
+        if (!FUSED) {
+UNROLL_SMALL
+            for (int k = tid * 16; k < nnz; k += SCAN_THREADS * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k));
+        }
 
         // ---- stage the window: letters, GC table, bit matrix with ranks -----------------------------
-        for (int k = tid; k < Smem::UW; k += SCAN_THREADS) sm.Ub[k] = 0;
-        for (int k = tid; k < CB_SLOTS * Smem::UW; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+        // (what runs once per window is kept small — no unrolling: 32 warps in different phases share 32 KB of instruction cache)
+UNROLL_SMALL
+        for (int k = tid; k < Smem::UW / 4; k += SCAN_THREADS) reinterpret_cast<uint4 *>(sm.Ub)[k] = make_uint4(0, 0, 0, 0);
+UNROLL_SMALL
+        for (int k = tid; k < CB_SLOTS * Smem::UW / 4; k += SCAN_THREADS) reinterpret_cast<uint4 *>(&sm.CB[0][0])[k] = make_uint4(0, 0, 0, 0);
+UNROLL_SMALL
         for (int k = tid; k < WCAP + 16; k += SCAN_THREADS) sm.letters[k] = k < wlen ? (uint8_t)get_code(J, gbase + k) : 0;
         if (tid == 0) sm.plain = 1;
         if (tid < 2) sm.chunk_ctr[tid] = 0;
@@ -457,6 +477,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         }
         if (tid < WCAP / 16 + 2) {                          // two-bit letters for the scoring engine
             uint32_t word = 0, other = 0;
+UNROLL_SMALL
             for (int k = 0; k < 16; k++) {
                 const int pos = tid * 16 + k;
                 const uint32_t c = pos < WCAP + 16 ? sm.letters[pos] : 0;
@@ -587,8 +608,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                     }
                 }
                 const double mean = cnt ? __ddiv_rn(sum, (double)cnt) : 0.0;
-                pass = act && mean >= thr_hi;
-                const bool unsure = act && !pass && mean >= thr_lo;
+                pass = act && mean >= J.thr_hi;
+                const bool unsure = act && !pass && mean >= J.thr_lo;
                 uint32_t um = __ballot_sync(FULL_MASK, unsure);
                 while (um) {                                  // the reference's own sum, one model at a time
                     const int mm = __shfl_sync(FULL_MASK, m, __ffs(um) - 1);
@@ -655,8 +676,6 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
         } else {
             // big entries x trie nodes -> placements (see the header of this file).  Every warp works on its
             // own share of the entries: no team-wide barrier in this loop.
-            const double big_min = J.min_bpp - J.min_bpp * 1e-12;   // a mean of values all below this stays below min_bpp
-            const double inv_sure_unit = 1.0 / (J.min_bpp * (1.0 + 1e-12));
             uint32_t *const wl = wq.wl, *const s2 = wq.s2;
             const int n_prel = c_n_prel;
             const int n_groups = c_n_groups;
@@ -664,7 +683,8 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             for (int grp = 0; grp < n_groups; grp++) {
                 if (grp > 0) {                                   // bitmaps of the next group of models
                     team_sync(team);
-                    for (int k = tid; k < CB_SLOTS * Smem::UW; k += SCAN_THREADS) (&sm.CB[0][0])[k] = 0;
+UNROLL_SMALL
+                    for (int k = tid; k < CB_SLOTS * Smem::UW / 4; k += SCAN_THREADS) reinterpret_cast<uint4 *>(&sm.CB[0][0])[k] = make_uint4(0, 0, 0, 0);
                     if (tid == 0) sm.chunk_ctr[(grp + 1) & 1] = 0;
                     team_sync(team);
                 }
@@ -672,25 +692,25 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 const bool last_group = grp + 1 == n_groups;
                 for (bool more = true;;) {
                     // rows shrink towards the end of the list so that the four warps finish together
-                    const int want = (int)sm.chunk_ctr[grp & 1] + TAIL_ENTRIES < nnz ? 16 : TAIL_ROW;
+                    const int want = (int)sm.chunk_ctr[grp & 1] + TAIL_ENTRIES < sm.nnz_s ? 16 : TAIL_ROW;
                     while (nl < want && more) {                   // the team's next 32 entries: keep the big ones
                         int chunk = 0;                            // taken from a team counter: the four warps stay balanced
                         if (lane == 0) chunk = (int)atomicAdd(&sm.chunk_ctr[grp & 1], 32u);
                         chunk = __shfl_sync(FULL_MASK, chunk, 0);
-                        if (chunk >= nnz) { more = false; break; }
+                        if (chunk >= sm.nnz_s) { more = false; break; }
                         const int e = chunk + lane;
                         uint32_t en = 0;
                         bool isbig = false;
-                        if (e < nnz) {
+                        if (e < sm.nnz_s) {
                             const double p = FUSED ? vals[e] : __ldg(vals + e);   // independent loads: one memory latency per chunk
                             uint32_t ei, ej;
                             if (FUSED) { const uint32_t w16 = __ldcg(J.bpp_ij + b0 + e); ei = w16 & 0xffu; ej = w16 >> 8; }
                             else { ei = J.bpp_i[b0 + e]; ej = J.bpp_j[b0 + e]; }
                             if (!(p >= 0.0)) atomicOr(&O.raw_count[7], ERR_BAD_VALUE);
-                            if (p >= big_min) {
+                            if (p >= J.big_min) {
                                 isbig = true;
                                 // the value in units of the threshold, rounded down (at most 254): compared with `need` per node
-                                const uint32_t level = (uint32_t)fmin(p * inv_sure_unit, 254.0);
+                                const uint32_t level = (uint32_t)fmin(p * J.inv_sure_unit, 254.0);
                                 en = ei | (ej << 8) | (level << 16);
                             }
                         }
@@ -785,7 +805,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                                 // a trie without a bitmap (two nodes): its first node produces the placement whenever that node's
                                 // own pair is big, the other node only otherwise (one entry and one node give one placement)
                                 const uint32_t f = plc + (ancw[(info >> 21) & 0x7fu] & 0xffffffu);
-                                ok = !(lookup((int)(f & 0xfffu), (int)(f >> 12)) >= big_min);
+                                ok = !(lookup((int)(f & 0xfffu), (int)(f >> 12)) >= J.big_min);
                             }
                         }
                         sure = sure && ok;
@@ -819,11 +839,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
             O.gate_pass[(long long)win_local * n_models + tid] = sm.gate_pass[tid];
             if (sm.gate_pass[tid]) atomicAdd(&O.raw_count[2], (unsigned long long)sm.gate_pass[tid]);
         }
-        if (tid == 0) {                                         // tests_all: closed form of the odometer
-            unsigned long long tests_all = 0;
-            for (int m = 0; m < n_models; m++) tests_all += odometer_count(c_models[m], wlen);
-            atomicAdd(&O.raw_count[1], tests_all);
-        }
+        if (tid == 0) atomicAdd(&O.raw_count[1], odometer_count_all(n_models, wlen));   // tests_all: closed form of the odometer
 #ifdef RMD_STATS
         if (lane == 0) {
             atomicAdd(&O.raw_count[4], dbg_visits); atomicAdd(&O.raw_count[5], dbg_iter); dbg_visits = 0; dbg_iter = 0;
