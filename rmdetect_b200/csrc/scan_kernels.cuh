@@ -58,7 +58,7 @@
 #define SCAN_MAX_THREADS 1024           // a CTA holds up to 8 teams of SCAN_THREADS
 #endif
 #ifndef REFILL_MIN_IDLE
-#define REFILL_MIN_IDLE 8               // the scoring engine hands out queued work once this many lanes are idle
+#define REFILL_MIN_IDLE 5               // the scoring engine hands out queued work once this many lanes are idle
 #endif
 #ifndef TAIL_ENTRIES
 #define TAIL_ENTRIES 192                // the last entries of a window are handed out in smaller rows
