@@ -120,6 +120,7 @@ struct rmd_ctx {
     unsigned int *h_ready = nullptr;    // pinned: progress marks of a streamed scan (windows whose lists have been copied)
     size_t h_gate_cap = 0;
     long long raw_cap = 0;
+    int stream_fallbacks = 0;           // streamed scans repeated as plain launches because the copies could not overlap (see scan_core)
     bool return_dropped = false;
     bool filter_score = false;          // rmd_set_min_score: drop hits with score <= min_score before the download
     double min_score = 0.0;
@@ -947,7 +948,8 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
     if (other_fast) RESERVE(ctx->d_other, sizeof(uint32_t) * (size_t)(nwin + 2));
     unsigned long long counters[16];
     int launches = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    bool grown = false;                              // the record buffer has been enlarged once for this call
+    for (int attempt = 0;; attempt++) {
         RESERVE(ctx->d_raw, sizeof(RawHit) * (size_t)ctx->raw_cap);
         launches = 0;
         CK(cudaMemsetAsync(ctx->d_counters.p, 0, 128, st));
@@ -1104,9 +1106,19 @@ static int scan_core(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_resu
         CK(cudaGetLastError());
         if (counters[7] & ERR_BAD_LIST) return fail(ctx, RMD_E_INVALID, "a window's bpp list is not a sorted, duplicate-free upper triangle (i < j < window length)");
         if (counters[7] & ERR_BAD_VALUE) return fail(ctx, RMD_E_INVALID, "a bpp value is negative or not a number");
-        if (counters[7] & ERR_TIMEOUT) return fail(ctx, RMD_E_CUDA, "streamed scan: the lists of some windows did not arrive within ten seconds");
+        if (counters[7] & ERR_TIMEOUT) {
+            // the copies did not advance while the launch was waiting for them: something serialises the GPU's work (ncu,
+            // a debugger).  The pieces are all enqueued; wait for them and scan the resident lists with a plain launch.
+            CK(cudaStreamSynchronize(ctx->copy_stream));
+            if (one_launch && attempt == 0) { ctx->stream_fallbacks++; continue; }
+            return fail(ctx, RMD_E_CUDA, "streamed scan: the lists of some windows did not arrive");
+        }
+        // Records are appended as they are found, their number is known only afterwards (at most one per gate pass).  The
+        // buffer holds 24 per window — five times what the shipped models leave on random sequence — and keeps the size it
+        // last needed; a scan that outgrows it is repeated once with room for exactly the number just counted.
         if ((long long)counters[0] <= ctx->raw_cap) break;
-        if (attempt == 1) return fail(ctx, RMD_E_NOMEM, "hit buffer overflow persisted (%llu records)", counters[0]);
+        if (grown) return fail(ctx, RMD_E_NOMEM, "hit buffer overflow persisted (%llu records)", counters[0]);
+        grown = true;
         ctx->raw_cap = (long long)counters[0] + (long long)counters[0] / 8 + 1024;   // rerun with room for every record
     }
     const long long n_raw = (long long)counters[0];

@@ -68,7 +68,8 @@
 #define SCAN_CTA_FIXED (TRIE_CAP * 32)   // bytes of CTA-wide state in front of the teams' blocks: gate tries (8 B per node), cinfo, ancw, cnw (16 B per node)
 #define ERR_BAD_LIST 1ull               // O.raw_count[7]: a window's list is not a strictly increasing upper triangle
 #define ERR_BAD_VALUE 2ull              // a stored probability is negative or not a number
-#define ERR_TIMEOUT 4ull                // a streamed scan waited ten seconds for lists that never arrived
+#define ERR_TIMEOUT 4ull                // a streamed scan saw no list arrive for STREAM_STALL_NS
+#define STREAM_STALL_NS 200000000ull    // 0.2 s
 
 struct WarpQueues {                      // one warp's work lists (one base address per warp)
     uint32_t wl[WL_CAP];                 // big entries waiting for a full row, i | j << 8 | sure-mask << 16
@@ -405,13 +406,18 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                 unsigned int have;
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(O.ready) : "memory");
                 if (have <= nx) {
+                    // pieces arrive every quarter of a millisecond; a mark that stands still for STREAM_STALL_NS means that the
+                    // copies cannot run beside this launch (a profiler or debugger that serialises the GPU's work): give up,
+                    // the host scans again once the lists are all there
                     unsigned long long t0, t1;
+                    unsigned int seen = have;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                     do {
                         __nanosleep(400);
                         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(O.ready) : "memory");
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 10000000000ull) { atomicOr(&O.raw_count[7], ERR_TIMEOUT); nx = 0xffffffffu; break; }
+                        if (have != seen) { seen = have; t0 = t1; }
+                        if (t1 - t0 > STREAM_STALL_NS) { atomicOr(&O.raw_count[7], ERR_TIMEOUT); nx = 0xffffffffu; break; }
                     } while (have <= nx);
                 }
             }
