@@ -909,7 +909,9 @@ static int ensure_host(rmd_ctx *ctx, size_t hits, size_t groups) {
 // are not on the device yet: they are copied in window chunks on the copy stream while the compute
 // stream scans the chunks already there.
 #define STREAM_CHUNKS 16
-#define STREAM_PIECES 40                  // copies of a streamed scan that runs as ONE launch (compact transport)
+#ifndef STREAM_PIECES
+#define STREAM_PIECES 80                  // copies of a streamed scan that runs as ONE launch (compact transport)
+#endif
 #ifndef STREAM_GROWTH_FUSED
 #define STREAM_GROWTH_FUSED 45             // per cent by which a chunk's end grows over the previous one's (compact transport)
 #endif
