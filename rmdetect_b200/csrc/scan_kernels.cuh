@@ -881,6 +881,7 @@ __global__ void __launch_bounds__(256) other_windows_kernel(const DevJob J, cons
 // chunks of 256, the bpp list is probed by binary search in global memory.  Exact, not fast.
 // ------------------------------------------------------------------------------------------------
 #define GEN_THREADS 256
+#define GEN_BITS_W 512
 
 __device__ __forceinline__ double bpp_search(const DevJob &J, long long b0, int nnz, int wlen, int a, int b) {
     const int lo = a < b ? a : b, hi = a < b ? b : a;
@@ -903,6 +904,9 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     __shared__ double gc[RMD_N_CODES];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_pass;
+    // which pairs are stored, for windows up to GEN_BITS_W letters: bit (lo * GEN_BITS_W + hi).  Nearly every pair the gate asks
+    // for is absent; the bit answers that without the binary search.
+    __shared__ uint32_t s_bits[GEN_BITS_W * GEN_BITS_W / 32];
     const int tid = threadIdx.x;
     const long long grp_local = blockIdx.x;
     const int m = (int)(grp_local % J.n_models);
@@ -933,8 +937,23 @@ scan_generic_kernel(const DevJob J, const long long w_begin, const long long w_e
     }
     if (tid < RMD_N_CODES) gc[tid] = J.gc_log[seq * RMD_N_CODES + tid];
     if (tid == 0) s_pass = 0;
+    const bool bits = wlen <= GEN_BITS_W;
+    if (bits) {
+        for (int k = tid; k < GEN_BITS_W * GEN_BITS_W / 32; k += GEN_THREADS) s_bits[k] = 0;
+        __syncthreads();
+        for (int e = tid; e < nnz; e += GEN_THREADS) {
+            const int i = J.bpp_i[b0 + e], j = J.bpp_j[b0 + e];
+            if (i < j && j < wlen) atomicOr(&s_bits[(i * GEN_BITS_W + j) >> 5], 1u << (j & 31));
+        }
+    }
     __syncthreads();
-    auto lookup = [&](int a, int b) { return bpp_search(J, b0, nnz, wlen, a, b); };
+    auto lookup = [&](int a, int b) {
+        if (bits) {
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            if (lo < 0 || hi >= wlen || !((s_bits[(lo * GEN_BITS_W + hi) >> 5] >> (hi & 31)) & 1u)) return 0.0;
+        }
+        return bpp_search(J, b0, nnz, wlen, a, b);
+    };
     auto letter = [&](int pos) { return get_code(J, gbase + pos); };
     const int L0 = M.chain_len[0], L1 = M.chain_len[1];
     const int n0 = rows_of(wlen, L0);
