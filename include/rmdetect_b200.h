@@ -191,7 +191,10 @@ int rmd_set_hit_format(rmd_ctx *ctx, int compact);
 int rmd_set_screen_policy(rmd_ctx *ctx, int64_t min_windows);
 /* scan windows [w_begin, w_end) of the resident job */
 int rmd_scan_resident(rmd_ctx *ctx, int64_t w_begin, int64_t w_end, rmd_scan_result *out);
-/* upload + scan of all windows + download, host buffers in, host buffers out */
+/* upload + scan of all windows + download, host buffers in, host buffers out.  With the compact transport (bpp_q) the
+   scan is one launch that runs while the copy stream is still delivering the lists; where the copies cannot run beside a
+   launch (a profiler or debugger that serialises the GPU's work) the launch sees no list arrive for 0.2 s, ends, and the
+   call scans the resident lists with a plain launch — same results, never an error for that reason. */
 int rmd_scan(rmd_ctx *ctx, const rmd_scan_input *in, rmd_scan_result *out);
 
 /* score n placements: sequence k is codes[seq_off[k] .. seq_off[k+1]) with table gc_log[k][16];

@@ -47,7 +47,9 @@ struct TrieNode {
     unsigned short skip;      // first node after this subtree
 };
 static_assert(sizeof(TrieNode) == 8, "TrieNode layout");
+#ifndef TRIE_CAP
 #define TRIE_CAP 128          // trie nodes of all resident models (checked by rmd_set_models)
+#endif
 __constant__ TrieNode c_trie[TRIE_CAP];
 __constant__ uint16_t c_prel[32];   // distinct (parent - node) offsets over all tries: (dr & 0xff) | (dc & 0xff) << 8
 __constant__ int c_n_prel;

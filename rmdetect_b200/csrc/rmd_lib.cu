@@ -532,7 +532,7 @@ extern "C" int rmd_set_models(rmd_ctx *ctx, const rmd_model_desc *models, int n_
         CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
         const size_t screens = sizeof(ScreenDesc) * (size_t)n_screens;          // always in shared memory
         const size_t tables = sizeof(XNode) * hx.size() + 16 * ((hcpt.size() + 1) / 2);
-        int teams = tune_env("RMD_TEAMS") ? atoi(tune_env("RMD_TEAMS")) : 8;
+        int teams = tune_env("RMD_TEAMS") ? atoi(tune_env("RMD_TEAMS")) : SCAN_MAX_THREADS / SCAN_THREADS;
         ctas_new = tune_env("RMD_CTAS_PER_SM") ? std::max(1, atoi(tune_env("RMD_CTAS_PER_SM"))) : 1;
         teams = std::max(1, std::min(teams, SCAN_MAX_THREADS / SCAN_THREADS));
         tables_in_smem = tables + screens + SCAN_CTA_FIXED + 2 * sizeof(FastSmem) <= (size_t)smem_max / ctas_new;

@@ -44,7 +44,9 @@
 #define FAST_W RMD_FAST_WINDOW          // 160
 #define FAST_WORDS (FAST_W / 32)        // 5
 #define UWORDS (FAST_W * FAST_WORDS)    // 800
+#ifndef SCAN_THREADS
 #define SCAN_THREADS 128
+#endif
 #define SCAN_WARPS (SCAN_THREADS / 32)
 #define Q1_CAP 64                       // gate candidates per warp: < 32 waiting + 32 pushed at once
 #define QS_CAP 96                       // gate survivors per warp: < 32 waiting + 32 sure + 32 from one gate batch
@@ -199,7 +201,7 @@ scan_fast_kernel(const DevJob J, const long long w_begin, const long long w_end,
                  const ScanOut O, const int min_wlen, unsigned int *next_window) {       // windows [w_begin, w_end); records are relative to w_base
     typedef FastSmemT<WCAP> Smem;                            // WCAP: the longest window this instantiation stages (160 or 256)
     extern __shared__ uint4 dyn_smem[];
-    int tid = threadIdx.x & (SCAN_THREADS - 1), lane = tid & 31;
+    int tid = threadIdx.x % SCAN_THREADS, lane = tid & 31;
     asm volatile("mov.u32 %0, %0;" : "+r"(tid));          // opaque like the team offset below: no re-derivation from %tid
     asm volatile("mov.u32 %0, %0;" : "+r"(lane));
     const int wid = tid >> 5, team = threadIdx.x / SCAN_THREADS;
