@@ -7,15 +7,37 @@
 //             over the letters the winning gap configuration consumed, chain 0 then chain 1
 //   :35-45    get_gc_weights: weight_i = e ** (sum_{all L letters} log gc_i[c] + L log 4)
 //   :292-295  hist_i[round(score_i, 1)] += weight_i
-// One thread per sample, classes in an inner loop with the per-class logs in shared memory.
-// Buckets are the reference's exactly (scores near a bucket boundary are recomputed in its order, see below);
-// histogram sums are order-free fp64 atomics (relative difference ~1e-13, far inside the 1e-6 bound).
+// Buckets are the reference's exactly (scores near a bucket boundary are recomputed in its order, see below); histogram
+// sums are order-free fp64 sums (relative difference ~1e-13, far inside the 1e-6 bound north_star states).
+//
+// Three kernels.  A sample that reaches no leaf of the search tree (all but a few in a thousand) scores 0 in every class
+// and only adds its weight to bucket 0, and the weight depends on the sample only through its letter counts
+// (n_A, n_C, n_G, n_U), which add up to L:  weight_i = (4 g_iU)^L x prod_{k in ACG} (g_ik / g_iU)^(n_k).  So
+//   calib_table_kernel   tabulates the powers once per session (n_class x 3 x (L + 1) doubles, the constant factor
+//                        folded into the first of the three);
+//   calibrate_kernel     one thread per sample: draw (or read) it, walk the tree, and count it in the cell
+//                        (n_A, n_C, n_G) of a per-CTA histogram in shared memory — one atomic instead of 165 weights;
+//                        a sample with a leaf is set aside in a list;
+//   calib_ok_kernel      the listed samples, one thread per (sample, class): the reference's per-class loop (score,
+//                        bucket, weight) with full warps (inside calibrate_kernel it took most of the time: a warp
+//                        with one such lane ran 165 iterations for it);
+//   calib_cells_kernel   bucket 0 of class i += sum over the cells of count x weight_i(cell): 165 x 1771 products
+//                        instead of 165 per sample.
+// A table entry is an `exp` of an exponent with one rounding, so a weight is within 1e-14 of the reference's (the tests
+// ask for 1e-9).  (Round 1/2a: every thread computed 165 weights with an `exp` each and the warps reduced bucket 0 by
+// shuffles: 0.78 ms per 2^20 KT samples.)
 #pragma once
 #include "device_common.cuh"
 
-#define CAL_THREADS 256
+#ifndef CAL_THREADS
+#define CAL_THREADS 512                 // 2 x 512 threads per SM at 64 registers (measured: 4 x 256 is 5 % slower, 3 x 256 at 85 registers 7 %)
+#define CAL_CTAS_PER_SM 2
+#endif
 #define CAL_MAX_CLASS 256
 #define CAL_SPACER 6
+#define CAL_SMEM_L 20                   // samples up to 20 letters (every shipped model) count in shared memory: 21^3 cells, 37 KB
+
+struct CalibOk { unsigned long long bits, used; double pm; int n_used, pad; };   // sample, consumed letters (2 bits each), prob_model
 
 struct CalibArgs {
     int model, L, n_class, n_bins;
@@ -23,6 +45,9 @@ struct CalibArgs {
     const uint8_t *samples;     // [n][L] codes, or nullptr: draw on the device
     unsigned long long seed;
     const double *class_log;    // [n_class][4]
+    const double *wtab;         // [n_class][3][L + 1] powers of the class frequencies (calib_table_kernel)
+    uint32_t *cells;            // [(L + 1)^3] samples without a solution, by letter counts; then the number of samples with one (zeroed per batch)
+    struct CalibOk *ok;         // the samples with a solution of the current batch
     const double *thr;          // [n_bins] rounding thresholds
     double cutoff, ln2, K;      // K = L * log(4.0)
     double *hist;               // [n_class][n_bins]
@@ -36,111 +61,142 @@ __device__ __forceinline__ unsigned long long mix64_dev(unsigned long long x) {
     return x ^ (x >> 31);
 }
 
-__global__ void __launch_bounds__(CAL_THREADS) calibrate_kernel(const CalibArgs A) {
-    __shared__ double cls[CAL_MAX_CLASS * 4];
-    __shared__ double bin0[CAL_THREADS / 32][CAL_MAX_CLASS];
-    __shared__ unsigned int s_ok;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int k = tid; k < A.n_class * 4; k += CAL_THREADS) cls[k] = A.class_log[k];
-    for (int k = tid; k < (CAL_THREADS / 32) * CAL_MAX_CLASS; k += CAL_THREADS) (&bin0[0][0])[k] = 0.0;
-    if (tid == 0) s_ok = 0;
+// The table of powers for one session: tab[i][k][n], k = 0..2 (A, C, G against U), n = 0..L
+__global__ void __launch_bounds__(256) calib_table_kernel(const double *class_log, const int n_class, const int L, double *tab) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x, NP = L + 1;
+    if (idx >= n_class * 3 * NP) return;
+    const int i = idx / (3 * NP), k = (idx / NP) % 3, n = idx % NP;
+    const double lu = class_log[4 * i + 3];
+    double e = (double)n * (class_log[4 * i + k] - lu);
+    if (k == 0) e += (double)L * (lu + 1.3862943611198906);          // (4 g_U)^L
+    tab[idx] = exp(e);
+}
+
+// the reference's own arithmetic for a score too close to a bucket boundary to call from the letter counts
+__device__ __noinline__ int calib_exact_bin(const double *lg, const unsigned long long used, const int n_used, const double pm,
+                                            const double ln2, const double *thr, const int n_bins) {
+    double p = 0.0;
+    for (int k = 0; k < n_used; k++) p = __dadd_rn(p, lg[(used >> (2 * k)) & 3]);
+    double score = __ddiv_rn(__dsub_rn(pm, p), ln2);
+    if (!(score > 0.0)) return 0;
+    int bin = (int)(score * 10.0 + 0.5);
+    if (bin > n_bins) bin = n_bins;
+    while (bin > 0 && score < __ldg(thr + bin - 1)) bin--;
+    while (bin < n_bins && score >= __ldg(thr + bin)) bin++;
+    return bin;
+}
+
+// One thread per sample; persistent CTAs (grid-stride over batches of CAL_THREADS samples) with the count histogram in
+// shared memory (SMEM_CELLS: (L + 1)^3 cells fit) or straight in global memory (samples longer than CAL_SMEM_L letters).
+template <bool SMEM_CELLS>
+__global__ void __launch_bounds__(CAL_THREADS, CAL_CTAS_PER_SM) calibrate_kernel(const CalibArgs A) {
+    extern __shared__ uint32_t cal_cells[];           // [(L + 1)^3], index (n_A * (L + 1) + n_C) * (L + 1) + n_G
+    const int tid = threadIdx.x;
+    const int L = A.L, NP = L + 1, n_cells = NP * NP * NP;
+    if (SMEM_CELLS)
+        for (int k = tid; k < n_cells; k += CAL_THREADS) cal_cells[k] = 0;
     __syncthreads();
 
     const CModel &M = c_models[A.model];
-    const int L = A.L, L0 = M.chain_len[0];
-    const long long s = (long long)blockIdx.x * CAL_THREADS + tid;
-    const bool live = s < A.n;
-    unsigned long long bits = 0;                      // the sample, 2 bits per letter
-    if (live) {
-        if (A.samples) {
-            for (int k = 0; k < L; k++) bits |= (unsigned long long)(A.samples[s * L + k] & 3) << (2 * k);
-        } else {
-            const unsigned long long g0 = (unsigned long long)(A.first + s) * (unsigned long long)L;
-            for (int k = 0; k < L; k++)
-                bits |= (mix64_dev(A.seed + 0x9E3779B97F4A7C15ULL * (g0 + k + 1)) >> 62) << (2 * k);
-        }
-    }
-    auto letter = [&](int pos) {                      // the sample with the CCCCCC spacer spliced in
-        if (pos < L0) return (int)((bits >> (2 * pos)) & 3);
-        if (pos < L0 + CAL_SPACER) return 1;
-        return (int)((bits >> (2 * (pos - CAL_SPACER))) & 3);
-    };
+    const int L0 = M.chain_len[0];
     double neutral[RMD_N_CODES];
 #pragma unroll
     for (int k = 0; k < RMD_N_CODES; k++) neutral[k] = -1.3862943611198906;   // math.log(0.25), GC.neutral()
-    EvalOut r; r.leaf = -1; r.pm = 0.0; r.pr = 0.0;
-    if (live) r = eval_placement(M, letter, neutral, 0, L0 + CAL_SPACER, A.cutoff);
-    const bool ok = r.leaf >= 0;
-    unsigned long long used = 0;                      // letters consumed by the winning configuration
-    int n_used = 0;
-    if (ok) {
+    for (long long s = (long long)blockIdx.x * CAL_THREADS + tid; s < A.n; s += (long long)gridDim.x * CAL_THREADS) {
+        unsigned long long bits = 0;                  // the sample, 2 bits per letter
+        if (A.samples) {
+            for (int k = 0; k < L; k++) bits |= (unsigned long long)(A.samples[s * L + k] & 3) << (2 * k);
+        } else {
+            // sample s of the stream: the low 2L bits of one 64-bit hash (host twin: synth.synth_calibration_samples)
+            const unsigned long long h = mix64_dev(A.seed + 0x9E3779B97F4A7C15ULL * ((unsigned long long)(A.first + s) + 1ULL));
+            bits = L >= 32 ? h : h & ((1ULL << (2 * L)) - 1ULL);
+        }
+        auto letter = [&](int pos) {                  // the sample with the CCCCCC spacer spliced in
+            if (pos < L0) return (int)((bits >> (2 * pos)) & 3);
+            if (pos < L0 + CAL_SPACER) return 1;
+            return (int)((bits >> (2 * (pos - CAL_SPACER))) & 3);
+        };
+        const EvalOut r = eval_placement(M, letter, neutral, 0, L0 + CAL_SPACER, A.cutoff);
+        // letter counts of the whole sample: A = 0, C = 1, G = 2, U = 3 in two bits per letter
+        const unsigned long long lo1 = bits & 0x5555555555555555ULL, hi1 = (bits >> 1) & 0x5555555555555555ULL;
+        const int n_c = __popcll(lo1 & ~hi1), n_g = __popcll(hi1 & ~lo1), n_a = L - n_c - n_g - __popcll(lo1 & hi1);
+        if (r.leaf < 0) {                             // no solution: score 0 in every class, the weights follow from the counts
+            const int cell = (n_a * NP + n_c) * NP + n_g;
+            if (SMEM_CELLS) atomicAdd(&cal_cells[cell], 1u);
+            else atomicAdd(A.cells + cell, 1u);
+            continue;
+        }
+        // a sample with a solution (a few in a thousand) scores in every class: it is set aside for calib_ok_kernel,
+        // which works through (sample, class) pairs with full warps
+        CalibOk rec;
+        rec.bits = bits; rec.used = 0; rec.pm = r.pm; rec.n_used = 0;
         const int8_t *lo = M.leaf_offsets + r.leaf * L;
-        for (int k = 0; k < L; k++) {
+        for (int k = 0; k < L; k++) {                 // letters consumed by the winning configuration, chain 0 then chain 1
             const int o = lo[k];
             if (o >= 0) {
                 const int pos = k < L0 ? o : L0 + o;  // index into the sample
-                used |= ((bits >> (2 * pos)) & 3ULL) << (2 * n_used);
-                n_used++;
+                rec.used |= ((bits >> (2 * pos)) & 3ULL) << (2 * rec.n_used);
+                rec.n_used++;
             }
         }
-        atomicAdd(&s_ok, 1u);
-    }
-    // letter counts: of the whole sample (weights) and of the letters the winning configuration consumed (scores)
-    double n_all[4] = {0.0, 0.0, 0.0, 0.0}, n_use[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < L; k++) {
-        const int c = (int)((bits >> (2 * k)) & 3);
-#pragma unroll
-        for (int q = 0; q < 4; q++) n_all[q] += c == q ? 1.0 : 0.0;
-    }
-    for (int k = 0; k < n_used; k++) {
-        const int c = (int)((used >> (2 * k)) & 3);
-#pragma unroll
-        for (int q = 0; q < 4; q++) n_use[q] += c == q ? 1.0 : 0.0;
-    }
-    const double inv_ln2 = 1.0 / A.ln2;
-    for (int i = 0; i < A.n_class; i++) {
-        const double *lg = cls + 4 * i;
-        const double l0 = lg[0], l1 = lg[1], l2 = lg[2], l3 = lg[3];
-        // The weight enters the histograms only as a sum of ~1e4-1e6 terms (order-free, tolerance 1e-6): its
-        // exponent comes from the letter counts.  The score decides a bucket, which must be the reference's: it is
-        // first estimated from the counts (within 1e-12 of the reference's letter-by-letter sum) and recomputed in
-        // the reference's order only when the estimate lies within 1e-8 of a bucket boundary.
-        const double pw = n_all[0] * l0 + n_all[1] * l1 + n_all[2] * l2 + n_all[3] * l3;
-        const double weight = live ? exp(pw + A.K) : 0.0;
-        int bin = 0;
-        if (ok) {
-            const double est = (r.pm - (n_use[0] * l0 + n_use[1] * l1 + n_use[2] * l2 + n_use[3] * l3)) * inv_ln2;
-            const double scaled = est * 10.0 + 0.5;
-            bin = scaled > 0.0 ? (int)scaled : 0;
-            const double frac = scaled - (double)bin;
-            if (scaled > -1e-6 && (frac < 1e-7 || frac > 1.0 - 1e-7)) {       // too close to call: the reference's own arithmetic
-                double p = 0.0;
-                for (int k = 0; k < n_used; k++) p = __dadd_rn(p, lg[(used >> (2 * k)) & 3]);
-                double score = __ddiv_rn(__dsub_rn(r.pm, p), A.ln2);
-                if (!(score > 0.0)) score = 0.0;
-                bin = 0;
-                if (score > 0.0) {
-                    bin = (int)(score * 10.0 + 0.5);
-                    if (bin > A.n_bins) bin = A.n_bins;
-                    while (bin > 0 && score < __ldg(A.thr + bin - 1)) bin--;
-                    while (bin < A.n_bins && score >= __ldg(A.thr + bin)) bin++;
-                }
-            }
-            if (bin > A.n_bins) bin = A.n_bins;
-        }
-        double w0 = bin == 0 ? weight : 0.0;          // the common bucket: reduce in the warp first
-        for (int o = 16; o; o >>= 1) w0 += __shfl_down_sync(FULL_MASK, w0, o);
-        if (lane == 0) bin0[wid][i] += w0;
-        if (bin != 0 && live) {
-            if (bin >= A.n_bins) atomicOr(A.overflow, 1);
-            else atomicAdd(A.hist + (long long)i * A.n_bins + bin, weight);
-        }
+        A.ok[atomicAdd(A.cells + n_cells, 1u)] = rec;
     }
     __syncthreads();
-    for (int i = tid; i < A.n_class; i += CAL_THREADS) {
-        double t = 0.0;
-        for (int w = 0; w < CAL_THREADS / 32; w++) t += bin0[w][i];
-        if (t != 0.0) atomicAdd(A.hist + (long long)i * A.n_bins, t);
+    if (SMEM_CELLS)
+        for (int k = tid; k < n_cells; k += CAL_THREADS)
+            if (cal_cells[k]) atomicAdd(A.cells + k, cal_cells[k]);
+}
+
+// The samples with a solution, one thread per (sample, class): the reference's per-class loop (rmcalibrate.py:47-62,292-295)
+__global__ void __launch_bounds__(256) calib_ok_kernel(const CalibArgs A) {
+    const int L = A.L, NP = L + 1;
+    const uint32_t cnt = A.cells[NP * NP * NP];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cnt) atomicAdd(A.n_ok, (unsigned long long)cnt);
+    const long long total = (long long)cnt * A.n_class;
+    const double inv_ln2 = 1.0 / A.ln2;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const int j = (int)(idx / A.n_class), i = (int)(idx - (long long)j * A.n_class);
+        const CalibOk rec = A.ok[j];
+        // letter counts of the whole sample (weight) and of the consumed letters (score): two bits per letter
+        unsigned long long lo1 = rec.bits & 0x5555555555555555ULL, hi1 = (rec.bits >> 1) & 0x5555555555555555ULL;
+        const int n_c = __popcll(lo1 & ~hi1), n_g = __popcll(hi1 & ~lo1), n_a = L - n_c - n_g - __popcll(lo1 & hi1);
+        lo1 = rec.used & 0x5555555555555555ULL; hi1 = (rec.used >> 1) & 0x5555555555555555ULL;
+        const int u_c = __popcll(lo1 & ~hi1), u_g = __popcll(hi1 & ~lo1), u_u = __popcll(lo1 & hi1), u_a = rec.n_used - u_c - u_g - u_u;
+        const double *lg = A.class_log + 4 * i, *tb = A.wtab + (long long)i * 3 * NP;
+        const double weight = __ldg(tb + n_a) * __ldg(tb + NP + n_c) * __ldg(tb + 2 * NP + n_g);
+        // The score decides a bucket, which must be the reference's: it is first estimated from the counts (within 1e-12 of
+        // the reference's letter-by-letter sum) and recomputed in the reference's order only when the estimate lies within
+        // 1e-8 of a bucket boundary.
+        const double est = (rec.pm - ((double)u_a * __ldg(lg) + (double)u_c * __ldg(lg + 1) + (double)u_g * __ldg(lg + 2) + (double)u_u * __ldg(lg + 3))) * inv_ln2;
+        const double scaled = est * 10.0 + 0.5;
+        int bin = scaled > 0.0 ? (int)scaled : 0;
+        const double frac = scaled - (double)bin;
+        if (scaled > -1e-6 && (frac < 1e-7 || frac > 1.0 - 1e-7))               // too close to call
+            bin = calib_exact_bin(lg, rec.used, rec.n_used, rec.pm, A.ln2, A.thr, A.n_bins);
+        if (bin >= A.n_bins) atomicOr(A.overflow, 1);
+        else atomicAdd(A.hist + (long long)i * A.n_bins + bin, weight);
     }
-    if (tid == 0 && s_ok) atomicAdd(A.n_ok, (unsigned long long)s_ok);
+}
+
+// bucket 0 of class blockIdx.x += sum over the cells of count x weight(cell)
+__global__ void __launch_bounds__(256) calib_cells_kernel(const CalibArgs A) {
+    __shared__ double part[8];
+    const int i = blockIdx.x, NP = A.L + 1;
+    const double *tb = A.wtab + (long long)i * 3 * NP;
+    double sum = 0.0;
+    for (int k = threadIdx.x; k < NP * NP * NP; k += 256) {
+        const uint32_t cnt = A.cells[k];
+        if (cnt) {
+            const int g = k % NP, c = (k / NP) % NP, a = k / (NP * NP);
+            sum += (double)cnt * (__ldg(tb + a) * __ldg(tb + NP + c) * __ldg(tb + 2 * NP + g));
+        }
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_down_sync(FULL_MASK, sum, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += part[w];
+        if (t != 0.0) A.hist[(long long)i * A.n_bins] += t;       // one CTA per class, after calibrate_kernel on the same stream
+    }
 }

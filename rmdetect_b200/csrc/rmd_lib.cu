@@ -117,6 +117,8 @@ struct rmd_ctx {
     bool compact_hits = false;          // rmd_set_hit_format
     DBuf d_pack;
     uint32_t *h_gate = nullptr, *h_group = nullptr;
+    double *h_calhist = nullptr;        // pinned: rmd_calibrate's download of a session's histogram
+    size_t h_calhist_n = 0;
     unsigned int *h_ready = nullptr;    // pinned: progress marks of a streamed scan (windows whose lists have been copied)
     size_t h_gate_cap = 0;
     long long raw_cap = 0;
@@ -125,8 +127,10 @@ struct rmd_ctx {
     bool filter_score = false;          // rmd_set_min_score: drop hits with score <= min_score before the download
     double min_score = 0.0;
     // eval / calibrate scratch
-    DBuf d_e0, d_e1, d_e2, d_e3, d_e4, d_e5, d_e6, d_e7;
-    // calibration session (rmd_calib_open .. rmd_calib_read): histogram in d_e3, counters in d_e4
+    DBuf d_e0, d_e1, d_e2, d_e3, d_e4, d_e5, d_e6, d_e7, d_caltab, d_calcells, d_calcls, d_calthr, d_calhist, d_calcnt, d_calok;
+    int cal_thr_bins = 0;                          // rounding thresholds resident in d_calthr for this many buckets
+    size_t cal_smem = 0;                           // calibrate_kernel's count histogram in shared memory (0: in global memory)
+    // calibration session (rmd_calib_open .. rmd_calib_read): buffers of its own (d_cal*), so that rmd_eval calls in between leave it alone
     CalibArgs cal{};
     bool cal_open = false, cal_timed = false;
     // the last scan's kept hits, still on the device (rmd_table_append_scan)
@@ -208,7 +212,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
                     &ctx->d_bpp_off, &ctx->d_bpp_i, &ctx->d_bpp_j, &ctx->d_bpp_p, &ctx->d_flag, &ctx->d_counts, &ctx->d_bpp_cnt, &ctx->d_bpp_ij, &ctx->d_bpp_q,
                     &ctx->d_raw, &ctx->d_counters, &ctx->d_gate_pass, &ctx->d_group_hits, &ctx->d_group_off, &ctx->d_scan_sums,
                     &ctx->d_final, &ctx->d_keep, &ctx->d_keep_off, &ctx->d_compact, &ctx->d_pack,
-                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_other, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7};
+                    &ctx->d_xnodes, &ctx->d_xcpt, &ctx->d_next, &ctx->d_other, &ctx->d_e0, &ctx->d_e1, &ctx->d_e2, &ctx->d_e3, &ctx->d_e4, &ctx->d_e5, &ctx->d_e6, &ctx->d_e7, &ctx->d_caltab, &ctx->d_calcells, &ctx->d_calcls, &ctx->d_calthr, &ctx->d_calhist, &ctx->d_calcnt, &ctx->d_calok};
     for (DBuf *b : bufs) if (b->p) cudaFree(b->p);
     HitTable &T = ctx->table;
     DBuf *tbufs[] = {&T.rows, &T.rows_alt, &T.keys, &T.keys_alt, &T.idx, &T.idx_alt, &T.flag, &T.off, &T.aux32, &T.aux64, &T.hist, &T.hist_off, &T.totals,
@@ -218,6 +222,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
     if (ctx->h_gate) cudaFreeHost(ctx->h_gate);
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
     if (ctx->h_ready) cudaFreeHost(ctx->h_ready);
+    if (ctx->h_calhist) cudaFreeHost(ctx->h_calhist);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1290,27 +1295,42 @@ extern "C" int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *
     if (L != M.chain_len[0] + M.chain_len[1]) return fail(ctx, RMD_E_INVALID, "rmd_calib_open: L is %d, the model has %d positions", L, M.chain_len[0] + M.chain_len[1]);
     if (L > 32) return fail(ctx, RMD_E_LIMIT, "rmd_calib_open: at most 32 positions");
     if (!class_log || n_class < 1 || n_class > CAL_MAX_CLASS || n_bins < 2) return fail(ctx, RMD_E_LIMIT, "rmd_calib_open: class count %d / bin count %d out of range", n_class, n_bins);
+    // a weight is a product of powers of frequency ratios (calib_kernels.cuh): every frequency must be positive, as in the
+    // reference, whose math.log raises on a zero (rmcalibrate.py:224, lib/gcx.py)
+    for (int k = 0; k < 4 * n_class; k++)
+        if (!std::isfinite(class_log[k])) return fail(ctx, RMD_E_INVALID, "rmd_calib_open: class %d has a log-frequency that is not finite", k / 4);
     std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    std::vector<double> thr;
-    calib_thresholds(thr, n_bins);
-    RESERVE(ctx->d_e1, sizeof(double) * 4 * n_class);
-    RESERVE(ctx->d_e2, sizeof(double) * n_bins);
-    RESERVE(ctx->d_e3, sizeof(double) * (size_t)n_class * n_bins);
-    RESERVE(ctx->d_e4, 64);
-    CK(cudaMemcpyAsync(ctx->d_e1.p, class_log, sizeof(double) * 4 * n_class, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_e2.p, thr.data(), sizeof(double) * n_bins, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(ctx->d_e3.p, 0, sizeof(double) * (size_t)n_class * n_bins, st));
-    CK(cudaMemsetAsync(ctx->d_e4.p, 0, 64, st));
-    CK(cudaStreamSynchronize(st));                 // thr goes out of scope
+    const size_t n_cells = (size_t)(L + 1) * (L + 1) * (L + 1);
+    ctx->cal_smem = L <= CAL_SMEM_L ? sizeof(uint32_t) * n_cells : 0;
+    RESERVE(ctx->d_caltab, sizeof(double) * (size_t)n_class * 3 * (L + 1));
+    RESERVE(ctx->d_calcells, sizeof(uint32_t) * (n_cells + 1));
+    RESERVE(ctx->d_calcls, sizeof(double) * 4 * n_class);
+    RESERVE(ctx->d_calhist, sizeof(double) * (size_t)n_class * n_bins);
+    RESERVE(ctx->d_calcnt, 64);
+    if (ctx->cal_thr_bins != n_bins) {               // the rounding thresholds depend on the bucket count only: once per context
+        std::vector<double> thr;
+        calib_thresholds(thr, n_bins);
+        ctx->cal_thr_bins = 0;
+        RESERVE(ctx->d_calthr, sizeof(double) * n_bins);
+        CK(cudaMemcpy(ctx->d_calthr.p, thr.data(), sizeof(double) * n_bins, cudaMemcpyHostToDevice));
+        ctx->cal_thr_bins = n_bins;
+    }
+    CK(cudaMemcpyAsync(ctx->d_calcls.p, class_log, sizeof(double) * 4 * n_class, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->d_calhist.p, 0, sizeof(double) * (size_t)n_class * n_bins, st));
+    CK(cudaMemsetAsync(ctx->d_calcnt.p, 0, 64, st));
+    calib_table_kernel<<<(unsigned)((n_class * 3 * (L + 1) + 255) / 256), 256, 0, st>>>((const double *)ctx->d_calcls.p, n_class, L, (double *)ctx->d_caltab.p);
+    CK(cudaStreamSynchronize(st));                 // the caller's class_log may be reused on return
+    CK(cudaGetLastError());
     CalibArgs &A = ctx->cal;
     A.model = model; A.L = L; A.n_class = n_class; A.n_bins = n_bins; A.n = 0; A.first = 0;
     A.samples = nullptr; A.seed = 0;
-    A.class_log = (const double *)ctx->d_e1.p; A.thr = (const double *)ctx->d_e2.p;
+    A.class_log = (const double *)ctx->d_calcls.p; A.thr = (const double *)ctx->d_calthr.p;
+    A.wtab = (const double *)ctx->d_caltab.p; A.cells = (uint32_t *)ctx->d_calcells.p;
     A.cutoff = cutoff; A.ln2 = std::log(2.0); A.K = L * std::log(4.0);
-    A.hist = (double *)ctx->d_e3.p;
-    A.n_ok = (unsigned long long *)ctx->d_e4.p; A.overflow = (int *)((char *)ctx->d_e4.p + 8);
+    A.hist = (double *)ctx->d_calhist.p;
+    A.n_ok = (unsigned long long *)ctx->d_calcnt.p; A.overflow = (int *)((char *)ctx->d_calcnt.p + 8);
     ctx->cal_open = true; ctx->cal_timed = false;
     return RMD_OK;
 }
@@ -1331,7 +1351,15 @@ extern "C" int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed
     }
     A.n = n; A.first = first; A.seed = seed;
     if (!ctx->cal_timed) { CK(cudaEventRecord(ctx->ev[0], st)); ctx->cal_timed = true; }
-    calibrate_kernel<<<(unsigned)((n + CAL_THREADS - 1) / CAL_THREADS), CAL_THREADS, 0, st>>>(A);
+    // persistent CTAs: the count histogram is flushed once per CTA
+    const unsigned grid = (unsigned)std::min<long long>((n + CAL_THREADS - 1) / CAL_THREADS, (long long)ctx->sm_count * CAL_CTAS_PER_SM);
+    RESERVE(ctx->d_calok, sizeof(CalibOk) * (size_t)n);              // every sample of the batch may have a solution
+    A.ok = (CalibOk *)ctx->d_calok.p;
+    CK(cudaMemsetAsync(A.cells, 0, sizeof(uint32_t) * ((size_t)(A.L + 1) * (A.L + 1) * (A.L + 1) + 1), st));
+    if (ctx->cal_smem) calibrate_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
+    else calibrate_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+    calib_ok_kernel<<<(unsigned)std::min<long long>((n * A.n_class + 255) / 256, (long long)ctx->sm_count * 8), 256, 0, st>>>(A);
+    calib_cells_kernel<<<(unsigned)A.n_class, 256, 0, st>>>(A);
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaGetLastError());
     if (samples) CK(cudaStreamSynchronize(st));    // the caller's buffer may be reused on return
@@ -1356,7 +1384,7 @@ extern "C" int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t
     cudaStream_t st = ctx->stream;
     unsigned long long small[2] = {0, 0};
     if (hist) CK(cudaMemcpyAsync(hist, ctx->cal.hist, sizeof(double) * (size_t)ctx->cal.n_class * ctx->cal.n_bins, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(small, ctx->d_e4.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(small, ctx->d_calcnt.p, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (n_ok) *n_ok = (int64_t)small[0];
@@ -1375,9 +1403,16 @@ static int calibrate_once(rmd_ctx *ctx, int model, const uint8_t *samples, uint6
     int r;
     if ((r = rmd_calib_open(ctx, model, L, class_log, n_class, cutoff, n_bins))) return r;
     if ((r = rmd_calib_add(ctx, samples, seed, first, n))) return r;
-    std::vector<double> h((size_t)n_class * n_bins);
-    if ((r = rmd_calib_read(ctx, h.data(), n_ok, overflow, ms_kernel))) return r;
-    for (size_t k = 0; k < h.size(); k++) hist[k] += h[k];
+    const size_t nh = (size_t)n_class * n_bins;
+    if (ctx->h_calhist_n < nh) {                   // pinned staging: the download is a third of a short call
+        if (ctx->h_calhist) cudaFreeHost(ctx->h_calhist);
+        ctx->h_calhist = nullptr; ctx->h_calhist_n = 0;
+        CK(cudaMallocHost((void **)&ctx->h_calhist, sizeof(double) * nh));
+        ctx->h_calhist_n = nh;
+    }
+    const double *h = ctx->h_calhist;
+    if ((r = rmd_calib_read(ctx, ctx->h_calhist, n_ok, overflow, ms_kernel))) return r;
+    for (size_t k = 0; k < nh; k++) hist[k] += h[k];
     ctx->cal_open = false;
     return RMD_OK;
 }

@@ -62,12 +62,12 @@ def synth_sequence(n, seed, start=0, reverse_total=0) -> str:
 
 
 def synth_calibration_samples(seed, first, n, L):
-    """Host twin of the draw inside rmd_calibrate_synth (csrc/calib_kernels.cuh): letter j of sample s is the top
-    two bits of mix64(seed + GOLDEN * (s * L + j + 1)), s in [first, first + n).  Returns codes [n][L]."""
-    g = (np.arange(first, first + n, dtype=np.int64)[:, None] * L + np.arange(L, dtype=np.int64)[None, :]).astype(U64)
+    """Host twin of the draw inside rmd_calibrate_synth (csrc/calib_kernels.cuh): sample s is the low 2L bits of
+    mix64(seed + GOLDEN * (s + 1)), letter j its bits 2j and 2j + 1, s in [first, first + n); L <= 32.  Returns codes [n][L]."""
+    g = np.arange(first, first + n, dtype=np.int64).astype(U64)
     with np.errstate(over="ignore"):
         h = mix64(U64(seed) + GOLDEN * (g + U64(1)))
-    return (h >> U64(62)).astype(np.uint8)
+    return ((h[:, None] >> (U64(2) * np.arange(L, dtype=U64))[None, :]) & U64(3)).astype(np.uint8)
 
 
 def _hash_bytes(seq: str) -> np.ndarray:
