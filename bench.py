@@ -109,11 +109,13 @@ class ClockSampler(threading.Thread):
 
 
 def cal_roofline(kernel_ms, samples, n_class):
-    """calibrate_kernel against the fp64 pipe: one exp (the class weight) and the score's bucket per (sample, class).  The
-    algorithmic work is counted in (sample, class) pairs; the pipe figures come from the committed ncu capture of one launch
-    of 2^20 samples (profiles/r*_calibrate_ncu_full.csv), the rate is measured live."""
+    """calibrate_kernel (csrc/calib_kernels.cuh): one tree walk per sample; the 165 weights per sample are not computed one
+    by one (samples without a solution are counted by letter composition, their weights follow from 165 x 1771 products), so
+    the kernel is bound by instruction issue in the tree walk.  The algorithmic work is counted in (sample, class) pairs, as
+    the reference does it; the pipe figures come from the committed ncu capture of one launch of 2^20 samples
+    (profiles/r*_calibrate_ncu_full.csv), the rate is measured live."""
     ncu = ncu_summary("calibrate")
-    out = {"bound": "fp64 pipe / issue", "achieved": samples * n_class / (kernel_ms * 1e-3), "unit": "(sample, class) pairs/s"}
+    out = {"bound": "issue (tree walk)", "achieved": samples * n_class / (kernel_ms * 1e-3), "unit": "(sample, class) pairs/s"}
     if ncu:
         p = ncu["pct"]
         out.update({"source": ncu["file"],
@@ -454,8 +456,8 @@ def run_ours(args):
             "calibration": {"metric": "calibration samples scored/sec", "value": CAL_SAMPLES * len(models) * world / cal_wall,
                             "unit": "samples/s", "samples_per_model_per_gpu": CAL_SAMPLES, "classes": int(len(cl)),
                             "ms_total": 1e3 * cal_wall, "kernel_ms": cal_kernel_ms,
-                            "note": "rmd_calibrate_synth: one batch of device-drawn samples per model and GPU, 165 weighted "
-                                    "scores each, histograms downloaded per model",
+                            "note": "rmd_calibrate_synth: one batch of device-drawn samples per model and GPU, scored against 165 "
+                                    "GC classes (weighted histograms), histograms downloaded per model",
                             "reference_loop": {
                                 "value": cal_done / cal_loop_wall, "unit": "samples/s", "samples": int(cal_done),
                                 "blocks": int(cal_blocks), "ms_total": 1e3 * cal_loop_wall, "kernel_ms": cal_loop_kernel_ms,

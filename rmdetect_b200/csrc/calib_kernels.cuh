@@ -48,6 +48,8 @@ struct CalibArgs {
     const double *wtab;         // [n_class][3][L + 1] powers of the class frequencies (calib_table_kernel)
     uint32_t *cells;            // [(L + 1)^3] samples without a solution, by letter counts; then the number of samples with one (zeroed per batch)
     struct CalibOk *ok;         // the samples with a solution of the current batch
+    const XNode *xnodes;        // the scoring engine's tables (all models; CModel::xnode0)
+    const double *xcpt;
     const double *thr;          // [n_bins] rounding thresholds
     double cutoff, ln2, K;      // K = L * log(4.0)
     double *hist;               // [n_class][n_bins]
@@ -84,6 +86,23 @@ __device__ __noinline__ int calib_exact_bin(const double *lg, const unsigned lon
     while (bin > 0 && score < __ldg(thr + bin - 1)) bin--;
     while (bin < n_bins && score >= __ldg(thr + bin)) bin++;
     return bin;
+}
+
+// a sample with a solution goes to the list of calib_ok_kernel with the letters its winning configuration consumed
+__device__ __noinline__ void calib_set_aside(const CalibArgs &A, const CModel &M, const unsigned long long bits, const int leaf,
+                                             const double pm, const int L, const int L0, const int n_cells) {
+    CalibOk rec;
+    rec.bits = bits; rec.used = 0; rec.pm = pm; rec.n_used = 0; rec.pad = 0;
+    const int8_t *lo = M.leaf_offsets + leaf * L;
+    for (int k = 0; k < L; k++) {                     // chain 0 then chain 1
+        const int o = lo[k];
+        if (o >= 0) {
+            const int pos = k < L0 ? o : L0 + o;      // index into the sample
+            rec.used |= ((bits >> (2 * pos)) & 3ULL) << (2 * rec.n_used);
+            rec.n_used++;
+        }
+    }
+    A.ok[atomicAdd(A.cells + n_cells, 1u)] = rec;
 }
 
 // One thread per sample; persistent CTAs (grid-stride over batches of CAL_THREADS samples) with the count histogram in
@@ -128,18 +147,99 @@ __global__ void __launch_bounds__(CAL_THREADS, CAL_CTAS_PER_SM) calibrate_kernel
         }
         // a sample with a solution (a few in a thousand) scores in every class: it is set aside for calib_ok_kernel,
         // which works through (sample, class) pairs with full warps
-        CalibOk rec;
-        rec.bits = bits; rec.used = 0; rec.pm = r.pm; rec.n_used = 0;
-        const int8_t *lo = M.leaf_offsets + r.leaf * L;
-        for (int k = 0; k < L; k++) {                 // letters consumed by the winning configuration, chain 0 then chain 1
-            const int o = lo[k];
-            if (o >= 0) {
-                const int pos = k < L0 ? o : L0 + o;  // index into the sample
-                rec.used |= ((bits >> (2 * pos)) & 3ULL) << (2 * rec.n_used);
-                rec.n_used++;
+        calib_set_aside(A, M, bits, r.leaf, r.pm, L, L0, n_cells);
+    }
+    __syncthreads();
+    if (SMEM_CELLS)
+        for (int k = tid; k < n_cells; k += CAL_THREADS)
+            if (cal_cells[k]) atomicAdd(A.cells + k, cal_cells[k]);
+}
+
+// The same with the scan kernel's scoring engine (scan_kernels.cuh; lib/node.py:176-277 on the pre-decoded 32-byte nodes):
+// walks of random samples end after 2 to 272 tree nodes, and with one sample per thread a warp waited for its longest walk
+// (7 of 32 lanes active, ncu).  Here a warp owns a contiguous range of the batch, every lane carries its own sample and walk,
+// visits one tree node per iteration, and lanes that have finished take the warp's next samples once CAL_REFILL_IDLE of
+// them are idle.  For model sets the engine's node format holds (chains up to 16 letters) and a cutoff that lets the root pass.
+#ifndef CAL_REFILL_IDLE
+#define CAL_REFILL_IDLE 8
+#endif
+template <bool SMEM_CELLS>
+__global__ void __launch_bounds__(CAL_THREADS, CAL_CTAS_PER_SM) calibrate_engine_kernel(const CalibArgs A) {
+    extern __shared__ uint32_t cal_cells[];           // [(L + 1)^3], index (n_A * (L + 1) + n_C) * (L + 1) + n_G
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int L = A.L, NP = L + 1, n_cells = NP * NP * NP;
+    if (SMEM_CELLS)
+        for (int k = tid; k < n_cells; k += CAL_THREADS) cal_cells[k] = 0;
+    __syncthreads();
+    uint32_t lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    const CModel &M = c_models[A.model];
+    const int L0 = M.chain_len[0];
+    const uint32_t xnode0 = (uint32_t)M.xnode0;
+    const uint4 *const xn = reinterpret_cast<const uint4 *>(A.xnodes);
+    const double g = -1.3862943611198906;             // math.log(0.25): GC.neutral() gives every letter (and the gap) this
+    const int d = L0 + CAL_SPACER;                    // pointers [0, L0 + 6] (rmcalibrate.py:229)
+    const unsigned long long m0 = (1ULL << (2 * L0)) - 1ULL;   // chain 0 of the sample (chains hold at most 16 letters)
+    // this warp's samples
+    const long long n_warps = (long long)gridDim.x * (CAL_THREADS / 32), warp = (long long)blockIdx.x * (CAL_THREADS / 32) + (tid >> 5);
+    const long long per = (A.n + n_warps - 1) / n_warps;
+    long long next = min(A.n, warp * per);
+    const long long end = min(A.n, next + per);
+
+    uint32_t e_t = XNODE_END;                         // node of the lane's walk (XNODE_END: idle)
+    unsigned long long bits = 0, e_m = 0;             // the sample; its chains as the engine reads them (chain 1 from bit 32 on)
+    double e_pm = 0.0, e_pr = 0.0, e_bpm = -500.0;
+    int e_leaf = -1;
+    double2 e_stk[RMD_MAX_BRANCH_DEPTH + 2];          // sums saved at gap branches (slot 0: the implicit root's zeros)
+    e_stk[0] = make_double2(0.0, 0.0);
+    for (;;) {
+        const uint32_t im = __ballot_sync(FULL_MASK, e_t == XNODE_END);
+        if (next < end && (__popc(im) >= CAL_REFILL_IDLE || im == FULL_MASK)) {   // idle lanes take the next samples
+            const long long s = next + __popc(im & lt_mask);
+            if ((im >> lane & 1) && s < end) {
+                if (A.samples) {
+                    bits = 0;
+                    for (int k = 0; k < L; k++) bits |= (unsigned long long)(A.samples[s * L + k] & 3) << (2 * k);
+                } else {
+                    const unsigned long long h = mix64_dev(A.seed + 0x9E3779B97F4A7C15ULL * ((unsigned long long)(A.first + s) + 1ULL));
+                    bits = L >= 32 ? h : h & ((1ULL << (2 * L)) - 1ULL);
+                }
+                e_m = (bits & m0) | ((bits >> (2 * L0)) << 32);
+                e_t = xnode0; e_pm = 0.0; e_pr = 0.0; e_bpm = -500.0; e_leaf = -1;     // lib/node.py:250-251
+            }
+            next = min(end, next + __popc(im));
+        }
+        const bool busy = e_t != XNODE_END;
+        if (!__any_sync(FULL_MASK, busy)) break;      // nothing in flight and nothing left to take
+        if (busy) {
+            const uint4 a = __ldg(xn + 2 * e_t);                      // sel, cpt, m0 | m1 << 16, skip | next << 16
+            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(xn + 2 * e_t + 1));   // leaf | model << 16 | flags << 24 | bdepth << 28, dlo | dspan << 16
+            const int nt = (a.x & XSEL_OWN_GAP) ? 4 : (int)((uint32_t)(e_m >> (a.x & 63u)) & 3u);          // :199-213
+            const uint32_t c0 = (uint32_t)(e_m >> ((a.x >> 8) & 63u)) & 3u, c1 = (uint32_t)(e_m >> ((a.x >> 16) & 63u)) & 3u;
+            double v = __ldg(A.xcpt + a.y + nt + c0 * (a.z & 0xffffu) + c1 * (a.z >> 16));
+            if (v == CUDART_INF) v = g;                               // GC-sentinel row (:217-218)
+            const uint32_t fl = b.x;
+            const int bdepth = fl >> 28;
+            if (fl & (RMD_F_RESTORE << 24)) { const double2 sv = e_stk[bdepth]; e_pm = sv.x; e_pr = sv.y; }
+            const bool apart = (uint32_t)(d - (int)(short)(b.y & 0xffffu)) >= (b.y >> 16);   // :184-192 as one interval test
+            e_pm = __dadd_rn(e_pm, v);                                // :227-228
+            e_pr = __dadd_rn(e_pr, g);
+            const bool alive = apart && e_pm >= __dadd_rn(e_pr, A.cutoff);             // :248
+            if (alive && (fl & (RMD_F_LEAF << 24)) && e_pm > e_bpm) { e_bpm = e_pm; e_leaf = (int)(fl & 0xffffu); }   // :265-275
+            if (alive && (fl & (RMD_F_SAVE << 24))) e_stk[bdepth + 1] = make_double2(e_pm, e_pr);
+            e_t = alive ? (a.w >> 16) : (a.w & 0xffffu);
+            if (e_t == XNODE_END) {                                   // the walk is over
+                if (e_leaf < 0) {                     // no solution: score 0 in every class, the weights follow from the counts
+                    const unsigned long long lo1 = bits & 0x5555555555555555ULL, hi1 = (bits >> 1) & 0x5555555555555555ULL;
+                    const int n_c = __popcll(lo1 & ~hi1), n_g = __popcll(hi1 & ~lo1), n_a = L - n_c - n_g - __popcll(lo1 & hi1);
+                    const int cell = (n_a * NP + n_c) * NP + n_g;
+                    if (SMEM_CELLS) atomicAdd(&cal_cells[cell], 1u);
+                    else atomicAdd(A.cells + cell, 1u);
+                } else {
+                    calib_set_aside(A, M, bits, e_leaf, e_bpm, L, L0, n_cells);
+                }
             }
         }
-        A.ok[atomicAdd(A.cells + n_cells, 1u)] = rec;
     }
     __syncthreads();
     if (SMEM_CELLS)
@@ -184,12 +284,17 @@ __global__ void __launch_bounds__(256) calib_cells_kernel(const CalibArgs A) {
     const int i = blockIdx.x, NP = A.L + 1;
     const double *tb = A.wtab + (long long)i * 3 * NP;
     double sum = 0.0;
-    for (int k = threadIdx.x; k < NP * NP * NP; k += 256) {
-        const uint32_t cnt = A.cells[k];
-        if (cnt) {
-            const int g = k % NP, c = (k / NP) % NP, a = k / (NP * NP);
-            sum += (double)cnt * (__ldg(tb + a) * __ldg(tb + NP + c) * __ldg(tb + 2 * NP + g));
-        }
+    const int n_cells = NP * NP * NP;
+    for (int k0 = threadIdx.x; k0 < n_cells; k0 += 4 * 256) {       // four counts in flight per thread (most cells are empty)
+        uint32_t cnt[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) cnt[u] = k0 + u * 256 < n_cells ? __ldg(A.cells + k0 + u * 256) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (cnt[u]) {
+                const int k = k0 + u * 256, g = k % NP, c = (k / NP) % NP, a = k / (NP * NP);
+                sum += (double)cnt[u] * (__ldg(tb + a) * __ldg(tb + NP + c) * __ldg(tb + 2 * NP + g));
+            }
     }
     for (int o = 16; o; o >>= 1) sum += __shfl_down_sync(FULL_MASK, sum, o);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;

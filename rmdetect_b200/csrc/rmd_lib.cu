@@ -1356,8 +1356,17 @@ extern "C" int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed
     RESERVE(ctx->d_calok, sizeof(CalibOk) * (size_t)n);              // every sample of the batch may have a solution
     A.ok = (CalibOk *)ctx->d_calok.p;
     CK(cudaMemsetAsync(A.cells, 0, sizeof(uint32_t) * ((size_t)(A.L + 1) * (A.L + 1) * (A.L + 1) + 1), st));
-    if (ctx->cal_smem) calibrate_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
-    else calibrate_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+    // the scoring engine's node format holds the model set (chains up to 16 letters) and the root passes its own test
+    // (lib/node.py:248: 0.0 >= 0.0 + cutoff): lane-level walks; else one sample per thread through eval_placement
+    const bool engine = ctx->motif_ok && ctx->hmodels[A.model].n_tree > 0 && 0.0 >= 0.0 + A.cutoff && !tune_env("RMD_CAL_NO_ENGINE");
+    A.xnodes = (const XNode *)ctx->d_xnodes.p; A.xcpt = (const double *)ctx->d_xcpt.p;
+    if (engine) {
+        if (ctx->cal_smem) calibrate_engine_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
+        else calibrate_engine_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+    } else {
+        if (ctx->cal_smem) calibrate_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
+        else calibrate_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+    }
     calib_ok_kernel<<<(unsigned)std::min<long long>((n * A.n_class + 255) / 256, (long long)ctx->sm_count * 8), 256, 0, st>>>(A);
     calib_cells_kernel<<<(unsigned)A.n_class, 256, 0, st>>>(A);
     CK(cudaEventRecord(ctx->ev[1], st));

@@ -108,6 +108,81 @@ def test_device_drawn_calibration_samples_against_the_oracle(name):
     assert np.allclose(dev, want, rtol=1e-9, atol=0)
 
 
+LONG_MODEL = """NAME    LONG 1.0
+%(nodes)s
+PROB    0   *   GC
+PROB    1   *   A:0.30          G:0.70
+PROB    2   *   A:0.55  C:0.15  G:0.15  U:0.15
+PROB    3   *   GC
+PROB    4   *   GC
+PROB    5   *   A:0.25  C:0.25  G:0.25  U:0.25
+PROB    6   *   GC
+PROB    7   *           C:0.50          U:0.50
+PROB    8   *   GC
+PROB    9   *   GC
+PROB    10  *   GC
+PROB    11  *   A:0.40  C:0.10  G:0.40  U:0.10
+PROB    12  *   GC
+PROB    13  *   GC
+PROB    14  *   GC
+PROB    15  *   GC
+PROB    16  *   GC
+PROB    17  A                           U:1.00
+PROB    17  C                   G:1.00
+PROB    17  G           C:0.60          U:0.40
+PROB    17  U   A:0.60          G:0.40
+PROB    18  *                   G:0.80  U:0.20
+PROB    19  *   A:1.00
+PROB    20  A                           U:1.00
+PROB    20  C                   G:1.00
+PROB    20  G           C:0.60          U:0.40
+PROB    20  U   A:0.60          G:0.40
+
+PAIRS   0   20  MUST
+PAIRS   16  17  MUST
+
+NO_PAIRING  1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 18 19
+
+ORDER   %(order)s
+
+SEPARATION  3   -
+"""
+
+
+def test_calibration_of_a_model_the_engine_cannot_hold(tmp_path):
+    """A chain of 17 letters does not fit the scoring engine's 16-letter words: calibration walks the tree through
+    eval_placement, one sample per thread, and (21 positions) counts the letter compositions in global memory.  Also a
+    cutoff that fails the root's own test (lib/node.py:248): nobody has a solution, every weight goes to bucket 0.  Both
+    against the oracle: same buckets, weights to 1e-9."""
+    from oracle import pyoracle
+    from rmdetect_b200.calibrate import N_BINS, class_logs
+    from rmdetect_b200.gcx import GC
+    from rmdetect_b200.modelfile import parse_model
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import synth_calibration_samples
+    nodes = ["NODE    %d   0   %d   -" % (k, k) for k in range(17)]
+    nodes += ["NODE    17  1   0   16", "NODE    18  1   1   -", "NODE    19  1   2   -", "NODE    20  1   3   0"]
+    path = tmp_path / "long_1.model"
+    path.write_text(LONG_MODEL % dict(nodes="\n".join(nodes), order=" ".join(str(k) for k in range(21))))
+    classes = GC.get_classes(5, 15, 85)
+    cl = class_logs(classes)
+    for m, cutoff, n in ((parse_model(str(path)), LN_CUTOFF, 6000), (load_model("KT_1.0"), 0.25, 3000)):
+        L = len(m.nodes)
+        samples = synth_calibration_samples(7, 1000, n, L)
+        eng = ScanEngine([m], [None], LN_UNKNOWN)
+        dev = np.zeros((len(classes), N_BINS))
+        ok_d, _ = eng.ctx.calibrate(0, None, cl, cutoff, dev, seed=7, first=1000, n=n, L=L)
+        host = np.zeros_like(dev)
+        ok_h, _ = eng.ctx.calibrate(0, samples, cl, cutoff, host)
+        eng.close()
+        want, ok_o = pyoracle.calibrate(pyoracle.OracleModel(m), ["".join("ACGU"[c] for c in row) for row in samples], classes,
+                                        LN_UNKNOWN, cutoff, N_BINS)
+        assert ok_d == ok_h == ok_o and (ok_o > 0) == (cutoff < 0)
+        assert np.array_equal(dev != 0, host != 0) and np.allclose(dev, host, rtol=1e-12, atol=0)
+        assert np.array_equal(dev != 0, want != 0)
+        assert np.allclose(dev, want, rtol=1e-9, atol=0)
+
+
 def test_calibration_loop_on_the_gpu_writes_the_reference_file(tmp_path):
     """calibrate_model end to end on the device (seeded reference sample stream, checkpoints, stop rule)."""
     from rmdetect_b200.calibrate import calibrate_model
