@@ -203,13 +203,14 @@ int rmd_eval(rmd_ctx *ctx, int model, const uint8_t *codes, const int64_t *seq_o
              const int32_t *p0, const int32_t *p1, int64_t n, double cutoff,
              int32_t *leaf, double *prob_model, double *prob_rand);
 
-/* calibration: samples[n][L] codes 0..3, class_log[n_class][4] = log(gc_i[letter]) in ACGU order,
-   hist[n_class][n_bins] is accumulated into (+=).  Returns via n_ok the samples whose eval held. */
+/* calibration: samples[n][L] codes 0..3, class_log[n_class][4] = log(gc_i[letter]) in ACGU order (finite: every
+   frequency positive, as the reference's math.log demands), hist[n_class][n_bins] is accumulated into (+=).
+   Returns via n_ok the samples whose eval held. */
 int rmd_calibrate(rmd_ctx *ctx, int model, const uint8_t *samples, int64_t n, int32_t L,
                   const double *class_log, int32_t n_class, double cutoff,
                   double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel);
-/* same with samples drawn on the device: letter j of sample s = top two bits of
-   mix64(seed + GOLDEN * (s * L + j + 1)), s in [first, first + n) */
+/* same with samples drawn on the device: sample s = the low 2L bits of mix64(seed + GOLDEN * (s + 1)), letter j its
+   bits 2j and 2j + 1, s in [first, first + n) (host twin: rmdetect_b200/synth.py synth_calibration_samples) */
 int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64_t first, int64_t n, int32_t L,
                         const double *class_log, int32_t n_class, double cutoff,
                         double *hist, int32_t n_bins, int64_t *n_ok, int32_t *overflow, float *ms_kernel);
@@ -221,7 +222,8 @@ int rmd_calibrate_synth(rmd_ctx *ctx, int model, uint64_t seed, int64_t first, i
    the histogram's device address (n_class * n_bins doubles), so that the GPUs of one job can all-reduce it in place
    (the one collective of the calibration path); rmd_calib_read downloads histogram (may be NULL),
    the number of samples whose eval held, the overflow flag and the device time of the batches since the last read.
-   rmd_calibrate / rmd_calibrate_synth / rmd_eval end an open session. */
+   rmd_calibrate / rmd_calibrate_synth end an open session (they are sessions of one batch); the session's buffers are
+   its own, other calls on the context leave it alone. */
 int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *class_log, int32_t n_class, double cutoff, int32_t n_bins);
 int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n);
 int rmd_calib_device_hist(rmd_ctx *ctx, void **dptr, int64_t *n_doubles);

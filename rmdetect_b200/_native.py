@@ -323,8 +323,12 @@ class Context:
         self._check(self.lib.rmd_calib_device_hist(self.h, C.byref(p), C.byref(n)), "rmd_calib_device_hist")
         return p.value, n.value
 
-    def calib_read(self, want_hist=True):
-        hist = np.zeros(self._cal_shape, dtype=np.float64) if want_hist else None
+    def calib_read(self, want_hist=True, out=None):
+        """(histogram, n_ok, device ms).  `out`: a float64 array of the session's shape that receives the histogram (a caller
+        that reads after every block keeps one buffer instead of mapping 676 KB of fresh pages per call)."""
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == self._cal_shape
+        hist = (out if out is not None else np.zeros(self._cal_shape, dtype=np.float64)) if want_hist else None
         n_ok, ovf, ms = C.c_int64(0), C.c_int32(0), C.c_float(0)
         self._check(self.lib.rmd_calib_read(self.h, _ptr(hist), C.byref(n_ok), C.byref(ovf), C.byref(ms)), "rmd_calib_read")
         if ovf.value:

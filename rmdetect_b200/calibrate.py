@@ -188,6 +188,7 @@ class Calibrator:
         self.hist = np.zeros((len(self.classes), N_BINS), dtype=np.float64)
         self.ms_kernel = 0.0
         self.n_ok = 0
+        self._pinned = None
         self.ctx.calib_open(self.model_index, self.L, self.class_log, self.cutoff, N_BINS)
 
     def add_samples(self, samples):
@@ -204,9 +205,13 @@ class Calibrator:
             ptr, n = self.ctx.calib_device_hist()                  # waits for the enqueued batches
             t = torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", self.ctx.device)).clone()
             dist.all_reduce(t)
-            self.hist = t.cpu().numpy().reshape(self.hist.shape)
+            if self._pinned is None:                               # one pinned landing buffer for every checkpoint
+                self._pinned = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            self._pinned.copy_(t)                                  # synchronous for the host
+            self.hist = self._pinned.numpy().reshape(self.hist.shape)
         else:
-            local, self.n_ok, ms = self.ctx.calib_read()
+            # self.hist is the landing buffer of every checkpoint (the table built from the previous one is a copy)
+            local, self.n_ok, ms = self.ctx.calib_read(out=self.hist)
             self.ms_kernel += ms
             self.hist = all_reduce_hist(local, dist)
         return self.hist
