@@ -183,6 +183,37 @@ def test_calibration_of_a_model_the_engine_cannot_hold(tmp_path):
         assert np.allclose(dev, want, rtol=1e-9, atol=0)
 
 
+def test_calibration_of_every_model_of_one_context_with_other_cutoffs():
+    """All shipped models resident in one context (the engine's nodes and tables are concatenated: a model's walk starts at
+    its own first node), each calibrated with a cutoff of its own — 1e-12 lets a quarter of the samples reach a leaf (the list
+    of solved samples is the main path then), 0.5 almost none: buckets and weights of the oracle."""
+    from oracle import pyoracle
+    from helpers import MODEL_FILES
+    from rmdetect_b200.calibrate import N_BINS, class_logs
+    from rmdetect_b200.gcx import GC
+    from rmdetect_b200.scanner import ScanEngine
+    from rmdetect_b200.synth import synth_calibration_samples
+    names = sorted(MODEL_FILES)
+    models = [load_model(n) for n in names]
+    classes = GC.get_classes(5, 15, 85)
+    cl = class_logs(classes)
+    eng = ScanEngine(models, [None] * len(models), LN_UNKNOWN)
+    solved = []
+    for mi, (m, c) in enumerate(zip(models, [1e-8, 0.5, 1e-6, 0.1, 1e-12])):
+        cutoff, L, n = math.log(c), len(m.nodes), 12000
+        dev = np.zeros((len(classes), N_BINS))
+        ok_d, _ = eng.ctx.calibrate(mi, None, cl, cutoff, dev, seed=99 + mi, first=5 * mi, n=n, L=L)
+        samples = synth_calibration_samples(99 + mi, 5 * mi, n, L)
+        want, ok_o = pyoracle.calibrate(pyoracle.OracleModel(m), ["".join("ACGU"[c] for c in row) for row in samples], classes,
+                                        LN_UNKNOWN, cutoff, N_BINS)
+        assert ok_d == ok_o, (names[mi], ok_d, ok_o)
+        assert np.array_equal(dev != 0, want != 0), names[mi]
+        assert np.allclose(dev, want, rtol=1e-9, atol=0), names[mi]
+        solved.append(ok_o)
+    eng.close()
+    assert max(solved) > 1000 and min(solved) < 100, solved
+
+
 def test_calibration_loop_on_the_gpu_writes_the_reference_file(tmp_path):
     """calibrate_model end to end on the device (seeded reference sample stream, checkpoints, stop rule)."""
     from rmdetect_b200.calibrate import calibrate_model
