@@ -228,6 +228,12 @@ int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *class_log, 
 int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n);
 int rmd_calib_device_hist(rmd_ctx *ctx, void **dptr, int64_t *n_doubles);
 int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t *overflow, float *ms_device);
+/* rows [first_class, first_class + n_rows) of the session's histogram after the batches enqueued so far — the stop rule of
+   rmcalibrate.py:241-257 reads one class (the middle one), so a checkpoint that does not save the table moves 4 KB
+   instead of 676 KB; `dptr` (may be NULL) receives the device address of the first of those rows; `cols` (may be NULL)
+   the first and the last bucket that is occupied in any class (-1, -1: none) — the score rows of the table run from one
+   to the other (rmcalibrate.py:65-83) */
+int rmd_calib_read_rows(rmd_ctx *ctx, int32_t first_class, int32_t n_rows, double *rows, void **dptr, int32_t *cols);
 
 /* rmbuild's CPT estimation (lib/bayes.py:69-150 JointProb counting, driven by lib/model.py:100-137 from rmbuild.py:343-352):
    rows of an alignment, one letter code (< K) per model node and row.  For every table t = (node column, parent column 0,

@@ -64,7 +64,7 @@ CL_MAX_PAIRS = 16
 
 EXPORTS = ["rmd_create", "rmd_destroy", "rmd_last_error", "rmd_version", "rmd_set_models", "rmd_set_evalues",
            "rmd_upload", "rmd_gc_counts", "rmd_set_gc", "rmd_set_return_dropped", "rmd_set_min_score", "rmd_set_hit_format", "rmd_set_screen_policy", "rmd_scan_resident", "rmd_scan", "rmd_eval",
-           "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_cpt_counts", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
+           "rmd_calibrate", "rmd_calibrate_synth", "rmd_calib_open", "rmd_calib_add", "rmd_calib_device_hist", "rmd_calib_read", "rmd_calib_read_rows", "rmd_cpt_counts", "rmd_synth_job", "rmd_synth_strand", "rmd_synth_counts", "rmd_download_codes", "rmd_download_bpp",
            "rmd_download_job", "rmd_compact_bpp", "rmd_parse_dot_ps", "rmd_host_alloc", "rmd_host_free",
            "rmd_table_clear", "rmd_table_rows", "rmd_table_append_scan", "rmd_table_append_rows", "rmd_table_download",
            "rmd_table_filter", "rmd_table_sort", "rmd_table_is_sorted", "rmd_table_top", "rmd_table_nooverlap", "rmd_table_cluster_index",
@@ -109,6 +109,7 @@ def load_library():
     L.rmd_calib_add.argtypes = [vp, vp, C.c_uint64, i64, i64]
     L.rmd_calib_device_hist.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.rmd_calib_read.argtypes = [vp, vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.rmd_calib_read_rows.argtypes = [vp, i32, i32, vp, C.POINTER(vp), C.POINTER(i32)]
     L.rmd_cpt_counts.argtypes = [vp, vp, i64, i32, i32, vp, i32, vp, i32, vp, vp]
     L.rmd_synth_job.argtypes = [vp, i64, i64, C.c_uint64, C.c_uint64, i32, i32, f64, f64, vp, vp,
                                 C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
@@ -334,6 +335,14 @@ class Context:
         if ovf.value:
             raise NativeError("calibration score beyond the histogram range (%d bins)" % self._cal_shape[1])
         return hist, n_ok.value, ms.value
+
+    def calib_read_rows(self, first_class, n_rows, want_rows=True):
+        """(rows [n_rows][n_bins] of the session's histogram or None, device address of the first row, (first, last) bucket
+        occupied in any class) after the enqueued batches."""
+        rows = np.empty((n_rows, self._cal_shape[1]), dtype=np.float64) if want_rows else None
+        p, cols = C.c_void_p(), (C.c_int32 * 2)()
+        self._check(self.lib.rmd_calib_read_rows(self.h, first_class, n_rows, _ptr(rows), C.byref(p), cols), "rmd_calib_read_rows")
+        return rows, p.value, (cols[0], cols[1])
 
     def cpt_counts(self, letters, K, tables, run, n_runs):
         """(counts [n_runs][n_tables][K^3] uint32, first_row [n_tables][K^3] int32) — include/rmdetect_b200.h: rmd_cpt_counts."""

@@ -94,26 +94,29 @@ def diff_gc_evalues(gce1, gce2, scores):
     return diff / atotal
 
 
-def score_grid(hist):
+def score_grid(hist, cols=None):
     """The score rows `get_gc_evalues` walks (rmcalibrate.py:65-83) for a dense [class][bucket] histogram: from the
     smallest to the largest occupied bucket in repeated `+= 0.1` steps, each rounded for use as a key — the float
     accumulation (and with it a possibly missing last row) is the reference's."""
-    cols = np.flatnonzero(hist.any(axis=0))
-    if len(cols) == 0:
+    if cols is None:
+        occupied = np.flatnonzero(hist.any(axis=0))
+        cols = (int(occupied[0]), int(occupied[-1])) if len(occupied) else (-1, -1)
+    if cols[1] < 0:
         return []
-    score, score_max, scores = round(int(cols[0]) / 10.0, 1), round(int(cols[-1]) / 10.0, 1), []
+    score, score_max, scores = round(int(cols[0]) / 10.0, 1), round(int(cols[1]) / 10.0, 1), []
     while score <= score_max:
         scores.append(round(score, 1))
         score += 0.1
     return scores
 
 
-def gc_evalues_dense(hist, evalue_min, classes=None):
+def gc_evalues_dense(hist, evalue_min, classes=None, cols=None):
     """`gc_evalues` on the dense histogram: (table [class][row], scores); `classes` restricts the table to those rows
-    of the histogram (the score grid still spans all of them).  Same additions in the same order (a
+    of the histogram (the score grid still spans all of them); `cols` = (first, last) occupied bucket of the WHOLE
+    histogram when `hist` holds only some of its rows.  Same additions in the same order (a
     sequential cumulative sum from the highest score down, floored at `evalue_min`; after the first row the floor
     never binds because every term is >= 0), so the values equal the dict version's bit for bit."""
-    scores = score_grid(hist)
+    scores = score_grid(hist, cols)
     idx = np.array([int(round(s * 10)) for s in scores], dtype=np.int64)
     sub = hist if classes is None else hist[list(classes)]
     count = np.array([float(sum(row[np.flatnonzero(row)].tolist())) for row in sub])      # Python's own sum(), like :85
@@ -216,6 +219,23 @@ class Calibrator:
             self.hist = all_reduce_hist(local, dist)
         return self.hist
 
+    def reduced_row(self, cls, dist=None):
+        """(row [1][N_BINS] of class `cls`, (first, last) occupied bucket over all classes) of the histogram of everything
+        added so far, summed over the ranks of `dist`: what the stop rule reads (rmcalibrate.py:241-257) and what spans the
+        table's score rows (:65-83) — 4 KB per checkpoint instead of the whole table."""
+        world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        nccl = world > 1 and dist.get_backend() == "nccl"
+        if nccl:
+            import torch
+            _, ptr, cols = self.ctx.calib_read_rows(cls, 1, want_rows=False)     # waits for the enqueued batches
+            t = torch.as_tensor(_DeviceArray(ptr, N_BINS), device=torch.device("cuda", self.ctx.device)).clone()
+            dist.all_reduce(t)
+            row = t.cpu().numpy().reshape(1, N_BINS)
+        else:
+            rows, _, cols = self.ctx.calib_read_rows(cls, 1)
+            row = all_reduce_hist(rows, dist)
+        return row, all_reduce_cols(cols, dist)
+
     def table(self):
         return gc_evalues(hist_dicts(self.reduced_hist()), 1.0 / float(4 ** self.L))
 
@@ -238,6 +258,20 @@ def all_reduce_hist(block, dist):
         t = t.cuda()
     dist.all_reduce(t)
     return t.cpu().numpy() if nccl else t.numpy()
+
+
+def all_reduce_cols(cols, dist):
+    """(first, last) occupied bucket over the ranks: the union of their occupied buckets; -1 marks an empty histogram."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return cols
+    import torch
+    first, last = cols
+    t = torch.tensor([-first if first >= 0 else -(1 << 30), last], dtype=torch.int64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    first, last = int(-t[0]), int(t[1])
+    return (first, last) if last >= 0 else (-1, -1)
 
 
 def calibrate_model(model, out_file, samples=1000000, unknown_prob=math.log(0.0001), cutoff=math.log(0.1),
@@ -276,13 +310,16 @@ def calibrate_model(model, out_file, samples=1000000, unknown_prob=math.log(0.00
     while done < total:
         # every block the reference recomputes the table, saves it and tests convergence (:237-263)
         if done > 0:
-            hist = cal.reduced_hist(dist)
             if save_every_block:
+                hist = cal.reduced_hist(dist)
                 tab, scores = gc_evalues_dense(hist, evalue_min)
                 save(tab, scores)
                 tab_mid = tab[mid:mid + 1]
+            elif hasattr(cal, "reduced_row"):         # only the class the stop rule reads crosses the bus
+                row, cols = cal.reduced_row(mid, dist)
+                tab_mid, scores = gc_evalues_dense(row, evalue_min, cols=cols)
             else:
-                tab_mid, scores = gc_evalues_dense(hist, evalue_min, classes=[mid])
+                tab_mid, scores = gc_evalues_dense(cal.reduced_hist(dist), evalue_min, classes=[mid])
             diff = 0.0
             if last is not None:
                 diff = diff_dense(last[0], last[1], tab_mid, scores, gc=0)

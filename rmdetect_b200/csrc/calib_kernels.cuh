@@ -305,3 +305,12 @@ __global__ void __launch_bounds__(256) calib_cells_kernel(const CalibArgs A) {
         if (t != 0.0) A.hist[(long long)i * A.n_bins] += t;       // one CTA per class, after calibrate_kernel on the same stream
     }
 }
+
+// first and last bucket occupied in any class: out[0] = min, out[1] = max (preset to n_bins and -1)
+__global__ void __launch_bounds__(256) calib_cols_kernel(const double *hist, const int n_class, const int n_bins, int *out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bins) return;
+    bool any = false;
+    for (int i = 0; i < n_class && !any; i++) any = hist[(long long)i * n_bins + b] != 0.0;
+    if (any) { atomicMin(out, b); atomicMax(out + 1, b); }
+}

@@ -1403,6 +1403,28 @@ extern "C" int rmd_calib_read(rmd_ctx *ctx, double *hist, int64_t *n_ok, int32_t
     return RMD_OK;
 }
 
+extern "C" int rmd_calib_read_rows(rmd_ctx *ctx, int32_t first_class, int32_t n_rows, double *rows, void **dptr, int32_t *cols) {
+    if (!ctx || !ctx->cal_open) return fail(ctx, RMD_E_STATE, "rmd_calib_read_rows: no open calibration session");
+    if (first_class < 0 || n_rows < 1 || first_class + n_rows > ctx->cal.n_class) return fail(ctx, RMD_E_INVALID, "rmd_calib_read_rows: classes %d..%d of %d", first_class, first_class + n_rows, ctx->cal.n_class);
+    std::lock_guard<std::recursive_mutex> lock_(g_dev_mutex[ctx->device]);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const double *src = ctx->cal.hist + (size_t)first_class * ctx->cal.n_bins;
+    int range[2] = {ctx->cal.n_bins, -1};
+    int *d_range = (int *)((char *)ctx->d_calcnt.p + 16);          // behind n_ok and the overflow flag
+    if (cols) {
+        CK(cudaMemcpyAsync(d_range, range, sizeof range, cudaMemcpyHostToDevice, st));
+        calib_cols_kernel<<<(unsigned)((ctx->cal.n_bins + 255) / 256), 256, 0, st>>>(ctx->cal.hist, ctx->cal.n_class, ctx->cal.n_bins, d_range);
+        CK(cudaMemcpyAsync(range, d_range, sizeof range, cudaMemcpyDeviceToHost, st));
+    }
+    if (rows) CK(cudaMemcpyAsync(rows, src, sizeof(double) * (size_t)n_rows * ctx->cal.n_bins, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (dptr) *dptr = (void *)src;
+    if (cols) { cols[0] = range[1] < 0 ? -1 : range[0]; cols[1] = range[1]; }
+    return RMD_OK;
+}
+
 static int calibrate_once(rmd_ctx *ctx, int model, const uint8_t *samples, uint64_t seed, int64_t first, int64_t n, int32_t L,
                           const double *class_log, int32_t n_class, double cutoff, double *hist, int32_t n_bins,
                           int64_t *n_ok, int32_t *overflow, float *ms_kernel) {

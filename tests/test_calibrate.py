@@ -86,6 +86,56 @@ class OracleScorer:
         return self.add_samples(synth_calibration_samples(seed, first, n, self.L))
 
 
+class RowScorer(OracleScorer):
+    """The same with the one-row checkpoint read of calibrate.Calibrator.reduced_row (rmd_calib_read_rows)."""
+
+    def reduced_row(self, cls, dist=None):
+        occupied = np.flatnonzero(self.hist.any(axis=0))
+        cols = (int(occupied[0]), int(occupied[-1])) if len(occupied) else (-1, -1)
+        self.rows_read = getattr(self, "rows_read", 0) + 1
+        return cal.all_reduce_hist(self.hist[cls:cls + 1], dist), cal.all_reduce_cols(cols, dist)
+
+
+def _row_rank_main(rank, world, port, name, samples, seed, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        st = {}
+        tab, scores, done = cal.calibrate_model(load_model(name), None, samples=samples, seed=seed, log=None, dist=dist,
+                                                scorer=RowScorer(name), device_samples=True, save_every_block=False, stats=st)
+        np.save(os.path.join(out_dir, "rowtab_r%d.npy" % rank), tab)
+        np.save(os.path.join(out_dir, "rowdone_r%d.npy" % rank), np.array([done, st["blocks"]]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_checkpoints_that_read_one_row_decide_as_the_full_table_does(tmp_path):
+    """Throughput mode (save_every_block=False): a checkpoint reads the middle class's row and the occupied bucket range
+    instead of the whole histogram — same score rows, same diff, same stop, same final table; on one rank and on two."""
+    import torch.multiprocessing as mp
+    name, samples, seed = "TGA_1.0", 60000, 7
+    full, rows = OracleScorer(name), RowScorer(name)
+    tab_f, scores_f, done_f = cal.calibrate_model(load_model(name), None, samples=samples, seed=seed, log=None, scorer=full,
+                                                  device_samples=True, save_every_block=False)
+    tab_r, scores_r, done_r = cal.calibrate_model(load_model(name), None, samples=samples, seed=seed, log=None, scorer=rows,
+                                                  device_samples=True, save_every_block=False)
+    assert rows.rows_read >= 5 and done_f == done_r and scores_f == scores_r and np.array_equal(tab_f, tab_r)
+    # the middle row's table from the row alone equals that row of the full table (the score grid spans every class)
+    h = full.hist
+    mid = h.shape[0] // 2
+    occupied = np.flatnonzero(h.any(axis=0))
+    t_row, s_row = cal.gc_evalues_dense(h[mid:mid + 1], 4.0 ** -8, cols=(int(occupied[0]), int(occupied[-1])))
+    t_all, s_all = cal.gc_evalues_dense(h, 4.0 ** -8)
+    assert s_row == s_all and np.array_equal(t_row[0], t_all[mid])
+    assert np.flatnonzero(h[mid])[-1] < occupied[-1]                # ... which the row by itself would not tell
+    port = 29500 + random.Random(os.getpid() + 17).randrange(2000)
+    mp.spawn(_row_rank_main, args=(2, port, name, samples, seed, str(tmp_path)), nprocs=2, join=True)
+    t0, t1 = np.load(tmp_path / "rowtab_r0.npy"), np.load(tmp_path / "rowtab_r1.npy")
+    assert np.array_equal(t0, t1) and np.allclose(t0, tab_f, rtol=1e-12, atol=0)
+    assert np.array_equal(np.load(tmp_path / "rowdone_r0.npy"), np.load(tmp_path / "rowdone_r1.npy"))
+
+
 @pytest.mark.parametrize("name", ["KT_1.0", "TGA_1.0"])
 def test_calibration_loop_writes_the_reference_file(name, tmp_path):
     """calibrate_model with the reference's seeded sample stream: checkpoints every 10 000 samples, the stop rule,

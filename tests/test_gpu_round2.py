@@ -214,6 +214,26 @@ def test_calibration_of_every_model_of_one_context_with_other_cutoffs():
     assert max(solved) > 1000 and min(solved) < 100, solved
 
 
+def test_one_row_checkpoint_read_equals_the_histogram():
+    """rmd_calib_read_rows: the middle class's row and the occupied bucket range of a device-resident session equal those of
+    the downloaded histogram, batch after batch."""
+    from rmdetect_b200.calibrate import Calibrator
+    m = load_model("GB_1.0")
+    c = Calibrator(m, LN_UNKNOWN, LN_CUTOFF)
+    mid = len(c.classes) // 2
+    for k in range(3):
+        c.add_synthetic(11, 20000 * k, 20000)
+        row, cols = c.reduced_row(mid)
+        rows2, _, _ = c.ctx.calib_read_rows(3, 4)
+        h = c.reduced_hist().copy()
+        occupied = np.flatnonzero(h.any(axis=0))
+        assert cols == (int(occupied[0]), int(occupied[-1]))
+        assert np.array_equal(row[0], h[mid]) and np.array_equal(rows2, h[3:7])
+    with pytest.raises(Exception):
+        c.ctx.calib_read_rows(len(c.classes) - 1, 2)
+    c.close()
+
+
 def test_calibration_loop_on_the_gpu_writes_the_reference_file(tmp_path):
     """calibrate_model end to end on the device (seeded reference sample stream, checkpoints, stop rule)."""
     from rmdetect_b200.calibrate import calibrate_model
