@@ -306,11 +306,13 @@ __global__ void __launch_bounds__(256) calib_cells_kernel(const CalibArgs A) {
     }
 }
 
-// first and last bucket occupied in any class: out[0] = min, out[1] = max (preset to n_bins and -1)
+// first and last bucket occupied in any class: out[0] = min, out[1] = max (preset to n_bins and -1); one CTA per class
 __global__ void __launch_bounds__(256) calib_cols_kernel(const double *hist, const int n_class, const int n_bins, int *out) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_bins) return;
-    bool any = false;
-    for (int i = 0; i < n_class && !any; i++) any = hist[(long long)i * n_bins + b] != 0.0;
-    if (any) { atomicMin(out, b); atomicMax(out + 1, b); }
+    const double *row = hist + (long long)blockIdx.x * n_bins;
+    int lo = n_bins, hi = -1;
+    for (int b = threadIdx.x; b < n_bins; b += 256)
+        if (row[b] != 0.0) { lo = min(lo, b); hi = max(hi, b); }
+    lo = __reduce_min_sync(FULL_MASK, lo);
+    hi = __reduce_max_sync(FULL_MASK, hi);
+    if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(out, lo); atomicMax(out + 1, hi); }
 }

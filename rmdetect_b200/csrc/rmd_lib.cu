@@ -1414,7 +1414,7 @@ extern "C" int rmd_calib_read_rows(rmd_ctx *ctx, int32_t first_class, int32_t n_
     int *d_range = (int *)((char *)ctx->d_calcnt.p + 16);          // behind n_ok and the overflow flag
     if (cols) {
         CK(cudaMemcpyAsync(d_range, range, sizeof range, cudaMemcpyHostToDevice, st));
-        calib_cols_kernel<<<(unsigned)((ctx->cal.n_bins + 255) / 256), 256, 0, st>>>(ctx->cal.hist, ctx->cal.n_class, ctx->cal.n_bins, d_range);
+        calib_cols_kernel<<<(unsigned)ctx->cal.n_class, 256, 0, st>>>(ctx->cal.hist, ctx->cal.n_class, ctx->cal.n_bins, d_range);
         CK(cudaMemcpyAsync(range, d_range, sizeof range, cudaMemcpyDeviceToHost, st));
     }
     if (rows) CK(cudaMemcpyAsync(rows, src, sizeof(double) * (size_t)n_rows * ctx->cal.n_bins, cudaMemcpyDeviceToHost, st));
