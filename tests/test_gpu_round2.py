@@ -46,6 +46,30 @@ def test_result_file_bytes_equal_the_reference(name, tmp_path):
     assert session.saves[0] == ("n", 0) and session.saves[-1][0] == "w"
 
 
+@pytest.mark.parametrize("name", ["lys_seq_both_all", "rnasel_stk_all", "arich_stk"])
+def test_result_file_from_the_input_file_without_a_reference_checkout(name, tmp_path):
+    """The standalone flow: the example input is read by rmdetect_b200.sequences.Sequences (strands,
+    gaps, column index, the header's sequence count), scanned, filtered, sorted and written — the bytes of the reference's
+    own result file."""
+    from rmdetect_b200.pipeline import ScanSession
+    from rmdetect_b200.scanner import Scanner
+    from rmdetect_b200.sequences import Sequences
+    from rmdetect_b200.synth import SynthFold
+    case = next(c for c in golden("res_files") if c["name"] == name)
+    here = os.path.dirname(os.path.abspath(__file__))
+    seqs = Sequences(fname=os.path.join(here, "golden", "ref_data", "examples", os.path.basename(case["seq_file"])),
+                     both_strands=case["both_strands"])
+    models, evs = fresh_models(case["models"])
+    sc = Scanner(Cfg(models, evs))
+    sc.rna_tools = SynthFold(case["seed"])
+    out = tmp_path / (name + ".res")
+    session = ScanSession(sc, seqs, str(out), min_score=5.0, min_bpp=0.001, seq_file=case["seq_file"])
+    cands, tries = session.run()
+    sc._engine.close()
+    assert tries == case["tries"] and session.n_sequences == case["n_sequences"]
+    assert out.read_text() == case["res"]
+
+
 def test_ten_megabases_against_the_oracle():
     """BASELINE configs[2]: 10 000 000 letters, 133 333 windows, 9.46e9 placements, four models."""
     from oracle import pyoracle
