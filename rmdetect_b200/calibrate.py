@@ -222,19 +222,30 @@ class Calibrator:
     def reduced_row(self, cls, dist=None):
         """(row [1][N_BINS] of class `cls`, (first, last) occupied bucket over all classes) of the histogram of everything
         added so far, summed over the ranks of `dist`: what the stop rule reads (rmcalibrate.py:241-257) and what spans the
-        table's score rows (:65-83) — 4 KB per checkpoint instead of the whole table."""
+        table's score rows (:65-83) — 4 KB per checkpoint instead of the whole table.  Over several ranks the bucket range
+        rides in the same all-reduce as the row: a 0/1 vector that is 1 from a rank's first to its last occupied bucket,
+        whose sum is non-zero exactly from the smallest first to the largest last."""
         world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
-        nccl = world > 1 and dist.get_backend() == "nccl"
-        if nccl:
+        if world == 1:
+            rows, _, cols = self.ctx.calib_read_rows(cls, 1)
+            return rows, cols
+        if dist.get_backend() == "nccl":
             import torch
             _, ptr, cols = self.ctx.calib_read_rows(cls, 1, want_rows=False)     # waits for the enqueued batches
-            t = torch.as_tensor(_DeviceArray(ptr, N_BINS), device=torch.device("cuda", self.ctx.device)).clone()
+            t = torch.zeros(2 * N_BINS, dtype=torch.float64, device=torch.device("cuda", self.ctx.device))
+            t[:N_BINS] = torch.as_tensor(_DeviceArray(ptr, N_BINS), device=t.device)
+            if cols[1] >= 0:
+                t[N_BINS + cols[0]:N_BINS + cols[1] + 1] = 1.0
             dist.all_reduce(t)
-            row = t.cpu().numpy().reshape(1, N_BINS)
+            both = t.cpu().numpy()
         else:
             rows, _, cols = self.ctx.calib_read_rows(cls, 1)
-            row = all_reduce_hist(rows, dist)
-        return row, all_reduce_cols(cols, dist)
+            both = np.zeros(2 * N_BINS)
+            both[:N_BINS] = rows[0]
+            if cols[1] >= 0:
+                both[N_BINS + cols[0]:N_BINS + cols[1] + 1] = 1.0
+            both = all_reduce_hist(both, dist)
+        return both[:N_BINS].reshape(1, N_BINS), span_of(both[N_BINS:])
 
     def table(self):
         return gc_evalues(hist_dicts(self.reduced_hist()), 1.0 / float(4 ** self.L))
@@ -258,6 +269,12 @@ def all_reduce_hist(block, dist):
         t = t.cuda()
     dist.all_reduce(t)
     return t.cpu().numpy() if nccl else t.numpy()
+
+
+def span_of(marks):
+    """(first, last) index of the non-zero entries; (-1, -1) when there is none."""
+    nz = np.flatnonzero(marks)
+    return (int(nz[0]), int(nz[-1])) if len(nz) else (-1, -1)
 
 
 def all_reduce_cols(cols, dist):
