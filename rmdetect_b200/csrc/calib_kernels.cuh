@@ -35,6 +35,9 @@
 #endif
 #define CAL_MAX_CLASS 256
 #define CAL_SPACER 6
+#ifndef CAL_PIECE
+#define CAL_PIECE (1LL << 22)           // samples per launch: rmd_calib_add cuts a larger batch into pieces
+#endif
 #define CAL_SMEM_L 20                   // samples up to 20 letters (every shipped model) count in shared memory: 21^3 cells, 37 KB
 
 struct CalibOk { unsigned long long bits, used; double pm; int n_used, pad; };   // sample, consumed letters (2 bits each), prob_model

@@ -1349,26 +1349,35 @@ extern "C" int rmd_calib_add(rmd_ctx *ctx, const uint8_t *samples, uint64_t seed
         CK(cudaMemcpyAsync(ctx->d_e0.p, samples, (size_t)n * A.L, cudaMemcpyHostToDevice, st));
         A.samples = (const uint8_t *)ctx->d_e0.p;
     }
-    A.n = n; A.first = first; A.seed = seed;
+    A.seed = seed;
     if (!ctx->cal_timed) { CK(cudaEventRecord(ctx->ev[0], st)); ctx->cal_timed = true; }
-    // persistent CTAs: the count histogram is flushed once per CTA
-    const unsigned grid = (unsigned)std::min<long long>((n + CAL_THREADS - 1) / CAL_THREADS, (long long)ctx->sm_count * CAL_CTAS_PER_SM);
-    RESERVE(ctx->d_calok, sizeof(CalibOk) * (size_t)n);              // every sample of the batch may have a solution
-    A.ok = (CalibOk *)ctx->d_calok.p;
-    CK(cudaMemsetAsync(A.cells, 0, sizeof(uint32_t) * ((size_t)(A.L + 1) * (A.L + 1) * (A.L + 1) + 1), st));
     // the scoring engine's node format holds the model set (chains up to 16 letters) and the root passes its own test
     // (lib/node.py:248: 0.0 >= 0.0 + cutoff): lane-level walks; else one sample per thread through eval_placement
     const bool engine = ctx->motif_ok && ctx->hmodels[A.model].n_tree > 0 && 0.0 >= 0.0 + A.cutoff && !tune_env("RMD_CAL_NO_ENGINE");
     A.xnodes = (const XNode *)ctx->d_xnodes.p; A.xcpt = (const double *)ctx->d_xcpt.p;
-    if (engine) {
-        if (ctx->cal_smem) calibrate_engine_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
-        else calibrate_engine_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
-    } else {
-        if (ctx->cal_smem) calibrate_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
-        else calibrate_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+    // a batch goes through in pieces of CAL_PIECE samples: the list of solved samples is sized for a piece (every sample
+    // of it may have a solution) and a count cell cannot overflow
+    const long long piece = std::min<long long>(n, CAL_PIECE);
+    RESERVE(ctx->d_calok, sizeof(CalibOk) * (size_t)piece);
+    A.ok = (CalibOk *)ctx->d_calok.p;
+    const uint8_t *const staged = A.samples;
+    for (long long c0 = 0; c0 < n; c0 += piece) {
+        const long long cn = std::min(piece, n - c0);
+        A.n = cn; A.first = first + c0;
+        if (staged) A.samples = staged + (size_t)c0 * A.L;
+        // persistent CTAs: the count histogram is flushed once per CTA
+        const unsigned grid = (unsigned)std::min<long long>((cn + CAL_THREADS - 1) / CAL_THREADS, (long long)ctx->sm_count * CAL_CTAS_PER_SM);
+        CK(cudaMemsetAsync(A.cells, 0, sizeof(uint32_t) * ((size_t)(A.L + 1) * (A.L + 1) * (A.L + 1) + 1), st));
+        if (engine) {
+            if (ctx->cal_smem) calibrate_engine_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
+            else calibrate_engine_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+        } else {
+            if (ctx->cal_smem) calibrate_kernel<true><<<grid, CAL_THREADS, ctx->cal_smem, st>>>(A);
+            else calibrate_kernel<false><<<grid, CAL_THREADS, 0, st>>>(A);
+        }
+        calib_ok_kernel<<<(unsigned)std::min<long long>((cn * A.n_class + 255) / 256, (long long)ctx->sm_count * 8), 256, 0, st>>>(A);
+        calib_cells_kernel<<<(unsigned)A.n_class, 256, 0, st>>>(A);
     }
-    calib_ok_kernel<<<(unsigned)std::min<long long>((n * A.n_class + 255) / 256, (long long)ctx->sm_count * 8), 256, 0, st>>>(A);
-    calib_cells_kernel<<<(unsigned)A.n_class, 256, 0, st>>>(A);
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaGetLastError());
     if (samples) CK(cudaStreamSynchronize(st));    // the caller's buffer may be reused on return
