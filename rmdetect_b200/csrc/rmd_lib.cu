@@ -117,6 +117,7 @@ struct rmd_ctx {
     bool compact_hits = false;          // rmd_set_hit_format
     DBuf d_pack;
     uint32_t *h_gate = nullptr, *h_group = nullptr;
+    double *h_calcls = nullptr;         // pinned: a session's class logs on their way to the device (CAL_MAX_CLASS x 4)
     double *h_calhist = nullptr;        // pinned: rmd_calibrate's download of a session's histogram
     size_t h_calhist_n = 0;
     unsigned int *h_ready = nullptr;    // pinned: progress marks of a streamed scan (windows whose lists have been copied)
@@ -223,6 +224,7 @@ extern "C" void rmd_destroy(rmd_ctx *ctx) {
     if (ctx->h_group) cudaFreeHost(ctx->h_group);
     if (ctx->h_ready) cudaFreeHost(ctx->h_ready);
     if (ctx->h_calhist) cudaFreeHost(ctx->h_calhist);
+    if (ctx->h_calcls) cudaFreeHost(ctx->h_calcls);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1317,11 +1319,14 @@ extern "C" int rmd_calib_open(rmd_ctx *ctx, int model, int32_t L, const double *
         CK(cudaMemcpy(ctx->d_calthr.p, thr.data(), sizeof(double) * n_bins, cudaMemcpyHostToDevice));
         ctx->cal_thr_bins = n_bins;
     }
-    CK(cudaMemcpyAsync(ctx->d_calcls.p, class_log, sizeof(double) * 4 * n_class, cudaMemcpyHostToDevice, st));
+    // the class logs leave through a pinned copy of the context's: no wait for the caller's buffer
+    if (!ctx->h_calcls) CK(cudaMallocHost((void **)&ctx->h_calcls, sizeof(double) * 4 * CAL_MAX_CLASS));
+    else CK(cudaStreamSynchronize(st));              // a previous session's copy may still be in flight (it never is after a read)
+    memcpy(ctx->h_calcls, class_log, sizeof(double) * 4 * n_class);
+    CK(cudaMemcpyAsync(ctx->d_calcls.p, ctx->h_calcls, sizeof(double) * 4 * n_class, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->d_calhist.p, 0, sizeof(double) * (size_t)n_class * n_bins, st));
     CK(cudaMemsetAsync(ctx->d_calcnt.p, 0, 64, st));
     calib_table_kernel<<<(unsigned)((n_class * 3 * (L + 1) + 255) / 256), 256, 0, st>>>((const double *)ctx->d_calcls.p, n_class, L, (double *)ctx->d_caltab.p);
-    CK(cudaStreamSynchronize(st));                 // the caller's class_log may be reused on return
     CK(cudaGetLastError());
     CalibArgs &A = ctx->cal;
     A.model = model; A.L = L; A.n_class = n_class; A.n_bins = n_bins; A.n = 0; A.first = 0;
@@ -1446,6 +1451,7 @@ static int calibrate_once(rmd_ctx *ctx, int model, const uint8_t *samples, uint6
     const size_t nh = (size_t)n_class * n_bins;
     if (ctx->h_calhist_n < nh) {                   // pinned staging: the download is a third of a short call
         if (ctx->h_calhist) cudaFreeHost(ctx->h_calhist);
+    if (ctx->h_calcls) cudaFreeHost(ctx->h_calcls);
         ctx->h_calhist = nullptr; ctx->h_calhist_n = 0;
         CK(cudaMallocHost((void **)&ctx->h_calhist, sizeof(double) * nh));
         ctx->h_calhist_n = nh;
