@@ -32,12 +32,48 @@ CONVERGED_DIFF = 0.001    # rmcalibrate.py:249
 CONVERGED_SAMPLES = 100000
 
 
-def draw_samples(n, L, seed=None):
-    """`n` samples of `L` letters as codes, consuming Python's RNG exactly like `draw_seq`."""
+def draw_samples_loop(n, L, seed=None):
+    """`n` samples of `L` letters as codes, letter by letter through `random.randint(0, 3)` as `draw_seq` does
+    (rmcalibrate.py:16-22): the definition that `draw_samples` reproduces."""
     if seed is not None:
         random.seed(seed)
     ri = random.randint
     return np.array([[ri(0, 3) for _ in range(L)] for _ in range(n)], dtype=np.uint8).reshape(n, L)
+
+
+def draw_samples(n, L, seed=None):
+    """`n` samples of `L` letters as codes, consuming Python's RNG exactly like `draw_seq` — without 16 million calls of
+    `random.randint` for a million samples (they took longer than everything else in a calibration run).
+
+    `randint(0, 3)` is `_randbelow(4)`: the top three bits of one 32-bit output of the Mersenne Twister, drawn again while
+    they are 4 or more.  The generator's state is handed to numpy's MT19937 (same algorithm, same state layout), the raw
+    outputs are taken in bulk, the rejected ones dropped, and the state after exactly the outputs consumed is handed back to
+    `random`, so that whatever draws next — the reference's own code included — continues the same stream."""
+    if seed is not None:
+        random.seed(seed)
+    need = int(n) * int(L)
+    if need == 0:
+        return np.zeros((n, L), dtype=np.uint8)
+    version, internal, gauss = random.getstate()
+    if version != 3 or len(internal) != 625:                      # an unknown generator layout: the plain loop
+        return draw_samples_loop(n, L)
+    start = {"bit_generator": "MT19937", "state": {"key": np.array(internal[:-1], dtype=np.uint32), "pos": int(internal[-1])}}
+    mt = np.random.MT19937()
+    mt.state = start
+    parts, have, used = [], 0, 0
+    while have < need:
+        raw = mt.random_raw(max(1024, int(2.1 * (need - have)) + 64))
+        v = (raw >> np.uint64(29)).astype(np.uint8)
+        ok = np.flatnonzero(v < 4)
+        take = min(len(ok), need - have)
+        parts.append(v[ok[:take]])
+        have += take
+        used += int(ok[take - 1]) + 1 if have == need else len(raw)
+    mt.state = start                                               # the state after exactly `used` outputs
+    mt.random_raw(used)
+    end = mt.state["state"]
+    random.setstate((version, tuple(int(x) for x in end["key"]) + (int(end["pos"]),), gauss))
+    return np.concatenate(parts).reshape(n, L)
 
 
 def class_logs(classes):

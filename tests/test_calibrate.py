@@ -61,6 +61,25 @@ def test_convergence_measure_equals_the_reference(name):
     assert cal.diff_dense(ta, sa_d, tb, sb_d) == g["diff"]
 
 
+@pytest.mark.parametrize("n,L,seed", [(1, 1, 0), (7, 16, 1), (1000, 20, 20261019), (10000, 8, 5), (0, 5, 1), (2500, 14, 123)])
+def test_bulk_sample_draw_is_the_randint_stream(n, L, seed):
+    """draw_samples takes the Mersenne Twister's outputs in bulk: the same letters as `random.randint(0, 3)` call by call
+    (rmcalibrate.py:16-22), and the generator is left in the same state, so later draws agree too."""
+    a = cal.draw_samples_loop(n, L, seed)
+    after_a = [random.random(), random.randint(0, 10 ** 9), random.getrandbits(70)]
+    b = cal.draw_samples(n, L, seed)
+    after_b = [random.random(), random.randint(0, 10 ** 9), random.getrandbits(70)]
+    assert a.shape == b.shape == (n, L) and b.dtype == np.uint8 and np.array_equal(a, b) and after_a == after_b
+
+
+def test_bulk_sample_draw_continues_a_stream_in_use():
+    random.seed(42)
+    x1 = cal.draw_samples_loop(500, 16); g1 = random.gauss(0, 1); y1 = cal.draw_samples_loop(300, 16); s1 = random.getstate()
+    random.seed(42)
+    x2 = cal.draw_samples(500, 16); g2 = random.gauss(0, 1); y2 = cal.draw_samples(300, 16); s2 = random.getstate()
+    assert np.array_equal(x1, x2) and g1 == g2 and np.array_equal(y1, y2) and s1 == s2
+
+
 class OracleScorer:
     """CPU stand-in for calibrate.Calibrator: the oracle's restatement of rmcalibrate.py:265-295."""
 
