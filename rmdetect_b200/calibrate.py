@@ -183,8 +183,20 @@ def diff_dense(tab1, scores1, tab2, scores2, gc=None):
 
 
 def table_text_dense(gc_classes, tab, scores):
-    """`table_text` for a dense table."""
-    return table_text(gc_classes, [dict(zip(scores, row.tolist())) for row in tab], scores)
+    """`table_text` for a dense table [class][row] — the same bytes, one format call per score row instead of one per
+    number (a checkpoint writes 165 x ~200 numbers; call by call that was two thirds of a checkpoint's time)."""
+    lines = ["[GC_CLASSES]\n"]
+    header = "#SCORES"
+    for i, gc in enumerate(gc_classes):
+        name = "GC_%04d" % i
+        header += "\t%10s" % name
+        lines.append(name + "".join("\t%s\t%.4f" % (k, v) for k, v in gc.items()) + "\n")
+    lines.append("[E_VALUES]\n%s\n" % header)
+    row_format = "%s" + "\t%10.3E" * len(gc_classes) + "\n"
+    cols = np.asarray(tab, dtype=np.float64).T.tolist()              # [row][class]
+    for s, values in zip(scores, cols):
+        lines.append(row_format % (s, *values))
+    return "".join(lines)
 
 
 def table_text(gc_classes, gc_evalue, scores):

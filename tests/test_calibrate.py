@@ -80,6 +80,21 @@ def test_bulk_sample_draw_continues_a_stream_in_use():
     assert np.array_equal(x1, x2) and g1 == g2 and np.array_equal(y1, y2) and s1 == s2
 
 
+def test_table_text_row_by_row_equals_number_by_number():
+    """table_text_dense formats a score row with one call; the bytes are those of the reference's number-by-number loop
+    (rmcalibrate.py:101-131), also for values that print with three-digit exponents and for a class without any hit."""
+    rng = np.random.default_rng(3)
+    h = np.zeros((165, cal.N_BINS))
+    h[:, :150] = rng.random((165, 150)) * 10.0 ** rng.integers(-300, 3, (165, 150))
+    h[7, :] = 0.0
+    h[7, 0] = 1.0
+    h[3, 170] = 1e-9
+    classes = GC.get_classes(5, 15, 85)
+    tab, scores = cal.gc_evalues_dense(h, 4.0 ** -16)
+    want = cal.table_text(classes, [dict(zip(scores, row.tolist())) for row in tab], scores)
+    assert cal.table_text_dense(classes, tab, scores) == want and len(scores) == 171
+
+
 class OracleScorer:
     """CPU stand-in for calibrate.Calibrator: the oracle's restatement of rmcalibrate.py:265-295."""
 
