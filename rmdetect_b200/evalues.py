@@ -38,21 +38,56 @@ class EValues:
         if last is not None and last[0] == key and last[1] is items:
             self.selected = last[2]
             return self.selected
+        # Which classes can be the minimum is settled in bulk (numpy, rounding differences of a few ulp); the reference's own
+        # arithmetic — same operations, same order, `** 2` through pow, strict '<' in class order — then decides among the
+        # classes within 1e-9 of the smallest distance, normally one.  Only the four `e ** gc[k]` are taken once per call
+        # instead of once per class (same function, same argument: same bits).
         power = {}
+        rows = range(len(items))
+        dense = self._class_dense(items)
+        if dense is not None:
+            letters, values, present = dense
+            e = np.array([math.e ** gc.get(k, 0) for k in letters], dtype=np.float64)
+            approx = np.sqrt((np.where(present, values - e, 0.0) ** 2).sum(axis=1))
+            if np.all(np.isfinite(approx)):
+                rows = np.flatnonzero(approx <= approx.min() * (1.0 + 1e-9) + 1e-300).tolist()
         min_d = None
-        for i, pairs in enumerate(items):
+        for i in rows:
             x = 0.0
-            for k, v in pairs:
-                e = power.get(k)
-                if e is None:
-                    e = power[k] = math.e ** gc.get(k, 0)
-                x += (v - e) ** 2
+            for k, v in items[i]:
+                e_k = power.get(k)
+                if e_k is None:
+                    e_k = power[k] = math.e ** gc.get(k, 0)
+                x += (v - e_k) ** 2
             d = math.sqrt(x)
             if min_d is None or d < min_d:
                 min_d = d
                 self.selected = i
         self._last_gc = (key, items, self.selected)
         return self.selected
+
+    def _class_dense(self, items):
+        """(letters, values [class][letter], present [class][letter]) of the classes, rebuilt when they change; None when
+        there is no class."""
+        cached = getattr(self, "_dense", None)
+        if cached is None or cached[0] is not items:
+            if not items:
+                return None
+            letters = []
+            for pairs in items:
+                for k, _ in pairs:
+                    if k not in letters:
+                        letters.append(k)
+            at = {k: n for n, k in enumerate(letters)}
+            values = np.zeros((len(items), len(letters)))
+            present = np.zeros((len(items), len(letters)), dtype=bool)
+            for i, pairs in enumerate(items):
+                for k, v in pairs:
+                    values[i, at[k]] = v
+                    present[i, at[k]] = True
+            cached = (items, (tuple(letters), values, present))
+            self._dense = cached
+        return cached[1]
 
     def _class_items(self):
         """gc_classes as a tuple of ((letter, value), ...) in dict order, rebuilt when the list changes."""

@@ -30,25 +30,26 @@ class CachedFold:
         return [self.coo(w) for w in wins]
 
 
-for name, models in (("lys.stk", ["CL_1.0", "TGA_1.0", "GB_1.0", "KT_1.0"]), ("rnaselci.stk", ["CL_1.0", "TGA_1.0", "GB_1.0", "KT_1.0"]),
-                     ("arich_test.stk", ["ARICH_1.0"])):
-    triples = golden("seqsets")[name]
-    ms, evs = fresh_models(models)
-    fold = CachedFold(SynthFold(7))
-    out = {}
-    for label, cap in (("one job per sequence", 1), ("one job per alignment", 1 << 19)):
-        sc = Scanner(Cfg(ms, evs))
-        sc.rna_tools = fold
-        sc.max_batch_windows = cap
-        sc.scan(SeqList(triples))                                  # warm-up: library load, model upload, provider cache
-        best = 1e9
-        for _ in range(5):
-            t0 = time.perf_counter()
-            cands, tries = sc.scan(SeqList(triples))
-            best = min(best, time.perf_counter() - t0)
-        out[label] = (best, len(cands), tries)
-        sc._engine.close()
-    (a, na, ta), (b, nb, tb) = out["one job per sequence"], out["one job per alignment"]
-    assert (na, ta) == (nb, tb)
-    print("%-16s %3d sequences, %d models: %7.2f ms one job per sequence -> %6.2f ms one job per alignment (%.1fx), %d hits, tries %s"
-          % (name, len(triples), len(models), 1e3 * a, 1e3 * b, a / b, na, ta))
+if __name__ == "__main__":
+    for name, models in (("lys.stk", ["CL_1.0", "TGA_1.0", "GB_1.0", "KT_1.0"]), ("rnaselci.stk", ["CL_1.0", "TGA_1.0", "GB_1.0", "KT_1.0"]),
+                         ("arich_test.stk", ["ARICH_1.0"])):
+        triples = golden("seqsets")[name]
+        ms, evs = fresh_models(models)
+        fold = CachedFold(SynthFold(7))
+        out = {}
+        for label, cap in (("one job per sequence", 1), ("one job per alignment", 1 << 19)):
+            sc = Scanner(Cfg(ms, evs))
+            sc.rna_tools = fold
+            sc.max_batch_windows = cap
+            sc.scan(SeqList(triples))                                  # warm-up: library load, model upload, provider cache
+            best = 1e9
+            for _ in range(5):
+                t0 = time.perf_counter()
+                cands, tries = sc.scan(SeqList(triples))
+                best = min(best, time.perf_counter() - t0)
+            out[label] = (best, len(cands), tries)
+            sc._engine.close()
+        (a, na, ta), (b, nb, tb) = out["one job per sequence"], out["one job per alignment"]
+        assert (na, ta) == (nb, tb)
+        print("%-16s %3d sequences, %d models: %7.2f ms one job per sequence -> %6.2f ms one job per alignment (%.1fx), %d hits, tries %s"
+              % (name, len(triples), len(models), 1e3 * a, 1e3 * b, a / b, na, ta))
