@@ -21,6 +21,9 @@ from fractions import Fraction
 import numpy as np
 
 
+_CLASS_SETS = {}                  # class lists seen so far -> id (EValues.class_set_id)
+
+
 class EValues:
     def __init__(self):
         self.gc_classes = []      # list of {letter: fraction}
@@ -93,9 +96,16 @@ class EValues:
         """gc_classes as a tuple of ((letter, value), ...) in dict order, rebuilt when the list changes."""
         cached = getattr(self, "_items", None)
         if cached is None or cached[0] is not self.gc_classes or cached[1] != len(self.gc_classes):
-            cached = (self.gc_classes, len(self.gc_classes), tuple(tuple(c.items()) for c in self.gc_classes))
+            items = tuple(tuple(c.items()) for c in self.gc_classes)
+            cached = (self.gc_classes, len(self.gc_classes), items, _CLASS_SETS.setdefault(items, len(_CLASS_SETS)))
             self._items = cached
         return cached[2]
+
+    def class_set_id(self):
+        """A small integer that is equal for tables calibrated on the same GC classes (same letters, values and order): what
+        decides whether two models select the same class for a sequence.  The deep comparison is made once per table."""
+        self._class_items()
+        return self._items[3]
 
     def compute(self, score):
         # reference lib/evalues.py:25-36 (host restatement, used by the drop-in API and tests)

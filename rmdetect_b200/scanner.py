@@ -116,7 +116,7 @@ class ScanEngine:
                     cls.append(-1)
                 else:
                     # models calibrated on the same GC classes (the shipped ones all are) select the same class
-                    items = ev._class_items() if hasattr(ev, "_class_items") else None
+                    items = ev.class_set_id() if hasattr(ev, "class_set_id") else None     # (a deep comparison once per table)
                     if items is not None and items in same:
                         ev.selected = same[items]
                     else:
