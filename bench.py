@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
 
 
 def cal_roofline(kernel_ms, samples, n_class):
-    """calibrate_kernel (csrc/calib_kernels.cuh): one tree walk per sample; the 165 weights per sample are not computed one
+    """calibrate_engine_kernel (csrc/calib_kernels.cuh): one tree walk per sample; the 165 weights per sample are not computed one
     by one (samples without a solution are counted by letter composition, their weights follow from 165 x 1771 products), so
     the kernel is bound by instruction issue in the tree walk.  The algorithmic work is counted in (sample, class) pairs, as
     the reference does it; the pipe figures come from the committed ncu capture of one launch of 2^20 samples
