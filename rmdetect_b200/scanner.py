@@ -81,6 +81,30 @@ class NoFoldProvider:
             "(the reference's lib.rnatools.RNATools, rmdetect_b200.fold.RNAfold, or synth.SynthFold)")
 
 
+def _checked_lists(lists, win_lens):
+    """The lists a provider's `coo_many` returned, in the kernel's form (bpprobs.to_coo): when every one is already a
+    (uint16, uint16, float64) triple, all windows are checked in one pass over the concatenation — strictly increasing upper
+    triangle inside its window, no zeros — instead of eight numpy calls per window; anything else goes through `to_coo`
+    window by window."""
+    ready = all(isinstance(i, np.ndarray) and i.dtype == np.uint16 and isinstance(j, np.ndarray) and j.dtype == np.uint16 and
+                isinstance(p, np.ndarray) and p.dtype == np.float64 and len(i) == len(j) == len(p) for i, j, p in lists)
+    if ready and lists:
+        counts = np.fromiter((len(t[0]) for t in lists), dtype=np.int64, count=len(lists))
+        if counts.sum() == 0:
+            return iter(lists)
+        i = np.concatenate([t[0] for t in lists]).astype(np.int32)
+        j = np.concatenate([t[1] for t in lists]).astype(np.int32)
+        p = np.concatenate([t[2] for t in lists])
+        wl = np.repeat(np.asarray(win_lens, dtype=np.int32), counts)
+        key = i * 65536 + j
+        rising = key[1:] > key[:-1]
+        starts = np.cumsum(counts)[:-1]
+        rising[starts[(starts > 0) & (starts < len(key))] - 1] = True       # the first entry of a window starts a new list
+        if (i < j).all() and (j < wl).all() and (p != 0.0).all() and rising.all():
+            return iter(lists)
+    return iter([to_coo(_Coo(i, j, p), n) for (i, j, p), n in zip(lists, win_lens)])
+
+
 class ScanEngine:
     """Models + E-value tables resident on one GPU; scans jobs given as arrays."""
 
@@ -136,13 +160,14 @@ class ScanEngine:
             lists = iter(provider.coo_many(todo, constraint) if todo else [])
         else:
             lists = None
+        if lists is not None:
+            lists = _checked_lists(list(lists), [len(w) for w in wins if len(w)])
         for win in wins:
             if len(win) == 0:
                 i = j = np.zeros(0, np.uint16)
                 p = np.zeros(0, np.float64)
             elif lists is not None:
                 i, j, p = next(lists)
-                i, j, p = to_coo(_Coo(i, j, p), len(win))
             elif hasattr(provider, "coo"):
                 i, j, p = provider.coo(win)
                 i, j, p = to_coo(_Coo(i, j, p), len(win))
