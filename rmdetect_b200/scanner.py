@@ -193,23 +193,32 @@ class ScanEngine:
     def scan_job(self, job):
         return self.ctx.scan(job)
 
+    HIT_FIELDS = ("model", "seq", "start", "p0", "p1", "leaf", "wlen", "score", "evalue")
+
+    @staticmethod
+    def hit_rows(hits):
+        """The fields `make_candidate` reads, as one list of Python tuples (a structured record per hit costs more than the
+        candidate it describes)."""
+        return list(zip(*(hits[f].tolist() for f in ScanEngine.HIT_FIELDS)))
+
     def make_candidate(self, hit, seqs, factory=Candidate):
-        """Candidate of one hit record (get_solution + set_data_build + update_chains_pos/cols)."""
-        m = int(hit["model"])
-        key, seq, cols = seqs[int(hit["seq"])]
-        start = int(hit["start"])
-        ptr = (int(hit["p0"]), int(hit["p1"]))
-        offs = self.flats[m].leaf_offsets[int(hit["leaf"])]
+        """Candidate of one hit record (get_solution + set_data_build + update_chains_pos/cols); `hit` is a record of the
+        result array or its tuple from `hit_rows`."""
+        if not isinstance(hit, tuple):
+            hit = (int(hit["model"]), int(hit["seq"]), int(hit["start"]), int(hit["p0"]), int(hit["p1"]), int(hit["leaf"]),
+                   int(hit["wlen"]), float(hit["score"]), float(hit["evalue"]))
+        m, si, start, p0, p1, leaf, wlen, score, evalue = hit
+        key, seq, cols = seqs[si]
+        offs = self.flats[m].leaf_offsets[leaf]
         chains_seqs, chains_pos = [], []
-        for c in range(2):
-            base = start + ptr[c]
-            chains_seqs.append(["." if o is None else seq[base + o] for o in offs[c]])
-            chains_pos.append([None if o is None else base + o for o in offs[c]])
-        cand = factory(self.models[m], key, (start, start + int(hit["wlen"])))
+        for base, chain in ((start + p0, offs[0]), (start + p1, offs[1])):
+            chains_seqs.append(["." if o is None else seq[base + o] for o in chain])
+            chains_pos.append([None if o is None else base + o for o in chain])
+        cand = factory(self.models[m], key, (start, start + wlen))
         cand.chains_seqs = chains_seqs
         cand.chains_pos = chains_pos
-        cand.score = float(hit["score"])
-        cand.evalue = float(hit["evalue"])
+        cand.score = score
+        cand.evalue = evalue
         cand.chains_cols = [[None if p is None else (p if cols is None else cols[p]) for p in ch]
                             for ch in chains_pos]
         return cand
@@ -321,11 +330,12 @@ class Scanner:
         hits = res["hits"]
         win_base = np.concatenate([[0], np.cumsum([len(s) for s in job["starts"]])]).astype(np.int64)
         bounds = np.searchsorted(hits["window"], np.arange(job["n_win"] + 1))
-        return dict(eng=eng, seqs=triples, job=job, res=res, win_base=win_base, bounds=bounds)
+        return dict(eng=eng, seqs=triples, job=job, res=res, win_base=win_base, bounds=bounds.tolist(), rows=eng.hit_rows(hits),
+                    keep=hits["keep"].tolist(), gate=res["gate_pass"].sum(axis=1).tolist() if job["n_win"] else [])
 
     def _replay_slide(self, run, si):
         """The window loop of `slide` (lib/scanner.py:80-111) for sequence `si` of a scanned job."""
-        eng, res, hits, bounds = run["eng"], run["res"], run["res"]["hits"], run["bounds"]
+        eng, bounds, rows, keep = run["eng"], run["bounds"], run["rows"], run["keep"]
         W, step = self.config.win_len, self.config.win_step
         seq = run["seqs"][si][1]
         w0 = int(run["win_base"][si])
@@ -333,12 +343,12 @@ class Scanner:
         for k, s in enumerate(run["job"]["starts"][si].tolist()):
             self.cback_before_window(len(seq), int(k * step))       # the value slide holds before re-anchoring
             wlen = len(seq[s:s + W])
-            for h in hits[bounds[w0 + k]:bounds[w0 + k + 1]]:
-                cand = eng.make_candidate(h, run["seqs"], self.candidate_factory)
-                cand._keep = bool(h["keep"])
+            for h in range(bounds[w0 + k], bounds[w0 + k + 1]):
+                cand = eng.make_candidate(rows[h], run["seqs"], self.candidate_factory)
+                cand._keep = bool(keep[h])
                 cands.append(cand)
             tries[0] += sum(placements_in_window(m, wlen) for m in self.config.models)
-            tries[1] += int(res["gate_pass"][w0 + k].sum())
+            tries[1] += int(run["gate"][w0 + k])
             self.cback_after_window(cands, tries)
         return cands, tries
 
