@@ -182,6 +182,18 @@ def test_calibration_loop_writes_the_reference_file(name, tmp_path):
     assert out.read_text() == g["text"]
 
 
+def test_a_million_samples_requested_stop_where_the_reference_stops(tmp_path):
+    """BASELINE configs[3] at its full size through the oracle (the GPU twin of this test is in test_gpu_round2.py): KT_1.0,
+    --samples 1000000, seeded stream; the reference's own run (tests/golden/make_calibrate_full.py, 98 s) converges after
+    370 000 simulations — the loop here stops there too and has written the same bytes."""
+    g = golden("calibrate_full")["KT_1.0"]
+    out = tmp_path / "kt_full.evalues"
+    _, _, done = cal.calibrate_model(load_model("KT_1.0"), str(out), samples=g["samples"], seed=g["seed"], log=None,
+                                     scorer=OracleScorer("KT_1.0"))
+    assert done == g["converged_after"] == 370000
+    assert out.read_text() == g["text"]
+
+
 def _rank_main(rank, world, port, name, samples, seed, device_samples, out_dir):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

@@ -269,6 +269,20 @@ def test_calibration_loop_on_the_gpu_writes_the_reference_file(tmp_path):
         assert out.read_text() == g["text"]
 
 
+def test_a_million_samples_write_the_reference_file(tmp_path):
+    """BASELINE configs[3] at its full size: KT_1.0, --samples 1000000, the reference's seeded sample stream, a table file at
+    every checkpoint, the stop rule — the `.evalues` text the reference's own run leaves behind (five minutes of one core
+    there: tests/golden/make_calibrate_full.py), byte for byte, and the same number of simulations."""
+    import hashlib
+    from rmdetect_b200.calibrate import calibrate_model
+    g = golden("calibrate_full")["KT_1.0"]
+    out = tmp_path / "kt_full.evalues"
+    _, _, done = calibrate_model(load_model("KT_1.0"), str(out), samples=g["samples"], seed=g["seed"], log=None)
+    text = out.read_text()
+    assert done == (g["converged_after"] if g["converged_after"] is not None else g["samples"])
+    assert hashlib.sha256(text.encode()).hexdigest() == g["sha256"] and text == g["text"]
+
+
 def test_compact_hit_records_carry_the_same_hits():
     """rmd_set_hit_format(1): 32-byte records on the way back; expand_hits rebuilds start / wlen from the geometry."""
     from rmdetect_b200._native import HIT32_DTYPE, expand_hits
