@@ -130,20 +130,45 @@ def diff_gc_evalues(gce1, gce2, scores):
     return diff / atotal
 
 
+class _Scores(list):
+    """A score grid as the list the reference builds, with what the dense functions derive from it again and again:
+    `idx[k]` = histogram bucket of row k, `at[score]` = row."""
+    __slots__ = ("idx", "at")
+
+
+_GRIDS = {}
+
+
+def _grid(first, last):
+    """The grid from bucket `first` to bucket `last` (rmcalibrate.py:65-83: repeated `+= 0.1` steps, each rounded for use as
+    a key — the float accumulation, and with it a possibly missing last row, is the reference's); cached: a calibration run
+    asks for the same few grids at every checkpoint."""
+    g = _GRIDS.get((first, last))
+    if g is None:
+        score, score_max, scores = round(first / 10.0, 1), round(last / 10.0, 1), []
+        while score <= score_max:
+            scores.append(round(score, 1))
+            score += 0.1
+        g = (tuple(scores), np.array([int(round(v * 10)) for v in scores], dtype=np.int64), {v: k for k, v in enumerate(scores)})
+        if len(_GRIDS) > 4096:
+            _GRIDS.clear()
+        _GRIDS[(first, last)] = g
+    out = _Scores(g[0])
+    out.idx, out.at = g[1], g[2]
+    return out
+
+
 def score_grid(hist, cols=None):
     """The score rows `get_gc_evalues` walks (rmcalibrate.py:65-83) for a dense [class][bucket] histogram: from the
-    smallest to the largest occupied bucket in repeated `+= 0.1` steps, each rounded for use as a key — the float
-    accumulation (and with it a possibly missing last row) is the reference's."""
+    smallest to the largest occupied bucket; `cols` = (first, last) occupied bucket when the caller knows them."""
     if cols is None:
         occupied = np.flatnonzero(hist.any(axis=0))
         cols = (int(occupied[0]), int(occupied[-1])) if len(occupied) else (-1, -1)
     if cols[1] < 0:
-        return []
-    score, score_max, scores = round(int(cols[0]) / 10.0, 1), round(int(cols[1]) / 10.0, 1), []
-    while score <= score_max:
-        scores.append(round(score, 1))
-        score += 0.1
-    return scores
+        out = _Scores()
+        out.idx, out.at = np.zeros(0, dtype=np.int64), {}
+        return out
+    return _grid(int(cols[0]), int(cols[1]))
 
 
 def gc_evalues_dense(hist, evalue_min, classes=None, cols=None):
@@ -153,7 +178,7 @@ def gc_evalues_dense(hist, evalue_min, classes=None, cols=None):
     sequential cumulative sum from the highest score down, floored at `evalue_min`; after the first row the floor
     never binds because every term is >= 0), so the values equal the dict version's bit for bit."""
     scores = score_grid(hist, cols)
-    idx = np.array([int(round(s * 10)) for s in scores], dtype=np.int64)
+    idx = scores.idx
     sub = hist if classes is None else hist[list(classes)]
     count = np.array([float(sum(row[np.flatnonzero(row)].tolist())) for row in sub])      # Python's own sum(), like :85
     p = sub[:, idx[::-1]] / count[:, None]
@@ -165,20 +190,24 @@ def gc_evalues_dense(hist, evalue_min, classes=None, cols=None):
 def diff_dense(tab1, scores1, tab2, scores2, gc=None):
     """`diff_gc_evalues` (rmcalibrate.py:134-157) for two dense tables: the middle class (row `gc` of the tables,
     default their middle row), rows of the NEWER grid `scores2`, a row pair skipped when the older table lacks one of
-    the scores."""
+    the scores.  The terms are formed row by row with the reference's operations (numpy, element by element) and summed
+    in its order (a running sum, `cumsum`), so the value is the loop's bit for bit."""
     gc = tab1.shape[0] // 2 if gc is None else gc
-    at1 = {s: k for k, s in enumerate(scores1)}
+    at1 = getattr(scores1, "at", None)
+    if at1 is None:
+        at1 = {s: k for k, s in enumerate(scores1)}
     diff = atotal = 0.0
-    for i in range(1, len(scores2)):
-        a, b = scores2[i - 1], scores2[i]
-        if a in at1 and b in at1:
-            ya1, yb1 = float(tab1[gc, at1[a]]), float(tab1[gc, at1[b]])
-            ya2, yb2 = float(tab2[gc, i - 1]), float(tab2[gc, i])
-            x = b - a
-            a1 = x * (yb1 + abs(yb1 - ya1) / 2.0)
-            a2 = x * (yb2 + abs(yb2 - ya2) / 2.0)
-            diff += abs(a1 - a2)
-            atotal += a1
+    if len(scores2) > 1:
+        k1 = np.array([at1.get(v, -1) for v in scores2], dtype=np.int64)
+        use = np.flatnonzero((k1[:-1] >= 0) & (k1[1:] >= 0))
+        if len(use):
+            s2 = np.asarray(scores2, dtype=np.float64)
+            r1, r2 = np.asarray(tab1[gc], dtype=np.float64), np.asarray(tab2[gc], dtype=np.float64)
+            x = s2[use + 1] - s2[use]
+            ya1, yb1, ya2, yb2 = r1[k1[use]], r1[k1[use + 1]], r2[use], r2[use + 1]
+            a1 = x * (yb1 + np.abs(yb1 - ya1) / 2.0)
+            a2 = x * (yb2 + np.abs(yb2 - ya2) / 2.0)
+            diff, atotal = float(np.cumsum(np.abs(a1 - a2))[-1]), float(np.cumsum(a1)[-1])
     return diff / atotal
 
 

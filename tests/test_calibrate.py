@@ -95,6 +95,47 @@ def test_table_text_row_by_row_equals_number_by_number():
     assert cal.table_text_dense(classes, tab, scores) == want and len(scores) == 171
 
 
+def _diff_loop(tab1, scores1, tab2, scores2, gc):
+    """rmcalibrate.py:134-157 row by row (what diff_dense has to equal bit for bit)."""
+    at1 = {s: k for k, s in enumerate(scores1)}
+    diff = atotal = 0.0
+    for i in range(1, len(scores2)):
+        a, b = scores2[i - 1], scores2[i]
+        if a in at1 and b in at1:
+            ya1, yb1 = float(tab1[gc, at1[a]]), float(tab1[gc, at1[b]])
+            ya2, yb2 = float(tab2[gc, i - 1]), float(tab2[gc, i])
+            x = b - a
+            a1 = x * (yb1 + abs(yb1 - ya1) / 2.0)
+            a2 = x * (yb2 + abs(yb2 - ya2) / 2.0)
+            diff += abs(a1 - a2)
+            atotal += a1
+    return diff / atotal
+
+
+def test_convergence_measure_in_bulk_equals_the_row_by_row_loop():
+    """diff_dense forms its terms with numpy and sums them with a running sum: the loop's value exactly, for grids that
+    start and end at different scores (rows the older table lacks are skipped), with cached and with plain score lists."""
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        n1, n2 = int(rng.integers(20, 200)), int(rng.integers(20, 200))
+        f1, f2 = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+        h1, h2 = np.zeros((3, cal.N_BINS)), np.zeros((3, cal.N_BINS))
+        h1[:, f1:f1 + n1] = rng.random((3, n1)) * 10.0 ** rng.integers(-8, 3, (3, n1))
+        h2[:, f2:f2 + n2] = rng.random((3, n2)) * 10.0 ** rng.integers(-8, 3, (3, n2))
+        t1, s1 = cal.gc_evalues_dense(h1, 4.0 ** -16)
+        t2, s2 = cal.gc_evalues_dense(h2, 4.0 ** -16)
+        assert s1 == cal.score_grid(h1) and list(s1.idx) == [int(round(v * 10)) for v in s1]
+        want = _diff_loop(t1, s1, t2, s2, 1)
+        assert cal.diff_dense(t1, s1, t2, s2) == want == cal.diff_dense(t1, list(s1), t2, list(s2), gc=1)
+    with pytest.raises(ZeroDivisionError):                        # no common row pair: the reference divides 0.0 by 0.0 too
+        h1, h2 = np.zeros((1, cal.N_BINS)), np.zeros((1, cal.N_BINS))
+        h1[0, 0:3] = 1.0
+        h2[0, 40:43] = 1.0
+        t1, s1 = cal.gc_evalues_dense(h1, 1e-9)
+        t2, s2 = cal.gc_evalues_dense(h2, 1e-9)
+        cal.diff_dense(t1, s1, t2, s2)
+
+
 class OracleScorer:
     """CPU stand-in for calibrate.Calibrator: the oracle's restatement of rmcalibrate.py:265-295."""
 
