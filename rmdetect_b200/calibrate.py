@@ -180,7 +180,9 @@ def gc_evalues_dense(hist, evalue_min, classes=None, cols=None):
     scores = score_grid(hist, cols)
     idx = scores.idx
     sub = hist if classes is None else hist[list(classes)]
-    count = np.array([float(sum(row[np.flatnonzero(row)].tolist())) for row in sub])      # Python's own sum(), like :85
+    # Python's own sum(), like :85 — not a numpy running sum: since Python 3.12 the built-in compensates its float sums
+    # (Neumaier), so only the built-in gives the number the reference's `sum(hist.values())` gives under the same interpreter
+    count = np.array([float(sum(row[np.flatnonzero(row)].tolist())) for row in sub])
     p = sub[:, idx[::-1]] / count[:, None]
     p[:, 0] = np.maximum(p[:, 0], evalue_min)
     tab = np.maximum(np.cumsum(p, axis=1), evalue_min)[:, ::-1]
