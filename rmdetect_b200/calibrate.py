@@ -60,17 +60,20 @@ def draw_samples(n, L, seed=None):
     start = {"bit_generator": "MT19937", "state": {"key": np.array(internal[:-1], dtype=np.uint32), "pos": int(internal[-1])}}
     mt = np.random.MT19937()
     mt.state = start
-    parts, have, used = [], 0, 0
+    parts, have = [], 0
     while have < need:
-        raw = mt.random_raw(max(1024, int(2.1 * (need - have)) + 64))
+        # half of the outputs are rejected: a first piece just short of what is needed, small pieces for the rest, so that
+        # little has to be drawn again to leave the generator exactly behind the last output used
+        before = mt.state
+        raw = mt.random_raw(int(1.9 * need) if have == 0 and need > 4096 else max(256, int(2.2 * (need - have)) + 32))
         v = (raw >> np.uint64(29)).astype(np.uint8)
         ok = np.flatnonzero(v < 4)
         take = min(len(ok), need - have)
         parts.append(v[ok[:take]])
         have += take
-        used += int(ok[take - 1]) + 1 if have == need else len(raw)
-    mt.state = start                                               # the state after exactly `used` outputs
-    mt.random_raw(used)
+        if have == need and int(ok[take - 1]) + 1 < len(raw):
+            mt.state = before
+            mt.random_raw(int(ok[take - 1]) + 1)
     end = mt.state["state"]
     random.setstate((version, tuple(int(x) for x in end["key"]) + (int(end["pos"]),), gauss))
     return np.concatenate(parts).reshape(n, L)
