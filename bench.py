@@ -419,7 +419,11 @@ def run_ours(args):
             issue_peak = sm_count * ISSUE_SLOTS_PER_SM_CYCLE * clocks["sm_max_mhz"] * 1e6
             issue_rate = ncu["warp_instructions"] / (ms_kernel * 1e-3)
             issue = {"achieved": issue_rate, "peak": issue_peak, "unit": "warp instructions/s", "frac": issue_rate / issue_peak,
-                     "source": "%s (smsp__inst_executed.sum)" % ncu["file"]}
+                     "source": "%s (smsp__inst_executed.sum)" % ncu["file"],
+                     # the pipe nearest its limit in that capture: integer / logic instructions take the ALU pipe two cycles each
+                     "alu_pipe_pct_of_peak": ncu["pct"].get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                     "fp64_pipe_pct_of_peak": ncu["pct"].get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                     "lsu_pipe_pct_of_peak": ncu["pct"].get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active")}
         if affinity is not None:
             os.sched_setaffinity(0, affinity)                    # the CPU baseline may use every core again
         cores = os.cpu_count() or 1
